@@ -1,0 +1,190 @@
+/*
+ * mar.h — C ABI of libmar.so, the sm_100a kernel library behind the drop-in sequence-classifier
+ * modules (multimodalaggressionrecognition_b200/models.py).
+ *
+ * The reference (cafe1930/MultimodalAggressionRecognition) has no native code and no FFI: every
+ * device op on its hot path is an implicit torch.nn library call made from models.py
+ * (SURVEY.md §2.2).  Each entry point below therefore cites the reference call site (file:line in
+ * /root/reference) and the torch op it stands in for; INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *    (PyTorch's caching allocator on the Python side) and must outlive the call in stream order.
+ *  - Every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns at
+ *    once; no hidden cudaDeviceSynchronize, safe under CUDA-graph capture.
+ *  - Return value: 0 = OK, negative = error (MAR_ERR_*); the message is in mar_last_error()
+ *    (thread-local).  Nothing throws across the ABI and nothing calls exit().
+ *  - dtype: MAR_F32 or MAR_BF16 is the storage type of ACTIVATIONS and WEIGHTS handed in; all
+ *    accumulation, statistics, losses and parameter gradients of reductions are fp32.
+ *  - Row-major everywhere.  A "linear" weight is (N,K) = (out_features, in_features) exactly as
+ *    nn.Linear stores it.
+ *  - Dropout masks are a pure function of (seed, step) held in a 2×uint64 DEVICE buffer
+ *    `rng_state`, a per-call `site` id and the element index, so backward regenerates the mask
+ *    instead of storing it and a captured CUDA graph draws fresh masks on every replay
+ *    (mar_rng_advance bumps `step` on the device).
+ */
+#ifndef MAR_H_
+#define MAR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAR_VERSION 100
+
+enum { MAR_F32 = 0, MAR_BF16 = 1 };
+
+enum {
+  MAR_OK = 0,
+  MAR_ERR_INVALID = -1,     /* bad shape / null pointer / misaligned pointer */
+  MAR_ERR_UNSUPPORTED = -2, /* configuration the kernels do not cover */
+  MAR_ERR_CUDA = -3,        /* CUDA runtime / driver error (message has the cudaError string) */
+  MAR_ERR_ARCH = -4         /* device is not compute capability 10.x */
+};
+
+/* GEMM engine selector.  AUTO picks tcgen05 for bf16 problems that meet its alignment rules and the
+ * SIMT kernel otherwise (all fp32 problems: fp32 mode must hold 1e-4, which rules out TF32). */
+enum { MAR_ENGINE_AUTO = 0, MAR_ENGINE_SIMT = 1, MAR_ENGINE_TCGEN05 = 2 };
+
+/* Epilogue flags of mar_linear_fwd:  out = residual + relu_post(dropout(relu_pre(x·Wᵀ + bias))) */
+enum {
+  MAR_EPI_RELU_PRE = 1,   /* ReLU before dropout  (FFN linear1, EmbeddingLayer, MLP heads)     */
+  MAR_EPI_DROPOUT = 2,    /* inverted dropout with probability p                               */
+  MAR_EPI_RELU_POST = 4   /* ReLU after dropout   (adaptors: Linear→Dropout→ReLU, models.py:743-748) */
+};
+
+int mar_version(void);
+const char* mar_last_error(void);
+/* sm_count / cc_major / cc_minor of the current device. */
+int mar_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of kernels this library launched in this process since load / since the last reset
+ * (bench.py's `gpu_launches`). */
+int64_t mar_launch_count(void);
+void mar_launch_count_reset(void);
+/* Which engine the most recent mar_linear_* call on this thread used (MAR_ENGINE_*). */
+int mar_last_engine(void);
+
+/* ---- RNG state (dropout) -------------------------------------------------------------------- */
+int mar_rng_init(uint64_t* rng_state, uint64_t seed, uint64_t step, void* stream);
+int mar_rng_advance(uint64_t* rng_state, void* stream);
+
+/* ---- Dense contractions --------------------------------------------------------------------- */
+/* nn.Linear forward with fused epilogue.  Replaces F.linear at models.py:143 (EmbeddingLayer),
+ * :383-386, :115-118 (MLP heads), :693/:744 (adaptors), :711-714 (aggression heads) and the
+ * in_proj / out_proj / linear1 / linear2 GEMMs of nn.TransformerEncoderLayer built at
+ * models.py:348, :398 (torch/nn/functional.py:5798, :6690; transformer.py:980-982).
+ * x (M,K) row stride ldx; w (N,K) contiguous; bias (N) fp32 or NULL; residual (M,N) row stride
+ * ldr or NULL; out (M,N) row stride ldo.  in_dtype is the type of x and w (and residual);
+ * out_dtype the type of out. */
+int mar_linear_fwd(const void* x, int64_t ldx, const void* w, const float* bias,
+                   const void* residual, int64_t ldr, void* out, int64_t ldo,
+                   int64_t M, int64_t N, int64_t K, int in_dtype, int out_dtype,
+                   int flags, float p_drop, const uint64_t* rng_state, uint32_t site,
+                   int engine, void* stream);
+
+/* Backward through the epilogue: dz = dout ⊙ d(epilogue)/dz, and dbias += column-sum(dz) (fp32,
+ * accumulated; pass NULL to skip).  `out` is the forward output (needed for the ReLU flags, may be
+ * NULL otherwise).  dz may alias dout.  All of (M,N), contiguous. */
+int mar_linear_bwd_epilogue(const void* dout, const void* out, void* dz, float* dbias,
+                            int64_t M, int64_t N, int dtype, int out_dtype, int flags, float p_drop,
+                            const uint64_t* rng_state, uint32_t site, void* stream);
+
+/* dx = dz·W (+ add).  dz (M,N); w (N,K); wt (K,N) = Wᵀ in the same dtype, required by the tcgen05
+ * engine (K-major B operand), may be NULL for SIMT; add (M,K) or NULL; dx (M,K) row stride lddx. */
+int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* add, void* dx,
+                     int64_t lddx, int64_t M, int64_t N, int64_t K, int dtype, int engine, void* stream);
+
+/* dw (N,K) fp32 (+)= dzᵀ·x.  dz (M,N) contiguous, x (M,K) row stride ldx.  accumulate=0 overwrites. */
+int mar_linear_wgrad(const void* dz, const void* x, int64_t ldx, float* dw, int64_t M, int64_t N,
+                     int64_t K, int dtype, int accumulate, int engine, void* stream);
+
+/* fp32 master weight (N,K) → compute-dtype copy w (N,K) and, if wt != NULL, its transpose (K,N). */
+int mar_cast_weight(const float* src, void* w, void* wt, int64_t N, int64_t K, int dtype, void* stream);
+/* elementwise cast between fp32 and bf16 buffers of n elements */
+int mar_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+/* ---- Attention ------------------------------------------------------------------------------ */
+/* softmax(QKᵀ/√dh + key mask)·V over the packed in-projection output qkv (B,T,3d) (rows of each
+ * token: [Q(d) | K(d) | V(d)], head h at columns h*dh..).  Replaces F.scaled_dot_product_attention
+ * (torch/nn/functional.py:6682) reached from models.py:365 (no mask) and :425 (key padding mask
+ * from the zero-row rule).  key_mask (B,T) uint8, 1 = key ignored, or NULL.  out (B,T,d).
+ * lse (B,H,T) fp32 log-sum-exp of the scaled scores (-inf for a fully masked row, whose output
+ * row is 0 — torch 2.11 safe-softmax behaviour).  Dropout on P with p_drop when > 0. */
+int mar_attention_fwd(const void* qkv, const uint8_t* key_mask, void* out, float* lse,
+                      int64_t B, int64_t T, int64_t H, int64_t dh, int dtype, float p_drop,
+                      const uint64_t* rng_state, uint32_t site, int engine, void* stream);
+/* dqkv (B,T,3d) from dout (B,T,d).  delta (B,H,T) fp32 is workspace. */
+int mar_attention_bwd(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout,
+                      const float* lse, float* delta, void* dqkv, int64_t B, int64_t T, int64_t H,
+                      int64_t dh, int dtype, float p_drop, const uint64_t* rng_state, uint32_t site,
+                      int engine, void* stream);
+
+/* ---- LayerNorm ------------------------------------------------------------------------------ */
+/* y = LN(x)·gamma + beta over the last dim D, eps inside the sqrt, biased variance
+ * (nn.LayerNorm at models.py:352, :403; norm1/norm2 at transformer.py:953-956).  The residual add
+ * is fused into the producing GEMM's epilogue.  mean/rstd (rows) fp32 are saved for backward
+ * (may be NULL in inference).  If zero_rows != NULL (rows, uint8) rows flagged 1 are treated as
+ * x = 0 (the eval-mode nested-tensor zero fill, transformer.py:547-548). */
+int mar_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                      float* rstd, const uint8_t* zero_rows, int64_t rows, int64_t D, float eps,
+                      int dtype, void* stream);
+/* dx, and dgamma/dbeta (fp32, ACCUMULATED into). */
+int mar_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                      const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t rows,
+                      int64_t D, int dtype, void* stream);
+
+/* ---- Pooling / masks ------------------------------------------------------------------------ */
+/* out (B,D) = mean over T of x (B,T,D) (SequenceAverageFeatures, models.py:105; :97). */
+int mar_meanpool_fwd(const void* x, void* out, int64_t B, int64_t T, int64_t D, int dtype, void* stream);
+int mar_meanpool_bwd(const void* dout, void* dx, int64_t B, int64_t T, int64_t D, int dtype, void* stream);
+/* mask (rows) uint8 = (sum over D of x == 0) (models.py:421-422). */
+int mar_rowzero_mask(const void* x, uint8_t* mask, int64_t rows, int64_t D, int dtype, void* stream);
+/* Copy a (B,T,D) block into columns [t_off, t_off+T) of a (B,T_total,D) buffer and back
+ * (torch.cat along T at models.py:419 and the slices at :430). */
+int mar_concat_rows(const void* src, void* dst, int64_t B, int64_t T, int64_t T_total, int64_t t_off,
+                    int64_t D, int dtype, int to_concat, void* stream);
+
+/* ---- Classifier loss ------------------------------------------------------------------------ */
+/* nn.CrossEntropyLoss (mean, optional class weights) on fp32 logits (B,C), int64 labels; rows
+ * with label < 0 are ignored (EMPTY samples, models.py:247-253).  loss: 1 float.  dlogits (B,C)
+ * = d loss / d logits (the caller scales by the upstream grad).  preds (B) int64 argmax or NULL
+ * (trainer.py:170, :726). */
+int mar_cross_entropy_fwd(const float* logits, const int64_t* labels, const float* class_weight,
+                          float* loss, float* dlogits, int64_t* preds, int64_t B, int64_t C, void* stream);
+
+/* ---- GRU / LSTM recurrence ------------------------------------------------------------------ */
+/* One-layer batch_first GRU, h0 = 0 (nn.GRU at models.py:110,122; gate order r,z,n).
+ * gi (B,T,3H) = x·W_ihᵀ + b_ih is produced by mar_linear_fwd.  w_hh (3H,H) in `dtype`, b_hh fp32.
+ * hseq (B,T,H) output sequence in `dtype`; saved (B,T,4H) in `dtype`: r, z, n and (W_hn h + b_hn)
+ * for backward (NULL in inference). */
+int mar_gru_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved,
+                float* work, int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream);
+/* dhseq (B,T,H) incoming grad for every step (zeros except the last for the reference heads).
+ * Produces dgi (B,T,3H) and dgh (B,T,3H) in `dtype` (dW_ih, dW_hh, biases and dx then follow from
+ * mar_linear_wgrad / mar_linear_dgrad / mar_linear_bwd_epilogue on those).  wt_hh = W_hhᵀ (H,3H)
+ * for the tcgen05 engine or NULL.  work: fp32 workspace of 2*B*H floats. */
+int mar_gru_bwd(const void* dhseq, const void* hseq, const void* saved, const void* w_hh, void* dgi,
+                void* dgh, float* work, int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream);
+int64_t mar_gru_work_floats(int64_t B, int64_t T, int64_t H);
+
+/* LSTM (train_video_rnn.py:94-106; gate order i,f,g,o).  saved (B,T,5H): i,f,g,o,c. */
+int mar_lstm_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved,
+                 float* work, int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream);
+int mar_lstm_bwd(const void* dhseq, const void* saved, const void* w_hh, void* dgates, float* work,
+                 int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream);
+
+/* ---- Optimizer ------------------------------------------------------------------------------ */
+/* torch.optim.Adam defaults (train_multimodal.py:444) over one flat fp32 buffer of n elements;
+ * `step_dev` (1 float on the device, incremented by the kernel's caller via mar_adam_tick) keeps
+ * the bias-correction step so the update is graph-capturable. */
+int mar_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* step_dev,
+                  int64_t n, float lr, float beta1, float beta2, float eps, void* stream);
+int mar_adam_tick(float* step_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAR_H_ */

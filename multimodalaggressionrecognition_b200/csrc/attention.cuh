@@ -1,0 +1,17 @@
+#pragma once
+#include "common.cuh"
+
+// SIMT fp32-math engine (attention_simt.cu)
+int attention_fwd_simt(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
+                       int64_t dh, int dtype, float p, const uint64_t* rng, uint32_t site, cudaStream_t st);
+int attention_bwd_simt(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
+                       float* delta, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, int dtype, float p,
+                       const uint64_t* rng, uint32_t site, cudaStream_t st);
+
+// bf16 tensor-core engine (attention_mma.cu); returns MAR_ERR_UNSUPPORTED for shapes it does not take
+bool attention_mma_supported(int64_t T, int64_t dh, int dtype);
+int attention_fwd_mma(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
+                      int64_t dh, float p, const uint64_t* rng, uint32_t site, cudaStream_t st);
+int attention_bwd_mma(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
+                      float* delta, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, float p,
+                      const uint64_t* rng, uint32_t site, cudaStream_t st);

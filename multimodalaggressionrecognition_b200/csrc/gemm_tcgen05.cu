@@ -1,0 +1,393 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA (128 B swizzle) -> smem ring ->
+// tcgen05.mma (cta_group::1, 128 x BN x 16) with fp32 accumulators in TMEM (double buffered) ->
+// tcgen05.ld epilogue with the fused linear epilogue (bias / ReLU / dropout / residual) or fp32
+// split-K reduction (wgrad).
+//
+//   D[M,N] = epilogue( A · B ),  reduction length Kr
+//   A: K-major  = row-major (M, Kr)         or MN-major = row-major (Kr, M)
+//   B: K-major  = row-major (N, Kr)         or MN-major = row-major (Kr, N)
+//
+//   forward  y  = x·Wᵀ   : A = x (M,K) K-major,        B = W (N,K) K-major
+//   dgrad    dx = dz·W   : A = dz (M,N) K-major,       B = Wᵀ (K,N) K-major (bf16 transposed copy)
+//   wgrad    dW = dzᵀ·x  : A = dz (rows,N) MN-major,   B = x (rows,K) MN-major, fp32 out, split-K
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue (warp w reads TMEM lanes 32*(w%4)..+31; one accumulator row per thread).
+// Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2·M·N·Kr.
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "gemm_tcgen05.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;            // 64 bf16 = 128 B = one swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int ATOM_BYTES = BLOCK_K * 128;              // one MN-major box: 64 k-rows x 128 B = 8 KB
+constexpr int NUM_THREADS = 256;
+
+template <int BN> struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;   // 512 or 256: power of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+  int M, N, Kr;
+  int splits, kb_per_split;
+  void* out;
+  int64_t ldo;
+  const float* bias;
+  const void* residual;   // bf16, row stride ldr
+  int64_t ldr;
+  int flags;
+  float p_drop;
+  const uint64_t* rng;
+  uint32_t site;
+  int atomic_out;         // fp32 out via red.add (split-K)
+  int accumulate;         // fp32 out += (no split)
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN, typename OutT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_work = num_tiles * p.splits;
+  const int kb_total = (p.Kr + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tma_a);
+    prefetch_tensormap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = w % num_tiles, split = w / num_tiles;
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; kb++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; i++)
+              tma_load_2d(sa + i * ATOM_BYTES, &tma_a, &full_bar[stage], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; i++)
+              tma_load_2d(sb + i * ATOM_BYTES, &tma_b, &full_bar[stage], n_blk * BN + i * 64, kb * BLOCK_K);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, it++) {
+        const int split = w / num_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; kb++) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * C::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+            const uint64_t adesc = A_MN ? make_desc_mnmajor(sa, k, ATOM_BYTES) : make_desc_kmajor(sa, k);
+            const uint64_t bdesc = B_MN ? make_desc_mnmajor(sb, k, ATOM_BYTES) : make_desc_kmajor(sb, k);
+            umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;   // TMEM lane quarter
+    const bool do_drop = (p.flags & MAR_EPI_DROPOUT) && p.p_drop > 0.f;
+    DropKey dk;
+    if (do_drop) dk = make_drop_key(p.rng, p.site, p.p_drop);
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, it++) {
+      const int tile = w % num_tiles, split = w / num_tiles;
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool first_split = split == 0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;   // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr && first_split) {
+#pragma unroll
+          for (int g = 0; g < 8; g++) {
+            if (col0 + g * 4 < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 4));
+              v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
+            }
+          }
+        }
+        if (p.flags & MAR_EPI_RELU_PRE) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (do_drop) {
+          const uint64_t e0 = (uint64_t)row * (uint64_t)p.N + (uint64_t)col0;
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            bool k0, k1;
+            drop_keep2(dk, (e0 >> 1) + j, k0, k1);
+            v[2 * j] = k0 ? v[2 * j] * dk.scale : 0.f;
+            v[2 * j + 1] = k1 ? v[2 * j + 1] * dk.scale : 0.f;
+          }
+        }
+        if (p.flags & MAR_EPI_RELU_POST) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (!row_ok) continue;
+        if (p.residual != nullptr) {
+          const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + (int64_t)row * p.ldr + col0;
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            if (col0 + g * 8 < p.N) {
+              float t8[8];
+              Vec8<bf16>::load(rp + g * 8, t8);
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[g * 8 + j] += t8[j];
+            }
+          }
+        }
+        if (sizeof(OutT) == 2) {
+          bf16* op = reinterpret_cast<bf16*>(p.out) + (int64_t)row * p.ldo + col0;
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            if (col0 + g * 8 < p.N) {
+              uint4 u;
+              u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+              u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+              u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+              u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(op + g * 8) = u;
+            }
+          }
+        } else {
+          float* op = reinterpret_cast<float*>(p.out) + (int64_t)row * p.ldo + col0;
+#pragma unroll
+          for (int g = 0; g < 8; g++) {
+            if (col0 + g * 4 < p.N) {
+              if (p.atomic_out) {
+                red_add_v4(op + g * 4, v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              } else {
+                float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                if (p.accumulate) {
+                  const float4 old = *reinterpret_cast<const float4*>(op + g * 4);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(op + g * 4) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major (rows, cols) matrix with leading dimension ld (elements);
+// box = (box_cols = 64 elements = 128 B, box_rows), 128 B swizzle, zero fill out of bounds.
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) { mar_set_error("cuTensorMapEncodeTiled not available from the driver"); return MAR_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mar_set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld base=%p", (int)r, (long long)rows,
+                  (long long)cols, (long long)ld, base);
+    return MAR_ERR_CUDA;
+  }
+  return MAR_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, typename OutT>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, OutT>;
+  static bool configured = false;
+  if (!configured) {
+    MAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (p.N + BN - 1) / BN;
+  const int64_t work = (int64_t)m_blocks * n_blocks * p.splits;
+  const int grid = (int)(work < mar_sm_count() ? work : mar_sm_count());
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+  MAR_LAUNCH_CHECK("gemm_tcgen05");
+  return MAR_OK;
+}
+
+}  // namespace
+
+bool gemm_tcgen05_supported(const TcGemmArgs& a) {
+  if (a.M < 1 || a.N < 8 || a.Kr < 8) return false;
+  if (a.N % 8 != 0) return false;
+  // TMA: 16 B aligned bases and row pitches
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) % 16) == 0; };
+  if (!al16(a.A) || !al16(a.B) || !al16(a.out)) return false;
+  if ((a.lda * 2) % 16 != 0 || (a.ldb * 2) % 16 != 0) return false;
+  if (a.residual != nullptr && (!al16(a.residual) || (a.ldr * 2) % 16 != 0)) return false;
+  const int64_t osz = a.out_fp32 ? 4 : 2;
+  if ((a.ldo * osz) % 16 != 0) return false;
+  if (a.a_mn_major != a.b_mn_major) return false;   // TN (fwd/dgrad) and NT-on-rows (wgrad) only
+  if (a.a_mn_major && !a.out_fp32) return false;
+  if (a.M >= (1ll << 31) || a.N >= (1ll << 31) || a.Kr >= (1ll << 31)) return false;
+  return true;
+}
+
+int gemm_tcgen05(const TcGemmArgs& a, cudaStream_t st) {
+  if (!gemm_tcgen05_supported(a)) MAR_UNSUPPORTED("gemm_tcgen05: unsupported problem M=%lld N=%lld K=%lld", (long long)a.M, (long long)a.N, (long long)a.Kr);
+  mar_set_engine(MAR_ENGINE_TCGEN05);
+  TcParams p;
+  p.M = (int)a.M; p.N = (int)a.N; p.Kr = (int)a.Kr;
+  p.out = a.out; p.ldo = a.ldo; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr;
+  p.flags = a.flags; p.p_drop = a.p_drop; p.rng = a.rng; p.site = a.site;
+  p.atomic_out = 0; p.accumulate = a.accumulate;
+  const int BN = (a.N > 128) ? 256 : 128;
+  const int kb_total = (int)ceil_div(a.Kr, BLOCK_K);
+  p.splits = 1; p.kb_per_split = kb_total;
+  if (a.allow_split && a.out_fp32 && a.flags == 0 && a.residual == nullptr) {
+    const int64_t tiles = ceil_div(a.M, BLOCK_M) * ceil_div(a.N, BN);
+    int64_t want = ceil_div((int64_t)mar_sm_count(), tiles);
+    int64_t max_split = kb_total / 8 > 0 ? kb_total / 8 : 1;   // at least 8 k-blocks (512 rows) per split
+    int64_t splits = want < max_split ? want : max_split;
+    if (splits > 1) {
+      p.kb_per_split = (int)ceil_div(kb_total, splits);
+      p.splits = (int)ceil_div(kb_total, p.kb_per_split);
+      p.atomic_out = 1;
+      if (!a.accumulate) {
+        if (a.ldo == a.N) MAR_CUDA(cudaMemsetAsync(a.out, 0, (size_t)a.M * a.N * 4, st));
+        else MAR_CUDA(cudaMemset2DAsync(a.out, (size_t)a.ldo * 4, 0, (size_t)a.N * 4, (size_t)a.M, st));
+      }
+    }
+  }
+  CUtensorMap ma, mb;
+  int rc;
+  if (!a.a_mn_major) {
+    rc = make_map(&ma, a.A, a.M, a.Kr, a.lda, BLOCK_M); if (rc) return rc;
+    rc = make_map(&mb, a.B, a.N, a.Kr, a.ldb, BN); if (rc) return rc;
+  } else {
+    rc = make_map(&ma, a.A, a.Kr, a.M, a.lda, BLOCK_K); if (rc) return rc;
+    rc = make_map(&mb, a.B, a.Kr, a.N, a.ldb, BLOCK_K); if (rc) return rc;
+  }
+  if (!a.a_mn_major) {
+    if (a.out_fp32) return BN == 256 ? launch<256, false, false, float>(ma, mb, p, st) : launch<128, false, false, float>(ma, mb, p, st);
+    return BN == 256 ? launch<256, false, false, bf16>(ma, mb, p, st) : launch<128, false, false, bf16>(ma, mb, p, st);
+  }
+  return BN == 256 ? launch<256, true, true, float>(ma, mb, p, st) : launch<128, true, true, float>(ma, mb, p, st);
+}

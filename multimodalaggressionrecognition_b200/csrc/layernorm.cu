@@ -1,0 +1,229 @@
+// LayerNorm forward / backward over the last dimension (HBM-bound).
+// One warp per row; a lane owns NCH chunks of 8 consecutive elements (16 B bf16 / 32 B fp32 loads,
+// a warp covers 256 contiguous elements per chunk round => fully coalesced).  Statistics in fp32.
+// Algorithmic bytes: fwd = rows*D*(read+write)*sizeof(T); bwd = rows*D*(2 reads + 1 write)*sizeof(T).
+#include "common.cuh"
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd,
+                     const uint8_t* __restrict__ zero_rows, int64_t rows, int D, float eps) {
+  const int lane = threadIdx.x % 32;
+  const int warps_per_block = blockDim.x / 32;
+  const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + threadIdx.x / 32;
+  const int64_t warp_stride = (int64_t)gridDim.x * warps_per_block;
+  const float invD = 1.f / (float)D;
+
+  for (int64_t row = warp_global; row < rows; row += warp_stride) {
+    float v[NCH][8];
+    const bool zero = zero_rows != nullptr && zero_rows[row] != 0;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      int col = (c * 32 + lane) * 8;
+      if (col < D && !zero) Vec8<T>::load(x + row * D + col, v[c]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[c][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) s += v[c][j];
+    }
+    const float mu = warp_sum(s) * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      int col = (c * 32 + lane) * 8;
+      if (col < D) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { float d = v[c][j] - mu; q += d * d; }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) * invD + eps);
+    if (lane == 0 && mean != nullptr) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      int col = (c * 32 + lane) * 8;
+      if (col < D) {
+        float g[8], b[8], o[8];
+        Vec8<float>::load(gamma + col, g);
+        Vec8<float>::load(beta + col, b);
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = (v[c][j] - mu) * rs * g[j] + b[j];
+        Vec8<T>::store(y + row * D + col, o);
+      }
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma ; dgamma += Σ dy*xhat ; dbeta += Σ dy
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int D) {
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  const int warps_per_block = blockDim.x / 32;
+  const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + warp;
+  const int64_t warp_stride = (int64_t)gridDim.x * warps_per_block;
+  const float invD = 1.f / (float)D;
+
+  float gam[NCH][8], dg[NCH][8], db[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) Vec8<float>::load(gamma + col, gam[c]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { dg[c][j] = 0.f; db[c][j] = 0.f; if (col >= D) gam[c][j] = 0.f; }
+  }
+
+  for (int64_t row = warp_global; row < rows; row += warp_stride) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[NCH][8], xh[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      int col = (c * 32 + lane) * 8;
+      if (col < D) {
+        float a[8], b[8];
+        Vec8<T>::load(dy + row * D + col, a);
+        Vec8<T>::load(x + row * D + col, b);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          xh[c][j] = (b[j] - mu) * rs;
+          dg[c][j] += a[j] * xh[c][j];
+          db[c][j] += a[j];
+          g[c][j] = a[j] * gam[c][j];
+          s1 += g[c][j];
+          s2 += g[c][j] * xh[c][j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { g[c][j] = 0.f; xh[c][j] = 0.f; }
+      }
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      int col = (c * 32 + lane) * 8;
+      if (col < D) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
+        Vec8<T>::store(dx + row * D + col, o);
+      }
+    }
+  }
+
+  // block reduction of the column partials: 8 warps -> 1, then one atomicAdd per column per block
+  extern __shared__ float red[];  // [warps][D] reused for dgamma then dbeta
+  for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      int col = (c * 32 + lane) * 8;
+      if (col < D) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) red[warp * D + col + j] = pass == 0 ? dg[c][j] : db[c][j];
+      }
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < warps_per_block; w++) s += red[w * D + col];
+      atomicAdd((pass == 0 ? dgamma : dbeta) + col, s);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+int launch_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+               const uint8_t* zero_rows, int64_t rows, int64_t D, float eps, cudaStream_t st) {
+  const int nch = (int)ceil_div(D, 256);
+  int64_t blocks = ceil_div(rows, 8);
+  int64_t cap = (int64_t)mar_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+#define LN_FWD(N)                                                                                             \
+  layernorm_fwd_kernel<T, N><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd,   \
+                                                               zero_rows, rows, (int)D, eps)
+  switch (nch) {
+    case 1: LN_FWD(1); break;
+    case 2: LN_FWD(2); break;
+    case 3: LN_FWD(3); break;
+    case 4: LN_FWD(4); break;
+    case 5: LN_FWD(5); break;
+    case 6: LN_FWD(6); break;
+    case 7: LN_FWD(7); break;
+    case 8: LN_FWD(8); break;
+    default: MAR_UNSUPPORTED("layernorm: D=%lld > 2048 not supported", (long long)D);
+  }
+#undef LN_FWD
+  MAR_LAUNCH_CHECK("layernorm_fwd");
+  return MAR_OK;
+}
+
+template <typename T>
+int launch_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+               float* dgamma, float* dbeta, int64_t rows, int64_t D, cudaStream_t st) {
+  const int nch = (int)ceil_div(D, 256);
+  int64_t blocks = ceil_div(rows, 8 * 4);
+  int64_t cap = (int64_t)mar_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  size_t smem = (size_t)8 * D * sizeof(float);
+#define LN_BWD(N)                                                                                                 \
+  do {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                         \
+      cudaFuncSetAttribute(layernorm_bwd_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    layernorm_bwd_kernel<T, N><<<(unsigned)blocks, 256, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, \
+                                                                    (T*)dx, dgamma, dbeta, rows, (int)D);         \
+  } while (0)
+  switch (nch) {
+    case 1: LN_BWD(1); break;
+    case 2: LN_BWD(2); break;
+    case 3: LN_BWD(3); break;
+    case 4: LN_BWD(4); break;
+    case 5: LN_BWD(5); break;
+    case 6: LN_BWD(6); break;
+    case 7: LN_BWD(7); break;
+    case 8: LN_BWD(8); break;
+    default: MAR_UNSUPPORTED("layernorm: D=%lld > 2048 not supported", (long long)D);
+  }
+#undef LN_BWD
+  MAR_LAUNCH_CHECK("layernorm_bwd");
+  return MAR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mar_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                      const uint8_t* zero_rows, int64_t rows, int64_t D, float eps, int dtype, void* stream) {
+  MAR_CHECK_ARG(x && gamma && beta && y && rows >= 0 && D > 0, "mar_layernorm_fwd: bad arguments");
+  MAR_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "mar_layernorm_fwd: mean and rstd go together");
+  MAR_CHECK_ARG(D % 8 == 0, "mar_layernorm_fwd: D must be a multiple of 8 (got %lld)", (long long)D);
+  if (rows == 0) return MAR_OK;
+  if (dtype == MAR_BF16) return launch_fwd<bf16>(x, gamma, beta, y, mean, rstd, zero_rows, rows, D, eps, S(stream));
+  if (dtype == MAR_F32) return launch_fwd<float>(x, gamma, beta, y, mean, rstd, zero_rows, rows, D, eps, S(stream));
+  MAR_UNSUPPORTED("mar_layernorm_fwd: dtype %d", dtype);
+}
+
+int mar_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                      void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t D, int dtype, void* stream) {
+  MAR_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && rows >= 0 && D > 0,
+                "mar_layernorm_bwd: bad arguments");
+  MAR_CHECK_ARG(D % 8 == 0, "mar_layernorm_bwd: D must be a multiple of 8 (got %lld)", (long long)D);
+  if (rows == 0) return MAR_OK;
+  if (dtype == MAR_BF16) return launch_bwd<bf16>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, S(stream));
+  if (dtype == MAR_F32) return launch_bwd<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, S(stream));
+  MAR_UNSUPPORTED("mar_layernorm_bwd: dtype %d", dtype);
+}
+
+}  // extern "C"

@@ -1,0 +1,647 @@
+"""autograd.Function wrappers over the libmar.so C ABI.
+
+Every Function launches hand-written sm_100a kernels on torch's current CUDA stream; tensors
+(inputs, outputs, saved-for-backward, workspaces) are allocated by PyTorch's caching allocator, so
+the whole step is CUDA-graph capturable.  No op has a PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import contextlib
+import threading
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_DROPOUT, EPI_RELU_POST, EPI_RELU_PRE, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, MAR_BF16,
+                   MAR_F32, call)
+
+# --------------------------------------------------------------------------------------
+# precision mode
+# --------------------------------------------------------------------------------------
+_state = threading.local()
+
+
+def _cfg():
+    if not hasattr(_state, "dtype"):
+        _state.dtype = torch.bfloat16
+        _state.engine = ENGINE_AUTO
+        _state.probe = False
+    return _state
+
+
+def set_precision(mode) -> None:
+    """'bf16' (default: bf16 storage + tensor cores, fp32 accumulate) or 'fp32' (SIMT fp32, 1e-4 parity)."""
+    d = {"bf16": torch.bfloat16, "fp32": torch.float32, torch.bfloat16: torch.bfloat16,
+         torch.float32: torch.float32}.get(mode)
+    if d is None:
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {mode!r}")
+    _cfg().dtype = d
+
+
+def get_precision() -> torch.dtype:
+    return _cfg().dtype
+
+
+@contextlib.contextmanager
+def precision(mode):
+    old = _cfg().dtype
+    set_precision(mode)
+    try:
+        yield
+    finally:
+        _cfg().dtype = old
+
+
+@contextlib.contextmanager
+def engine(which: str):
+    """Force a kernel engine: 'auto', 'simt' (fp32-math SIMT kernels) or 'tensor' (tcgen05 GEMM, tensor-core
+    attention, persistent GRU; raises if a call cannot run there).  Used by tests and benchmarks."""
+    e = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tensor": ENGINE_TCGEN05}[which]
+    old = _cfg().engine
+    _cfg().engine = e
+    try:
+        yield
+    finally:
+        _cfg().engine = old
+
+
+@contextlib.contextmanager
+def shape_probe():
+    """Inside this context the drop-in modules return zero tensors of the right shape without launching
+    anything, for the reference's CPU shape probing (train_multimodal.py:346-353)."""
+    old = _cfg().probe
+    _cfg().probe = True
+    try:
+        yield
+    finally:
+        _cfg().probe = old
+
+
+def probing() -> bool:
+    return _cfg().probe
+
+
+def _eng() -> int:
+    return _cfg().engine
+
+
+def last_engine() -> str:
+    return {0: "none", 1: "simt", 2: "tensor"}[_lib.load().mar_last_engine()]
+
+
+def launch_count() -> int:
+    return int(_lib.load().mar_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().mar_launch_count_reset()
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return MAR_F32
+    if t.dtype == torch.bfloat16:
+        return MAR_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what}: got a {t.device} tensor. multimodalaggressionrecognition_b200 runs only on sm_100a CUDA "
+            "devices; there is no CPU path (use shape_probe() for the reference's CPU shape probing).")
+    _lib.check_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """2-D view with unit column stride (copy only if needed)."""
+    if t.dim() != 2:
+        t = t.reshape(-1, t.shape[-1])
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+class _Rng:
+    """Device-side (seed, step) + host-side site counter.  See include/mar.h on the mask function."""
+
+    def __init__(self):
+        self.states = {}
+        self.site = 0
+        self.seed = None
+
+    def state(self, device: torch.device) -> torch.Tensor:
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        st = self.states.get(key)
+        if st is None:
+            with torch.cuda.device(key):
+                st = torch.zeros(2, dtype=torch.int64, device=f"cuda:{key}")
+                seed = self.seed if self.seed is not None else torch.initial_seed()
+                call("mar_rng_init", st.data_ptr(), seed & 0xFFFFFFFFFFFFFFFF, 0, _stream())
+            self.states[key] = st
+        return st
+
+    def next_site(self) -> int:
+        self.site = (self.site + 1) & 0x7FFFFFFF
+        return self.site
+
+
+_rng = _Rng()
+
+
+def manual_seed(seed: int) -> None:
+    """Seed of the dropout mask function (defaults to torch.initial_seed())."""
+    _rng.seed = int(seed)
+    _rng.site = 0
+    for key, st in _rng.states.items():
+        with torch.cuda.device(key):
+            call("mar_rng_init", st.data_ptr(), seed & 0xFFFFFFFFFFFFFFFF, 0, _stream())
+
+
+def rng_advance(device=None) -> None:
+    """Bump the device-side step (captured into CUDA graphs so every replay draws fresh masks)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    st = _rng.state(dev)
+    call("mar_rng_advance", st.data_ptr(), _stream())
+
+
+# ---- compute-dtype copies of the fp32 master weights ---------------------------------------
+_wcache = {}
+
+
+def clear_weight_cache() -> None:
+    _wcache.clear()
+
+
+def compute_weight(w: torch.Tensor, dtype: torch.dtype, need_t: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """(W, Wᵀ) in the compute dtype.  fp32 mode uses the parameter itself.  bf16 copies are cached per
+    parameter version (optimizer steps bump it), so eval loops cast once."""
+    if dtype == torch.float32:
+        return (w if w.is_contiguous() else w.contiguous()), None
+    key = (w.data_ptr(), tuple(w.shape), dtype)
+    ent = _wcache.get(key)
+    ver = w._version
+    if ent is not None and ent[0] == ver and (ent[2] is not None or not need_t) and not torch.cuda.is_current_stream_capturing():
+        return ent[1], ent[2]
+    src = w.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    N, K = src.shape
+    wc = torch.empty((N, K), dtype=dtype, device=w.device)
+    wt = torch.empty((K, N), dtype=dtype, device=w.device) if need_t else None
+    call("mar_cast_weight", src.data_ptr(), wc.data_ptr(), _p(wt), N, K, _dt(wc), _stream())
+    _wcache[key] = (ver, wc, wt)
+    return wc, wt
+
+
+# --------------------------------------------------------------------------------------
+# cast
+# --------------------------------------------------------------------------------------
+class _Cast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src_dtype = x.dtype
+        x = x.contiguous()
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+        call("mar_cast", x.data_ptr(), _dt(x), out.data_ptr(), _dt(out), x.numel(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        out = torch.empty(g.shape, dtype=ctx.src_dtype, device=g.device)
+        call("mar_cast", g.data_ptr(), _dt(g), out.data_ptr(), _dt(out), g.numel(), _stream())
+        return out, None
+
+
+def to_compute(x: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Activation in the compute dtype (contiguous)."""
+    _require_cuda(x, "input")
+    dtype = dtype or get_precision()
+    if x.dtype == dtype:
+        return x if x.is_contiguous() else x.contiguous()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return _Cast.apply(x, dtype)
+
+
+# --------------------------------------------------------------------------------------
+# linear (+ fused epilogue)
+# --------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, flags, p, out_dtype):
+        # x (M,K) compute dtype; weight (N,K) fp32 master; bias (N) fp32; residual (M,N) compute dtype
+        M, K = x.shape
+        N = weight.shape[0]
+        cd = x.dtype
+        need_t = cd == torch.bfloat16 and (x.requires_grad or True)
+        wc, wt = compute_weight(weight, cd, need_t)
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        site = 0
+        rng = None
+        if (flags & EPI_DROPOUT) and p > 0.0:
+            rng = _rng.state(x.device)
+            site = _rng.next_site()
+        else:
+            flags &= ~EPI_DROPOUT
+        b32 = None
+        if bias is not None:
+            b32 = bias.detach()
+            if b32.dtype != torch.float32:
+                b32 = b32.float()
+        call("mar_linear_fwd", x.data_ptr(), x.stride(0), wc.data_ptr(), _p(b32), _p(residual),
+             0 if residual is None else residual.stride(0), out.data_ptr(), out.stride(0), M, N, K, _dt(x), _dt(out),
+             flags, float(p), _p(rng), site, _eng(), _stream())
+        ctx.flags, ctx.p, ctx.site, ctx.rng = flags, float(p), site, rng
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.wc, ctx.wt = wc, wt
+        ctx.w_shape = tuple(weight.shape)
+        ctx.eng = _eng()
+        need_out = bool(flags & (EPI_RELU_PRE | EPI_RELU_POST))
+        ctx.save_for_backward(x, out if need_out else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, out = ctx.saved_tensors
+        M, K = x.shape
+        N = ctx.w_shape[0]
+        cd = x.dtype
+        st = _stream()
+        if dout.dtype != cd:
+            dout = _Cast.apply(dout, cd)
+        dout = dout.contiguous()
+        needs_x, needs_w, needs_b, needs_r = ctx.needs_input_grad[0:4]
+        dbias = torch.zeros(N, dtype=torch.float32, device=x.device) if (ctx.has_bias and needs_b) else None
+        if ctx.flags != 0:
+            dz = torch.empty_like(dout)
+            call("mar_linear_bwd_epilogue", dout.data_ptr(), _p(out), dz.data_ptr(), _p(dbias), M, N, _dt(dout),
+                 _dt(out) if out is not None else _dt(dout), ctx.flags, ctx.p, _p(ctx.rng), ctx.site, st)
+        else:
+            dz = dout
+            if dbias is not None:
+                call("mar_linear_bwd_epilogue", dout.data_ptr(), None, None, dbias.data_ptr(), M, N, _dt(dout),
+                     _dt(dout), 0, 0.0, None, 0, st)
+        dx = dw = None
+        if needs_x:
+            dx = torch.empty((M, K), dtype=cd, device=x.device)
+            call("mar_linear_dgrad", dz.data_ptr(), ctx.wc.data_ptr(), _p(ctx.wt), None, dx.data_ptr(), K, M, N, K,
+                 _dt(dz), ctx.eng, st)
+        if needs_w:
+            dw = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
+            call("mar_linear_wgrad", dz.data_ptr(), x.data_ptr(), x.stride(0), dw.data_ptr(), M, N, K, _dt(dz), 0,
+                 ctx.eng, st)
+        dres = dout if (ctx.has_res and needs_r) else None
+        return dx, dw, dbias, dres, None, None, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, relu_pre: bool = False, dropout_p: float = 0.0,
+           relu_post: bool = False, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """out = residual + relu_post(dropout(relu_pre(x·Wᵀ + b))) on the last dim of x."""
+    shape = x.shape
+    x2 = _rows(to_compute(x))
+    r2 = None
+    if residual is not None:
+        r2 = _rows(to_compute(residual, x2.dtype))
+    flags = (EPI_RELU_PRE if relu_pre else 0) | (EPI_DROPOUT if dropout_p > 0 else 0) | (EPI_RELU_POST if relu_post else 0)
+    out = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype)
+    return out.view(*shape[:-1], weight.shape[0])
+
+
+# --------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, key_mask, H, p):
+        B, T, d3 = qkv.shape
+        d = d3 // 3
+        dh = d // H
+        out = torch.empty((B, T, d), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+        rng, site = None, 0
+        if p > 0.0:
+            rng = _rng.state(qkv.device)
+            site = _rng.next_site()
+        call("mar_attention_fwd", qkv.data_ptr(), _p(key_mask), out.data_ptr(), lse.data_ptr(), B, T, H, dh, _dt(qkv),
+             float(p), _p(rng), site, _eng(), _stream())
+        ctx.dims = (B, T, H, dh)
+        ctx.p, ctx.site, ctx.rng, ctx.eng = float(p), site, rng, _eng()
+        ctx.save_for_backward(qkv, out, lse, key_mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, key_mask = ctx.saved_tensors
+        B, T, H, dh = ctx.dims
+        if dout.dtype != qkv.dtype:
+            dout = _Cast.apply(dout, qkv.dtype)
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+        call("mar_attention_bwd", qkv.data_ptr(), _p(key_mask), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+             delta.data_ptr(), dqkv.data_ptr(), B, T, H, dh, _dt(qkv), ctx.p, _p(ctx.rng), ctx.site, ctx.eng, _stream())
+        return dqkv, None, None, None
+
+
+def attention(qkv: torch.Tensor, key_mask: Optional[torch.Tensor], num_heads: int, dropout_p: float) -> torch.Tensor:
+    """qkv (B,T,3d) packed in-projection output → (B,T,d).  key_mask (B,T) uint8/bool, 1 = ignore key."""
+    qkv = to_compute(qkv)
+    if key_mask is not None:
+        if key_mask.dtype == torch.bool:
+            key_mask = key_mask.view(torch.uint8) if key_mask.is_contiguous() else key_mask.contiguous().view(torch.uint8)
+        key_mask = key_mask.contiguous()
+    return _Attention.apply(qkv, key_mask, int(num_heads), float(dropout_p))
+
+
+# --------------------------------------------------------------------------------------
+# layer norm
+# --------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, zero_rows):
+        rows, D = x.shape
+        y = torch.empty_like(x)
+        need_grad = x.requires_grad or gamma.requires_grad or beta.requires_grad
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need_grad else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need_grad else None
+        call("mar_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _p(mean), _p(rstd),
+             _p(zero_rows), rows, D, float(eps), _dt(x), _stream())
+        if zero_rows is not None and need_grad:
+            raise RuntimeError("layer_norm(zero_rows=...) is the eval-only nested-tensor zero fill; no backward")
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        rows, D = x.shape
+        if dy.dtype != x.dtype:
+            dy = _Cast.apply(dy, x.dtype)
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dgamma = torch.zeros(D, dtype=torch.float32, device=x.device)
+        dbeta = torch.zeros(D, dtype=torch.float32, device=x.device)
+        call("mar_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+             dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D, _dt(x), _stream())
+        return dx, dgamma, dbeta, None, None
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+               zero_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    shape = x.shape
+    x2 = to_compute(x).reshape(-1, shape[-1])
+    g = gamma if gamma.dtype == torch.float32 else gamma.float()
+    b = beta if beta.dtype == torch.float32 else beta.float()
+    return _LayerNorm.apply(x2, g, b, eps, zero_rows).view(shape)
+
+
+# --------------------------------------------------------------------------------------
+# pooling / masks / concat
+# --------------------------------------------------------------------------------------
+class _MeanPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, T, D = x.shape
+        out = torch.empty((B, D), dtype=x.dtype, device=x.device)
+        call("mar_meanpool_fwd", x.data_ptr(), out.data_ptr(), B, T, D, _dt(x), _stream())
+        ctx.dims = (B, T, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, D = ctx.dims
+        dout = dout.contiguous()
+        dx = torch.empty((B, T, D), dtype=dout.dtype, device=dout.device)
+        call("mar_meanpool_bwd", dout.data_ptr(), dx.data_ptr(), B, T, D, _dt(dout), _stream())
+        return dx
+
+
+def mean_pool(x: torch.Tensor) -> torch.Tensor:
+    """(B,T,D) → (B,D): x.mean(dim=1) (SequenceAverageFeatures, models.py:105)."""
+    return _MeanPool.apply(to_compute(x))
+
+
+def rowzero_mask(x: torch.Tensor) -> torch.Tensor:
+    """(B,T,D) → (B,T) uint8, 1 where the feature row sums to exactly 0 (models.py:421-422)."""
+    x = to_compute(x)
+    B, T, D = x.shape
+    mask = torch.empty((B, T), dtype=torch.uint8, device=x.device)
+    call("mar_rowzero_mask", x.data_ptr(), mask.data_ptr(), B * T, D, _dt(x), _stream())
+    return mask
+
+
+class _ConcatT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *xs):
+        B, _, D = xs[0].shape
+        Ts = [x.shape[1] for x in xs]
+        total = sum(Ts)
+        out = torch.empty((B, total, D), dtype=xs[0].dtype, device=xs[0].device)
+        off = 0
+        for x, T in zip(xs, Ts):
+            call("mar_concat_rows", x.data_ptr(), out.data_ptr(), B, T, total, off, D, _dt(x), 1, _stream())
+            off += T
+        ctx.Ts, ctx.B, ctx.D = Ts, B, D
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        total = sum(ctx.Ts)
+        outs, off = [], 0
+        for T in ctx.Ts:
+            dx = torch.empty((ctx.B, T, ctx.D), dtype=g.dtype, device=g.device)
+            call("mar_concat_rows", g.data_ptr(), dx.data_ptr(), ctx.B, T, total, off, ctx.D, _dt(g), 0, _stream())
+            outs.append(dx)
+            off += T
+        return tuple(outs)
+
+
+def concat_time(xs) -> torch.Tensor:
+    """torch.cat(xs, dim=1) for (B,T_i,D) blocks (models.py:419)."""
+    xs = [to_compute(x) for x in xs]
+    return _ConcatT.apply(*xs)
+
+
+class _SliceT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, t0, t1):
+        B, total, D = x.shape
+        out = torch.empty((B, t1 - t0, D), dtype=x.dtype, device=x.device)
+        call("mar_concat_rows", x.data_ptr(), out.data_ptr(), B, t1 - t0, total, t0, D, _dt(x), 0, _stream())
+        ctx.dims = (B, total, D, t0, t1)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, total, D, t0, t1 = ctx.dims
+        g = g.contiguous()
+        dx = torch.zeros((B, total, D), dtype=g.dtype, device=g.device)
+        call("mar_concat_rows", g.data_ptr(), dx.data_ptr(), B, t1 - t0, total, t0, D, _dt(g), 1, _stream())
+        return dx, None, None
+
+
+def slice_time(x: torch.Tensor, t0: int, t1: int) -> torch.Tensor:
+    """Contiguous copy of x[:, t0:t1] (models.py:430)."""
+    return _SliceT.apply(x.contiguous(), int(t0), int(t1))
+
+
+# --------------------------------------------------------------------------------------
+# classifier loss
+# --------------------------------------------------------------------------------------
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, weight):
+        B, C = logits.shape
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        call("mar_cross_entropy_fwd", logits.data_ptr(), labels.data_ptr(), _p(weight), loss.data_ptr(),
+             dlogits.data_ptr(), None, B, C, _stream())
+        ctx.save_for_backward(dlogits)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None, None
+
+
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.CrossEntropyLoss (mean; optional class weights).  Rows with label < 0 are ignored."""
+    _require_cuda(logits, "cross_entropy")
+    if logits.dtype != torch.float32:
+        logits = to_compute(logits, torch.float32)
+    logits = logits.contiguous()
+    labels = labels.to(device=logits.device, dtype=torch.int64).contiguous()
+    if weight is not None:
+        weight = weight.to(device=logits.device, dtype=torch.float32).contiguous()
+    return _CrossEntropy.apply(logits, labels, weight)
+
+
+def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
+    """argmax over classes on the device (trainer.py:170, :726)."""
+    logits = to_compute(logits, torch.float32).contiguous()
+    B, C = logits.shape
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    preds = torch.empty(B, dtype=torch.int64, device=logits.device)
+    labels = torch.full((B,), -1, dtype=torch.int64, device=logits.device)
+    call("mar_cross_entropy_fwd", logits.data_ptr(), labels.data_ptr(), None, loss.data_ptr(), None, preds.data_ptr(),
+         B, C, _stream())
+    return preds
+
+
+# --------------------------------------------------------------------------------------
+# recurrences
+# --------------------------------------------------------------------------------------
+class _GRU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gi, w_hh, b_hh):
+        B, T, H3 = gi.shape
+        H = H3 // 3
+        cd = gi.dtype
+        wc, _ = compute_weight(w_hh, cd, False)
+        need_grad = gi.requires_grad or w_hh.requires_grad or b_hh.requires_grad
+        hseq = torch.empty((B, T, H), dtype=cd, device=gi.device)
+        saved = torch.empty((B, T, 5 * H), dtype=cd, device=gi.device) if need_grad else None
+        work = torch.empty(B * 5 * H, dtype=torch.float32, device=gi.device)
+        b32 = b_hh.detach().float().contiguous()
+        call("mar_gru_fwd", gi.data_ptr(), wc.data_ptr(), b32.data_ptr(), hseq.data_ptr(), _p(saved), work.data_ptr(),
+             B, T, H, _dt(gi), _eng(), _stream())
+        ctx.dims = (B, T, H)
+        ctx.wc = wc
+        ctx.eng = _eng()
+        ctx.save_for_backward(hseq, saved)
+        return hseq
+
+    @staticmethod
+    def backward(ctx, dhseq):
+        hseq, saved = ctx.saved_tensors
+        B, T, H = ctx.dims
+        cd = hseq.dtype
+        st = _stream()
+        if dhseq.dtype != cd:
+            dhseq = _Cast.apply(dhseq, cd)
+        dhseq = dhseq.contiguous()
+        dgi = torch.empty((B, T, 3 * H), dtype=cd, device=hseq.device)
+        dgh = torch.empty((B, T, 3 * H), dtype=cd, device=hseq.device)
+        work = torch.empty(B * 5 * H, dtype=torch.float32, device=hseq.device)
+        call("mar_gru_bwd", dhseq.data_ptr(), hseq.data_ptr(), saved.data_ptr(), ctx.wc.data_ptr(), dgi.data_ptr(),
+             dgh.data_ptr(), work.data_ptr(), B, T, H, _dt(hseq), ctx.eng, st)
+        dw = torch.empty((3 * H, H), dtype=torch.float32, device=hseq.device)
+        hprev = saved.view(B * T, 5 * H)[:, 4 * H:]
+        call("mar_linear_wgrad", dgh.data_ptr(), hprev.data_ptr(), 5 * H, dw.data_ptr(), B * T, 3 * H, H, _dt(dgh), 0,
+             ctx.eng, st)
+        db = torch.zeros(3 * H, dtype=torch.float32, device=hseq.device)
+        call("mar_linear_bwd_epilogue", dgh.data_ptr(), None, None, db.data_ptr(), B * T, 3 * H, _dt(dgh), _dt(dgh), 0,
+             0.0, None, 0, st)
+        return dgi, dw, db
+
+
+def gru(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh) -> torch.Tensor:
+    """1-layer batch_first GRU with h0 = 0 → (B,T,H) (nn.GRU as used at models.py:110,122)."""
+    gi = linear(x, w_ih, b_ih)
+    return _GRU.apply(gi.contiguous(), w_hh, b_hh)
+
+
+class _LSTM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gi, w_hh, b_hh):
+        B, T, H4 = gi.shape
+        H = H4 // 4
+        cd = gi.dtype
+        wc, _ = compute_weight(w_hh, cd, False)
+        need_grad = gi.requires_grad or w_hh.requires_grad or b_hh.requires_grad
+        hseq = torch.empty((B, T, H), dtype=cd, device=gi.device)
+        saved = torch.empty((B, T, 6 * H), dtype=cd, device=gi.device) if need_grad else None
+        work = torch.empty(B * 5 * H, dtype=torch.float32, device=gi.device)
+        b32 = b_hh.detach().float().contiguous()
+        call("mar_lstm_fwd", gi.data_ptr(), wc.data_ptr(), b32.data_ptr(), hseq.data_ptr(), _p(saved), work.data_ptr(),
+             B, T, H, _dt(gi), _eng(), _stream())
+        ctx.dims = (B, T, H)
+        ctx.wc = wc
+        ctx.eng = _eng()
+        ctx.save_for_backward(saved)
+        return hseq
+
+    @staticmethod
+    def backward(ctx, dhseq):
+        (saved,) = ctx.saved_tensors
+        B, T, H = ctx.dims
+        cd = saved.dtype
+        st = _stream()
+        if dhseq.dtype != cd:
+            dhseq = _Cast.apply(dhseq, cd)
+        dhseq = dhseq.contiguous()
+        dg = torch.empty((B, T, 4 * H), dtype=cd, device=saved.device)
+        work = torch.empty(B * 2 * H, dtype=torch.float32, device=saved.device)
+        call("mar_lstm_bwd", dhseq.data_ptr(), saved.data_ptr(), ctx.wc.data_ptr(), dg.data_ptr(), work.data_ptr(),
+             B, T, H, _dt(saved), ctx.eng, st)
+        dw = torch.empty((4 * H, H), dtype=torch.float32, device=saved.device)
+        hprev = saved.view(B * T, 6 * H)[:, 5 * H:]
+        call("mar_linear_wgrad", dg.data_ptr(), hprev.data_ptr(), 6 * H, dw.data_ptr(), B * T, 4 * H, H, _dt(dg), 0,
+             ctx.eng, st)
+        db = torch.zeros(4 * H, dtype=torch.float32, device=saved.device)
+        call("mar_linear_bwd_epilogue", dg.data_ptr(), None, None, db.data_ptr(), B * T, 4 * H, _dt(dg), _dt(dg), 0,
+             0.0, None, 0, st)
+        return dg, dw, db
+
+
+def lstm(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh) -> torch.Tensor:
+    """1-layer batch_first LSTM with (h0,c0) = 0 → (B,T,H) (train_video_rnn.py:94-106)."""
+    gi = linear(x, w_ih, b_ih)
+    return _LSTM.apply(gi.contiguous(), w_hh, b_hh)

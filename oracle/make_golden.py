@@ -1,0 +1,245 @@
+"""Generate tests/golden/*.pt by running the LIVE reference classes (imported from /root/reference,
+build container only) and pin the CPU oracle against them.
+
+    python oracle/make_golden.py            # writes tests/golden/golden_v1.pt, asserts oracle == reference
+
+Each case stores: the builder name + kwargs, the init seed (weights are re-created from the seed: the
+drop-in and the reference construct identical torch.nn containers in identical order), a checksum of
+the weights, the batch seed/kwargs, and the reference's outputs (logits, per-head losses, per-parameter
+gradient norms, a few full gradients, a 3-step Adam loss curve).  Dropout is disabled on the reference
+for every case (exact parity is defined at p = 0).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.dont_write_bytecode = True
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+import models as ref  # noqa: E402  the reference
+
+from multimodalaggressionrecognition_b200 import workloads as W  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+torch.set_num_threads(8)
+O.DROPOUT_ENABLED = False   # the reference side runs with every dropout p = 0
+
+CASES = {
+    "c1_small": dict(builder="build_c1", bkw={}, batch="batch_c1", dkw=dict(B=4, T=50)),
+    "c1_odd": dict(builder="build_c1", bkw={}, batch="batch_c1", dkw=dict(B=3, T=37)),
+    "c2_small": dict(builder="build_c2", bkw=dict(heads=("LSTM_1L", "GRU_1L", "Avg_features")), batch="batch_c2",
+                     dkw=dict(B=8, T=16)),
+    "c3_small": dict(builder="build_c3", bkw=dict(t_audio=50, t_video=16), batch="batch_c3",
+                     dkw=dict(B=4, t_audio=50, t_video=16)),
+    "c3_video_empty": dict(builder="build_c3", bkw=dict(t_audio=50, t_video=16), batch="batch_c3",
+                           dkw=dict(B=4, t_audio=50, t_video=16, empty="video")),
+    "c3_audio_empty": dict(builder="build_c3", bkw=dict(t_audio=50, t_video=16), batch="batch_c3",
+                           dkw=dict(B=4, t_audio=50, t_video=16, empty="audio")),
+    "c3_audio_padded": dict(builder="build_c3", bkw=dict(t_audio=50, t_video=16), batch="batch_c3",
+                            dkw=dict(B=4, t_audio=50, t_video=16, zero_pad_audio=13)),
+}
+FULL_GRADS = {
+    "build_c1": ["1.classifier.4.weight", "0.transformer_squence_processing.norm.weight",
+                 "0.transformer_squence_processing.layers.0.self_attn.in_proj_bias"],
+    "build_c2": ["models_dict.GRU_1L.output_classifier.3.weight", "models_dict.GRU_1L.sequence_nn.bias_hh_l0",
+                 "models_dict.LSTM_1L.sequence_nn.bias_hh_l0"],
+    "build_c3": ["classifiers.classifiers_dict.verb.3.weight", "modality_fusion_module.modality_fusion_transformer.norm.weight",
+                 "modality_extractors_dict.video.feature_extractor.embedding.0.bias"],
+}
+INIT_SEED = 1234
+
+
+def weights_checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+def ref_loss(builder, model, batch):
+    data, labels = batch
+    pred = model(data)
+    if builder == "build_c1":
+        return pred, {"loss": torch.nn.CrossEntropyLoss()(pred, labels)}
+    if builder == "build_c2":
+        return pred, ref.MultiCrossEntropyLoss()(pred, labels)
+    crit = ref.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(), "verb": torch.nn.CrossEntropyLoss()})
+    return pred, crit(pred, labels)
+
+
+def oracle_forward(builder, bkw, sd, data, training, grad_enabled):
+    if builder == "build_c1":
+        h = O.transformer_sequence_processor(data, sd, "0.", 2, 8, "identity", training)
+        return O.output_classifier(h, sd, "1.", training)
+    if builder == "build_c2":
+        kinds = {"GRU_1L": "gru", "LSTM_1L": "lstm", "Avg_features": "avg"}
+        return O.video_multi_nn(data, sd, {h: kinds[h] for h in bkw["heads"]}, training)
+    cfg = W.c3_oracle_cfg(bkw["t_audio"], bkw["t_video"])
+    return O.physverb_model(data, sd, cfg, training, grad_enabled)
+
+
+def oracle_loss(builder, pred, labels):
+    if builder == "build_c1":
+        return {"loss": O.cross_entropy(pred, labels)}
+    if builder == "build_c2":
+        return O.multi_ce(pred, labels)
+    return O.multimodal_ce(pred, labels, heads=["phys", "verb"])
+
+
+def as_dict(pred):
+    return pred if isinstance(pred, dict) else {"logits": pred}
+
+
+def check(name, a, b, tol=2e-5):
+    err = (a - b).abs().max().item()
+    scale = max(b.abs().max().item(), 1e-6)
+    assert err <= tol * max(scale, 1.0), f"oracle != reference at {name}: max err {err:.3e} (scale {scale:.3e})"
+    return err
+
+
+def _ref_train_pass(builder, bkw, sd0, batch, dtype):
+    """train-mode forward + per-head backward of the LIVE reference in `dtype` (dropout off)."""
+    model = W.disable_dropout(getattr(W, builder)(ref, **bkw)).to(dtype)
+    model.load_state_dict({k: v.to(dtype) for k, v in sd0.items()})
+    model.train()
+    data, labels = batch
+    if dtype == torch.float64:
+        data = [[n, t.double()] for n, t in data] if isinstance(data, list) else data.double()
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)     # the reference's zero stubs use the default dtype (models.py:851)
+    try:
+        pred, losses = ref_loss(builder, model, (data, labels))
+        if hasattr(losses, "backward"):
+            losses.backward()
+        else:
+            sum(losses.values()).backward()
+    finally:
+        torch.set_default_dtype(old)
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    return as_dict(pred), losses, grads
+
+
+def run_case(name, spec):
+    builder, bkw = spec["builder"], spec["bkw"]
+    torch.manual_seed(INIT_SEED)
+    model = W.perturb_norms(W.disable_dropout(getattr(W, builder)(ref, **bkw)))
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    # ReLU is discontinuous: a pre-activation within fp32 rounding of 0 can flip between two correct fp32
+    # implementations and move a weight-gradient row by several percent.  Pick a batch seed for which the
+    # reference's own fp32 and fp64 runs agree, and record the fp64 run (rounded to fp32) as the golden value.
+    for seed in range(1000, 1040):
+        dkw = dict(spec["dkw"], seed=seed)
+        batch = getattr(W, spec["batch"])(**dkw)
+        _, l32, g32 = _ref_train_pass(builder, bkw, sd0, batch, torch.float32)
+        pred64, l64, g64 = _ref_train_pass(builder, bkw, sd0, batch, torch.float64)
+        sdo = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+        lo = oracle_loss(builder, oracle_forward(builder, bkw, sdo, batch[0], True, True), batch[1])
+        if lo:
+            sum(lo.values()).backward()
+        worst = 0.0
+        for k, g in g64.items():
+            if g is None:
+                continue
+            den = g.abs().max().clamp_min(1e-30)
+            worst = max(worst, float((g32[k].double() - g).abs().max() / den),
+                        float((sdo[k].grad.double() - g).abs().max() / den))
+        if worst < 2e-4:
+            break
+        print(f"  {name}: seed {seed}: an fp32 ReLU flip (reference-fp32 or oracle-fp32 vs reference-fp64, "
+              f"worst rel grad err {worst:.2e}); next seed")
+    else:
+        raise AssertionError("no flip-free seed found")
+    spec = dict(spec, dkw=dkw)
+    data, labels = batch
+    out = {"spec": spec, "init_seed": INIT_SEED, "weights_checksum": weights_checksum(sd0)}
+
+    # eval forward under no_grad (this is the nested-tensor zero-fill path when a padding mask exists)
+    model.eval()
+    with torch.no_grad():
+        try:
+            pred_eval = as_dict(model(data))
+            out["eval"] = {k: v.clone() for k, v in pred_eval.items()}
+        except RuntimeError as e:  # all-masked batch in eval
+            out["eval_error"] = str(e)
+        try:
+            with torch.no_grad():
+                po = as_dict(oracle_forward(builder, bkw, sd0, data, False, False))
+            for k in out.get("eval", {}):
+                check(f"{name}/eval/{k}", po[k], out["eval"][k])
+            assert "eval_error" not in out
+        except RuntimeError as e:
+            assert "eval_error" in out, f"oracle raised but the reference did not: {e}"
+
+    out["train"] = {k: v.detach().float() for k, v in pred64.items()}
+    out["losses"] = {k: float(v.detach()) for k, v in l64.items()}
+    grads = {k: (g.float() if g is not None else None) for k, g in g64.items()}
+    out["grad_norms"] = {k: (float(g.norm()) if g is not None else None) for k, g in grads.items()}
+    out["grads"] = {k: grads[k].clone() for k in FULL_GRADS[builder] if grads.get(k) is not None}
+
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    po = oracle_forward(builder, bkw, sdo, data, True, True)
+    lo = oracle_loss(builder, po, labels)
+    for k in out["train"]:
+        check(f"{name}/train/{k}", as_dict(po)[k].detach(), out["train"][k])
+    assert set(lo) == set(out["losses"]), (set(lo), set(out["losses"]))
+    for k in lo:
+        assert abs(float(lo[k].detach()) - out["losses"][k]) < 2e-5, (name, k)
+    if lo:
+        sum(lo.values()).backward()
+    for k, g in grads.items():
+        go = sdo[k].grad
+        if g is None:
+            assert go is None or float(go.abs().max()) == 0.0, f"{name}: oracle has a grad for {k}, reference has none"
+        else:
+            check(f"{name}/grad/{k}", go, g, tol=5e-5)
+
+    # 3 Adam steps: loss curve (train_multimodal.py:444 default Adam)
+    torch.manual_seed(INIT_SEED)
+    model = W.perturb_norms(W.disable_dropout(getattr(W, builder)(ref, **bkw))).train()
+    opt = torch.optim.Adam(model.parameters())
+    curve = []
+    for _ in range(3):
+        opt.zero_grad()
+        _, losses = ref_loss(builder, model, batch)
+        if hasattr(losses, "backward"):
+            losses.backward()
+        else:
+            sum(losses.values()).backward()
+        opt.step()
+        curve.append({k: float(v.detach()) for k, v in losses.items()})
+    out["adam_curve"] = curve
+
+    def fwd(sd, d, training):
+        return oracle_forward(builder, bkw, sd, d, training, True)
+    tr = O.OracleTrainer(sd0, fwd, lambda p, t: oracle_loss(builder, p, t))
+    for i in range(3):
+        got = tr.step(data, labels, training=True)
+        for k, v in curve[i].items():
+            assert abs(got[k] - v) < 1e-4 * max(1.0, abs(v)), f"{name}: Adam curve step {i} {k}: oracle {got[k]} ref {v}"
+    print(f"  {name}: ok  losses={out['losses']}  curve[-1]={curve[-1]}")
+    return out
+
+
+def main():
+    golden = {"torch": torch.__version__, "cases": {}}
+    for name, spec in CASES.items():
+        golden["cases"][name] = run_case(name, spec)
+    # structural known-answer: the module tree print-out of the reference's A+T PhysVerbModel (1.txt) is
+    # reproduced by the drop-in classes (checked in tests/test_structure.py from this string)
+    torch.manual_seed(0)
+    golden["c3_module_tree"] = str(W.build_c3(ref))
+    golden["param_counts"] = {
+        "c1": sum(p.numel() for p in W.build_c1(ref).parameters()),
+        "c2_gru": sum(p.numel() for p in W.build_c2(ref).parameters()),
+        "c3": sum(p.numel() for p in W.build_c3(ref).parameters()),
+    }
+    path = os.path.join(ROOT, "tests", "golden", "golden_v1.pt")
+    torch.save(golden, path)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
