@@ -158,22 +158,23 @@ int mar_cross_entropy_fwd(const float* logits, const int64_t* labels, const floa
 /* ---- GRU / LSTM recurrence ------------------------------------------------------------------ */
 /* One-layer batch_first GRU, h0 = 0 (nn.GRU at models.py:110,122; gate order r,z,n).
  * gi (B,T,3H) = x·W_ihᵀ + b_ih is produced by mar_linear_fwd.  w_hh (3H,H) in `dtype`, b_hh fp32.
- * hseq (B,T,H) output sequence in `dtype`; saved (B,T,4H) in `dtype`: r, z, n and (W_hn h + b_hn)
- * for backward (NULL in inference). */
-int mar_gru_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved,
+ * hseq (B,T,H): output sequence in `dtype`.  The hidden state is carried in fp32 between steps; only the
+ * recurrent GEMM operand is rounded to `dtype`.  For training (NULL in inference):
+ *   saved (B,T,5H) fp32: r, z, n, (W_hn h + b_hn), h_{t-1};   hprev (B,T,H) in `dtype`: h_{t-1} (wgrad operand).
+ * work: mar_gru_work_floats() floats. */
+int mar_gru_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved,
                 float* work, int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream);
-/* dhseq (B,T,H) incoming grad for every step (zeros except the last for the reference heads).
- * Produces dgi (B,T,3H) and dgh (B,T,3H) in `dtype` (dW_ih, dW_hh, biases and dx then follow from
- * mar_linear_wgrad / mar_linear_dgrad / mar_linear_bwd_epilogue on those).  wt_hh = W_hhᵀ (H,3H)
- * for the tcgen05 engine or NULL.  work: fp32 workspace of 2*B*H floats. */
-int mar_gru_bwd(const void* dhseq, const void* hseq, const void* saved, const void* w_hh, void* dgi,
-                void* dgh, float* work, int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream);
+/* dhseq (B,T,H): incoming grad of every step's output (zeros except the last step for the reference's heads).
+ * Produces dgi (B,T,3H) and dgh (B,T,3H) in `dtype`; dW_ih, dW_hh, the biases and dx then follow from
+ * mar_linear_wgrad / mar_linear_dgrad / mar_linear_bwd_epilogue on those. */
+int mar_gru_bwd(const void* dhseq, const float* saved, const void* w_hh, void* dgi, void* dgh, float* work,
+                int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream);
 int64_t mar_gru_work_floats(int64_t B, int64_t T, int64_t H);
 
-/* LSTM (train_video_rnn.py:94-106; gate order i,f,g,o).  saved (B,T,5H): i,f,g,o,c. */
-int mar_lstm_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved,
+/* LSTM (train_video_rnn.py:94-106; gate order i,f,g,o).  saved (B,T,5H) fp32: i,f,g,o,c; hprev as above. */
+int mar_lstm_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved,
                  float* work, int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream);
-int mar_lstm_bwd(const void* dhseq, const void* saved, const void* w_hh, void* dgates, float* work,
+int mar_lstm_bwd(const void* dhseq, const float* saved, const void* w_hh, void* dgates, float* work,
                  int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream);
 
 /* ---- Optimizer ------------------------------------------------------------------------------ */

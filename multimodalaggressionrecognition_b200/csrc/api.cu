@@ -181,42 +181,44 @@ int mar_attention_bwd(const void* qkv, const uint8_t* key_mask, const void* out,
 // ------------------------------------------------------------------------------------------
 int64_t mar_gru_work_floats(int64_t B, int64_t T, int64_t H) { (void)T; return B * 5 * H; }
 
-int mar_gru_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved, float* work, int64_t B,
-                int64_t T, int64_t H, int dtype, int engine, void* stream) {
+int mar_gru_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, float* work,
+                int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream) {
   MAR_CHECK_ARG(gi && w_hh && b_hh && hseq && work, "mar_gru_fwd: null pointer");
+  MAR_CHECK_ARG((saved == nullptr) == (hprev == nullptr), "mar_gru_fwd: saved and hprev go together");
   MAR_CHECK_ARG(B > 0 && T > 0 && H > 0, "mar_gru_fwd: bad shape");
   MAR_CHECK_ARG(dtype == MAR_F32 || dtype == MAR_BF16, "mar_gru_fwd: bad dtype");
   const bool pers_ok = gru_persistent_supported(B, T, H, dtype);
   if (engine == MAR_ENGINE_TCGEN05 && !pers_ok) MAR_UNSUPPORTED("mar_gru_fwd: persistent engine cannot take B=%lld T=%lld H=%lld dtype=%d", (long long)B, (long long)T, (long long)H, dtype);
   if (engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && pers_ok && !env_flag("MAR_FORCE_SIMT"))) {
     mar_set_engine(MAR_ENGINE_TCGEN05);
-    return gru_fwd_persistent(gi, w_hh, b_hh, hseq, saved, B, T, H, S(stream));
+    return gru_fwd_persistent(gi, w_hh, b_hh, hseq, hprev, saved, B, T, H, S(stream));
   }
   mar_set_engine(MAR_ENGINE_SIMT);
-  return gru_fwd_steps(gi, w_hh, b_hh, hseq, saved, work, B, T, H, dtype, S(stream));
+  return gru_fwd_steps(gi, w_hh, b_hh, hseq, hprev, saved, work, B, T, H, dtype, S(stream));
 }
 
-int mar_gru_bwd(const void* dhseq, const void* hseq, const void* saved, const void* w_hh, void* dgi, void* dgh,
-                float* work, int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream) {
+int mar_gru_bwd(const void* dhseq, const float* saved, const void* w_hh, void* dgi, void* dgh, float* work, int64_t B,
+                int64_t T, int64_t H, int dtype, int engine, void* stream) {
   MAR_CHECK_ARG(dhseq && saved && w_hh && dgi && dgh && work, "mar_gru_bwd: null pointer");
   MAR_CHECK_ARG(B > 0 && T > 0 && H > 0, "mar_gru_bwd: bad shape");
   MAR_CHECK_ARG(dtype == MAR_F32 || dtype == MAR_BF16, "mar_gru_bwd: bad dtype");
   (void)engine;
   mar_set_engine(MAR_ENGINE_SIMT);
-  return gru_bwd_steps(dhseq, hseq, saved, w_hh, dgi, dgh, work, B, T, H, dtype, S(stream));
+  return gru_bwd_steps(dhseq, saved, w_hh, dgi, dgh, work, B, T, H, dtype, S(stream));
 }
 
-int mar_lstm_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved, float* work, int64_t B,
-                 int64_t T, int64_t H, int dtype, int engine, void* stream) {
+int mar_lstm_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, float* work,
+                 int64_t B, int64_t T, int64_t H, int dtype, int engine, void* stream) {
   MAR_CHECK_ARG(gi && w_hh && b_hh && hseq && work, "mar_lstm_fwd: null pointer");
+  MAR_CHECK_ARG((saved == nullptr) == (hprev == nullptr), "mar_lstm_fwd: saved and hprev go together");
   MAR_CHECK_ARG(B > 0 && T > 0 && H > 0, "mar_lstm_fwd: bad shape");
   MAR_CHECK_ARG(dtype == MAR_F32 || dtype == MAR_BF16, "mar_lstm_fwd: bad dtype");
   (void)engine;
   mar_set_engine(MAR_ENGINE_SIMT);
-  return lstm_fwd_steps(gi, w_hh, b_hh, hseq, saved, work, B, T, H, dtype, S(stream));
+  return lstm_fwd_steps(gi, w_hh, b_hh, hseq, hprev, saved, work, B, T, H, dtype, S(stream));
 }
 
-int mar_lstm_bwd(const void* dhseq, const void* saved, const void* w_hh, void* dgates, float* work, int64_t B,
+int mar_lstm_bwd(const void* dhseq, const float* saved, const void* w_hh, void* dgates, float* work, int64_t B,
                  int64_t T, int64_t H, int dtype, int engine, void* stream) {
   MAR_CHECK_ARG(dhseq && saved && w_hh && dgates && work, "mar_lstm_bwd: null pointer");
   MAR_CHECK_ARG(B > 0 && T > 0 && H > 0, "mar_lstm_bwd: bad shape");

@@ -79,7 +79,7 @@ attn_fwd_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ key_
       else { p = valid ? expf(s - m_new) : 0.f; corr = expf(m[i] - m_new); }
       l[i] = l[i] * corr + warp_sum(p);
       m[i] = m_new;
-      if (drop) p = drop_keep(dk, ((uint64_t)bh * dm.T + q) * dm.T + kk) ? p * dk.scale : 0.f;
+      if (drop) p = drop_keep(dk, ((uint64_t)bh * dm.T + q) * (uint64_t)((dm.T + 1) & ~1ll) + kk) ? p * dk.scale : 0.f;
       Ps[warp * TILE + lane] = p;
       __syncwarp();
 #pragma unroll
@@ -179,7 +179,7 @@ attn_bwd_dq_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ k
         dp = fmaf(dOs[qi * dh + c], Vs[lane * ldk + c], dp);
       }
       float p = (valid && ls[i] != -INFINITY) ? expf(s - ls[i]) : 0.f;
-      if (drop) dp = drop_keep(dk, ((uint64_t)bh * dm.T + q) * dm.T + kk) ? dp * dk.scale : 0.f;
+      if (drop) dp = drop_keep(dk, ((uint64_t)bh * dm.T + q) * (uint64_t)((dm.T + 1) & ~1ll) + kk) ? dp * dk.scale : 0.f;
       const float ds = p * (dp - dl[i]);
       Ps[warp * TILE + lane] = ds;
       __syncwarp();
@@ -272,7 +272,7 @@ attn_bwd_dkv_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ 
       float p = qvalid ? expf(s - lq) : 0.f;
       float pd = p;
       if (drop) {
-        const bool keep = drop_keep(dk, ((uint64_t)bh * dm.T + q) * dm.T + kk);
+        const bool keep = drop_keep(dk, ((uint64_t)bh * dm.T + q) * (uint64_t)((dm.T + 1) & ~1ll) + kk);
         pd = keep ? p * dk.scale : 0.f;
         dp = keep ? dp * dk.scale : 0.f;
       }
@@ -316,7 +316,8 @@ int fwd_impl(const void* qkv, const uint8_t* key_mask, void* out, float* lse, in
              int64_t dh, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
   AttnDims dm{B, Tn, H, dh};
   size_t smem = (size_t)(2 * TILE * (dh + 1) + ROWS * dh + 4 * TILE) * sizeof(float);
-  cudaFuncSetAttribute(attn_fwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t cfg_fwd = 0;
+  if (smem > cfg_fwd) { cudaFuncSetAttribute(attn_fwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg_fwd = smem; }
   dim3 grid((unsigned)ceil_div(Tn, ROWS), (unsigned)(B * H));
   attn_fwd_simt_kernel<T><<<grid, 128, smem, st>>>((const T*)qkv, key_mask, (T*)out, lse, dm, p, rng, site);
   MAR_LAUNCH_CHECK("attn_fwd_simt");
@@ -336,14 +337,16 @@ int bwd_impl(const void* qkv, const uint8_t* key_mask, const void* out, const vo
   dim3 grid((unsigned)ceil_div(Tn, ROWS), (unsigned)(B * H));
   {
     size_t smem = (size_t)(2 * TILE * (dh + 1) + 2 * ROWS * dh + 4 * TILE) * sizeof(float);
-    cudaFuncSetAttribute(attn_bwd_dq_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t cfg_dq = 0;
+    if (smem > cfg_dq) { cudaFuncSetAttribute(attn_bwd_dq_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg_dq = smem; }
     attn_bwd_dq_simt_kernel<T><<<grid, 128, smem, st>>>((const T*)qkv, key_mask, (const T*)dout, lse, delta, (T*)dqkv, dm,
                                                         p, rng, site);
     MAR_LAUNCH_CHECK("attn_bwd_dq_simt");
   }
   {
     size_t smem = (size_t)(2 * TILE * (dh + 1) + 2 * ROWS * dh + 8 * TILE + 2 * TILE) * sizeof(float);
-    cudaFuncSetAttribute(attn_bwd_dkv_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t cfg_dkv = 0;
+    if (smem > cfg_dkv) { cudaFuncSetAttribute(attn_bwd_dkv_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg_dkv = smem; }
     attn_bwd_dkv_simt_kernel<T><<<grid, 128, smem, st>>>((const T*)qkv, key_mask, (const T*)dout, lse, delta, (T*)dqkv, dm,
                                                          p, rng, site);
     MAR_LAUNCH_CHECK("attn_bwd_dkv_simt");

@@ -179,8 +179,11 @@ int launch_bwd(const void* dy, const void* x, const float* mean, const float* rs
   size_t smem = (size_t)8 * D * sizeof(float);
 #define LN_BWD(N)                                                                                                 \
   do {                                                                                                            \
-    if (smem > 48 * 1024)                                                                                         \
-      cudaFuncSetAttribute(layernorm_bwd_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    static bool cfg = false;                                                                                      \
+    if (smem > 48 * 1024 && !cfg) {                                                                               \
+      cudaFuncSetAttribute(layernorm_bwd_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);   \
+      cfg = true;                                                                                                 \
+    }                                                                                                             \
     layernorm_bwd_kernel<T, N><<<(unsigned)blocks, 256, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, \
                                                                     (T*)dx, dgamma, dbeta, rows, (int)D);         \
   } while (0)

@@ -13,7 +13,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // ---- GRU ------------------------------------------------------------------------------------
 template <typename T>
 __global__ void gru_cell_fwd_kernel(const T* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ b_hh,
-                                    T* __restrict__ hseq, T* __restrict__ saved, int64_t B, int64_t Tn, int64_t H,
+                                    const float* __restrict__ h_in, float* __restrict__ h_out, T* __restrict__ hseq,
+                                    T* __restrict__ hprev, float* __restrict__ saved, int64_t B, int64_t Tn, int64_t H,
                                     int64_t t) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
@@ -24,31 +25,31 @@ __global__ void gru_cell_fwd_kernel(const T* __restrict__ gi, const float* __res
   else {
     const float* q = gh + b * 3 * H;
     ghr = q[j]; ghz = q[H + j]; ghn = q[2 * H + j];
-    hp = to_f32<T>(hseq[(b * Tn + t - 1) * H + j]);
+    hp = h_in[idx];                       // fp32 carry: only the GEMM operand is rounded to T
   }
   const float r = sigmoidf_(to_f32<T>(g[j]) + ghr);
   const float z = sigmoidf_(to_f32<T>(g[H + j]) + ghz);
   const float n = tanhf(to_f32<T>(g[2 * H + j]) + r * ghn);
   const float h = (1.f - z) * n + z * hp;
+  h_out[idx] = h;
   hseq[(b * Tn + t) * H + j] = from_f32<T>(h);
   if (saved != nullptr) {
-    T* s = saved + (b * Tn + t) * 5 * H;
-    s[j] = from_f32<T>(r); s[H + j] = from_f32<T>(z); s[2 * H + j] = from_f32<T>(n); s[3 * H + j] = from_f32<T>(ghn);
-    s[4 * H + j] = from_f32<T>(hp);
+    float* s = saved + (b * Tn + t) * 5 * H;
+    s[j] = r; s[H + j] = z; s[2 * H + j] = n; s[3 * H + j] = ghn; s[4 * H + j] = hp;
+    hprev[(b * Tn + t) * H + j] = from_f32<T>(hp);
   }
 }
 
 template <typename T>
 __global__ void gru_cell_bwd_kernel(const T* __restrict__ dhseq, const float* __restrict__ dh_carry,
-                                    const T* __restrict__ hseq, const T* __restrict__ saved, T* __restrict__ dgi,
+                                    const float* __restrict__ saved, T* __restrict__ dgi,
                                     T* __restrict__ dgh, float* __restrict__ dh_direct, int64_t B, int64_t Tn, int64_t H,
                                     int64_t t, int has_carry) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   const int64_t b = idx / H, j = idx % H;
-  const T* s = saved + (b * Tn + t) * 5 * H;
-  const float r = to_f32<T>(s[j]), z = to_f32<T>(s[H + j]), n = to_f32<T>(s[2 * H + j]), hn = to_f32<T>(s[3 * H + j]);
-  const float hp = to_f32<T>(s[4 * H + j]);
+  const float* s = saved + (b * Tn + t) * 5 * H;
+  const float r = s[j], z = s[H + j], n = s[2 * H + j], hn = s[3 * H + j], hp = s[4 * H + j];
   float dh = to_f32<T>(dhseq[(b * Tn + t) * H + j]);
   if (has_carry) dh += dh_carry[idx];
   const float dn_pre = dh * (1.f - z) * (1.f - n * n);
@@ -64,8 +65,8 @@ __global__ void gru_cell_bwd_kernel(const T* __restrict__ dhseq, const float* __
 // ---- LSTM -----------------------------------------------------------------------------------
 template <typename T>
 __global__ void lstm_cell_fwd_kernel(const T* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ b_hh,
-                                     T* __restrict__ hseq, T* __restrict__ saved, float* __restrict__ c_state, int64_t B,
-                                     int64_t Tn, int64_t H, int64_t t) {
+                                     T* __restrict__ hseq, T* __restrict__ hprev, float* __restrict__ saved,
+                                     float* __restrict__ c_state, int64_t B, int64_t Tn, int64_t H, int64_t t) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   const int64_t b = idx / H, j = idx % H;
@@ -80,24 +81,22 @@ __global__ void lstm_cell_fwd_kernel(const T* __restrict__ gi, const float* __re
   c_state[idx] = c;
   hseq[(b * Tn + t) * H + j] = from_f32<T>(o * tanhf(c));
   if (saved != nullptr) {
-    T* s = saved + (b * Tn + t) * 6 * H;
-    s[j] = from_f32<T>(i); s[H + j] = from_f32<T>(f); s[2 * H + j] = from_f32<T>(gg); s[3 * H + j] = from_f32<T>(o);
-    s[4 * H + j] = from_f32<T>(c);
-    s[5 * H + j] = t == 0 ? from_f32<T>(0.f) : hseq[(b * Tn + t - 1) * H + j];
+    float* s = saved + (b * Tn + t) * 5 * H;
+    s[j] = i; s[H + j] = f; s[2 * H + j] = gg; s[3 * H + j] = o; s[4 * H + j] = c;
+    hprev[(b * Tn + t) * H + j] = t == 0 ? from_f32<T>(0.f) : hseq[(b * Tn + t - 1) * H + j];
   }
 }
 
 template <typename T>
 __global__ void lstm_cell_bwd_kernel(const T* __restrict__ dhseq, const float* __restrict__ dh_carry,
-                                     float* __restrict__ dc_carry, const T* __restrict__ saved, T* __restrict__ dgates,
+                                     float* __restrict__ dc_carry, const float* __restrict__ saved, T* __restrict__ dgates,
                                      int64_t B, int64_t Tn, int64_t H, int64_t t, int has_carry) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   const int64_t b = idx / H, j = idx % H;
-  const T* s = saved + (b * Tn + t) * 6 * H;
-  const float i = to_f32<T>(s[j]), f = to_f32<T>(s[H + j]), g = to_f32<T>(s[2 * H + j]), o = to_f32<T>(s[3 * H + j]);
-  const float c = to_f32<T>(s[4 * H + j]);
-  const float cp = t > 0 ? to_f32<T>(saved[(b * Tn + t - 1) * 6 * H + 4 * H + j]) : 0.f;
+  const float* s = saved + (b * Tn + t) * 5 * H;
+  const float i = s[j], f = s[H + j], g = s[2 * H + j], o = s[3 * H + j], c = s[4 * H + j];
+  const float cp = t > 0 ? saved[(b * Tn + t - 1) * 5 * H + 4 * H + j] : 0.f;
   float dh = to_f32<T>(dhseq[(b * Tn + t) * H + j]);
   float dc = 0.f;
   if (has_carry) { dh += dh_carry[idx]; dc = dc_carry[idx]; }
@@ -112,9 +111,10 @@ __global__ void lstm_cell_bwd_kernel(const T* __restrict__ dhseq, const float* _
 }
 
 template <typename T>
-int gru_fwd_impl(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved, float* work, int64_t B,
-                 int64_t Tn, int64_t H, int dtype, cudaStream_t st) {
+int gru_fwd_impl(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, float* work,
+                 int64_t B, int64_t Tn, int64_t H, int dtype, cudaStream_t st) {
   const unsigned blocks = (unsigned)ceil_div(B * H, 256);
+  float* hbuf[2] = {work + B * 3 * H, work + B * 4 * H};    // fp32 h ping-pong
   for (int64_t t = 0; t < Tn; t++) {
     if (t > 0) {
       // gh (B,3H) fp32 = h_{t-1} (B,H; row stride T*H) · W_hhᵀ + b_hh
@@ -124,21 +124,22 @@ int gru_fwd_impl(const void* gi, const void* w_hh, const float* b_hh, void* hseq
                          MAR_F32, 3 * H, B, 3 * H, H, epi, st);
       if (rc) return rc;
     }
-    gru_cell_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T*)gi, work, b_hh, (T*)hseq, (T*)saved, B, Tn, H, t);
+    gru_cell_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T*)gi, work, b_hh, hbuf[(t + 1) & 1], hbuf[t & 1], (T*)hseq,
+                                                   (T*)hprev, saved, B, Tn, H, t);
     MAR_LAUNCH_CHECK("gru_cell_fwd");
   }
   return MAR_OK;
 }
 
 template <typename T>
-int gru_bwd_impl(const void* dhseq, const void* hseq, const void* saved, const void* w_hh, void* dgi, void* dgh,
+int gru_bwd_impl(const void* dhseq, const float* saved, const void* w_hh, void* dgi, void* dgh,
                  float* work, int64_t B, int64_t Tn, int64_t H, int dtype, cudaStream_t st) {
   const unsigned blocks = (unsigned)ceil_div(B * H, 256);
   float* dh_carry = work;          // (B,H)
   float* dh_direct = work + B * H; // (B,H)
   for (int64_t t = Tn - 1; t >= 0; t--) {
-    gru_cell_bwd_kernel<T><<<blocks, 256, 0, st>>>((const T*)dhseq, dh_carry, (const T*)hseq, (const T*)saved, (T*)dgi,
-                                                   (T*)dgh, dh_direct, B, Tn, H, t, t != Tn - 1);
+    gru_cell_bwd_kernel<T><<<blocks, 256, 0, st>>>((const T*)dhseq, dh_carry, saved, (T*)dgi, (T*)dgh, dh_direct, B, Tn,
+                                                   H, t, t != Tn - 1);
     MAR_LAUNCH_CHECK("gru_cell_bwd");
     if (t > 0) {
       // dh_carry (B,H) fp32 = dgh_t (B,3H; row stride T*3H) · W_hh (3H,H) + dh_direct
@@ -153,8 +154,8 @@ int gru_bwd_impl(const void* dhseq, const void* hseq, const void* saved, const v
 }
 
 template <typename T>
-int lstm_fwd_impl(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved, float* work, int64_t B,
-                  int64_t Tn, int64_t H, int dtype, cudaStream_t st) {
+int lstm_fwd_impl(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, float* work,
+                  int64_t B, int64_t Tn, int64_t H, int dtype, cudaStream_t st) {
   const unsigned blocks = (unsigned)ceil_div(B * H, 256);
   float* gh = work;                // (B,4H)
   float* c_state = work + B * 4 * H;  // (B,H)
@@ -166,21 +167,21 @@ int lstm_fwd_impl(const void* gi, const void* w_hh, const float* b_hh, void* hse
                          4 * H, B, 4 * H, H, epi, st);
       if (rc) return rc;
     }
-    lstm_cell_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T*)gi, gh, b_hh, (T*)hseq, (T*)saved, c_state, B, Tn, H, t);
+    lstm_cell_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T*)gi, gh, b_hh, (T*)hseq, (T*)hprev, saved, c_state, B, Tn, H, t);
     MAR_LAUNCH_CHECK("lstm_cell_fwd");
   }
   return MAR_OK;
 }
 
 template <typename T>
-int lstm_bwd_impl(const void* dhseq, const void* saved, const void* w_hh, void* dgates, float* work, int64_t B,
+int lstm_bwd_impl(const void* dhseq, const float* saved, const void* w_hh, void* dgates, float* work, int64_t B,
                   int64_t Tn, int64_t H, int dtype, cudaStream_t st) {
   const unsigned blocks = (unsigned)ceil_div(B * H, 256);
   float* dh_carry = work;
   float* dc_carry = work + B * H;
   for (int64_t t = Tn - 1; t >= 0; t--) {
-    lstm_cell_bwd_kernel<T><<<blocks, 256, 0, st>>>((const T*)dhseq, dh_carry, dc_carry, (const T*)saved, (T*)dgates, B,
-                                                    Tn, H, t, t != Tn - 1);
+    lstm_cell_bwd_kernel<T><<<blocks, 256, 0, st>>>((const T*)dhseq, dh_carry, dc_carry, saved, (T*)dgates, B, Tn, H, t,
+                                                    t != Tn - 1);
     MAR_LAUNCH_CHECK("lstm_cell_bwd");
     if (t > 0) {
       SimtEpilogue epi;
@@ -194,22 +195,22 @@ int lstm_bwd_impl(const void* dhseq, const void* saved, const void* w_hh, void* 
 
 }  // namespace
 
-int gru_fwd_steps(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved, float* work, int64_t B,
+int gru_fwd_steps(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, float* work,
+                  int64_t B, int64_t T, int64_t H, int dtype, cudaStream_t st) {
+  if (dtype == MAR_BF16) return gru_fwd_impl<bf16>(gi, w_hh, b_hh, hseq, hprev, saved, work, B, T, H, dtype, st);
+  return gru_fwd_impl<float>(gi, w_hh, b_hh, hseq, hprev, saved, work, B, T, H, dtype, st);
+}
+int gru_bwd_steps(const void* dhseq, const float* saved, const void* w_hh, void* dgi, void* dgh, float* work, int64_t B,
                   int64_t T, int64_t H, int dtype, cudaStream_t st) {
-  if (dtype == MAR_BF16) return gru_fwd_impl<bf16>(gi, w_hh, b_hh, hseq, saved, work, B, T, H, dtype, st);
-  return gru_fwd_impl<float>(gi, w_hh, b_hh, hseq, saved, work, B, T, H, dtype, st);
+  if (dtype == MAR_BF16) return gru_bwd_impl<bf16>(dhseq, saved, w_hh, dgi, dgh, work, B, T, H, dtype, st);
+  return gru_bwd_impl<float>(dhseq, saved, w_hh, dgi, dgh, work, B, T, H, dtype, st);
 }
-int gru_bwd_steps(const void* dhseq, const void* hseq, const void* saved, const void* w_hh, void* dgi, void* dgh,
-                  float* work, int64_t B, int64_t T, int64_t H, int dtype, cudaStream_t st) {
-  if (dtype == MAR_BF16) return gru_bwd_impl<bf16>(dhseq, hseq, saved, w_hh, dgi, dgh, work, B, T, H, dtype, st);
-  return gru_bwd_impl<float>(dhseq, hseq, saved, w_hh, dgi, dgh, work, B, T, H, dtype, st);
+int lstm_fwd_steps(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, float* work,
+                   int64_t B, int64_t T, int64_t H, int dtype, cudaStream_t st) {
+  if (dtype == MAR_BF16) return lstm_fwd_impl<bf16>(gi, w_hh, b_hh, hseq, hprev, saved, work, B, T, H, dtype, st);
+  return lstm_fwd_impl<float>(gi, w_hh, b_hh, hseq, hprev, saved, work, B, T, H, dtype, st);
 }
-int lstm_fwd_steps(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* saved, float* work, int64_t B,
-                   int64_t T, int64_t H, int dtype, cudaStream_t st) {
-  if (dtype == MAR_BF16) return lstm_fwd_impl<bf16>(gi, w_hh, b_hh, hseq, saved, work, B, T, H, dtype, st);
-  return lstm_fwd_impl<float>(gi, w_hh, b_hh, hseq, saved, work, B, T, H, dtype, st);
-}
-int lstm_bwd_steps(const void* dhseq, const void* saved, const void* w_hh, void* dgates, float* work, int64_t B,
+int lstm_bwd_steps(const void* dhseq, const float* saved, const void* w_hh, void* dgates, float* work, int64_t B,
                    int64_t T, int64_t H, int dtype, cudaStream_t st) {
   if (dtype == MAR_BF16) return lstm_bwd_impl<bf16>(dhseq, saved, w_hh, dgates, work, B, T, H, dtype, st);
   return lstm_bwd_impl<float>(dhseq, saved, w_hh, dgates, work, B, T, H, dtype, st);

@@ -242,12 +242,12 @@ def to_compute(x: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Te
 # --------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, flags, p, out_dtype):
+    def forward(ctx, x, weight, bias, residual, flags, p, out_dtype, need_dx):
         # x (M,K) compute dtype; weight (N,K) fp32 master; bias (N) fp32; residual (M,N) compute dtype
         M, K = x.shape
         N = weight.shape[0]
         cd = x.dtype
-        need_t = cd == torch.bfloat16 and (x.requires_grad or True)
+        need_t = cd == torch.bfloat16 and need_dx
         wc, wt = compute_weight(weight, cd, need_t)
         out = torch.empty((M, N), dtype=out_dtype, device=x.device)
         site = 0
@@ -305,7 +305,7 @@ class _Linear(torch.autograd.Function):
             call("mar_linear_wgrad", dz.data_ptr(), x.data_ptr(), x.stride(0), dw.data_ptr(), M, N, K, _dt(dz), 0,
                  ctx.eng, st)
         dres = dout if (ctx.has_res and needs_r) else None
-        return dx, dw, dbias, dres, None, None, None
+        return dx, dw, dbias, dres, None, None, None, None
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
@@ -318,7 +318,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     if residual is not None:
         r2 = _rows(to_compute(residual, x2.dtype))
     flags = (EPI_RELU_PRE if relu_pre else 0) | (EPI_DROPOUT if dropout_p > 0 else 0) | (EPI_RELU_POST if relu_post else 0)
-    out = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype)
+    need_dx = torch.is_grad_enabled() and x2.requires_grad
+    out = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype, need_dx)
     return out.view(*shape[:-1], weight.shape[0])
 
 
@@ -373,16 +374,15 @@ def attention(qkv: torch.Tensor, key_mask: Optional[torch.Tensor], num_heads: in
 # --------------------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, zero_rows):
+    def forward(ctx, x, gamma, beta, eps, zero_rows, need_grad):
         rows, D = x.shape
         y = torch.empty_like(x)
-        need_grad = x.requires_grad or gamma.requires_grad or beta.requires_grad
+        if zero_rows is not None and need_grad:
+            raise RuntimeError("layer_norm(zero_rows=...) is the eval-only nested-tensor zero fill; no backward")
         mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need_grad else None
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need_grad else None
         call("mar_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _p(mean), _p(rstd),
              _p(zero_rows), rows, D, float(eps), _dt(x), _stream())
-        if zero_rows is not None and need_grad:
-            raise RuntimeError("layer_norm(zero_rows=...) is the eval-only nested-tensor zero fill; no backward")
         ctx.save_for_backward(x, gamma, mean, rstd)
         return y
 
@@ -398,7 +398,7 @@ class _LayerNorm(torch.autograd.Function):
         dbeta = torch.zeros(D, dtype=torch.float32, device=x.device)
         call("mar_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
              dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D, _dt(x), _stream())
-        return dx, dgamma, dbeta, None, None
+        return dx, dgamma, dbeta, None, None, None
 
 
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
@@ -407,7 +407,8 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     x2 = to_compute(x).reshape(-1, shape[-1])
     g = gamma if gamma.dtype == torch.float32 else gamma.float()
     b = beta if beta.dtype == torch.float32 else beta.float()
-    return _LayerNorm.apply(x2, g, b, eps, zero_rows).view(shape)
+    need_grad = torch.is_grad_enabled() and (x2.requires_grad or g.requires_grad or b.requires_grad)
+    return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad).view(shape)
 
 
 # --------------------------------------------------------------------------------------
@@ -550,29 +551,30 @@ def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 class _GRU(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gi, w_hh, b_hh):
+    def forward(ctx, gi, w_hh, b_hh, need_grad):
         B, T, H3 = gi.shape
         H = H3 // 3
         cd = gi.dtype
         wc, _ = compute_weight(w_hh, cd, False)
-        need_grad = gi.requires_grad or w_hh.requires_grad or b_hh.requires_grad
         hseq = torch.empty((B, T, H), dtype=cd, device=gi.device)
-        saved = torch.empty((B, T, 5 * H), dtype=cd, device=gi.device) if need_grad else None
+        saved = torch.empty((B, T, 5 * H), dtype=torch.float32, device=gi.device) if need_grad else None
+        hprev = torch.empty((B, T, H), dtype=cd, device=gi.device) if need_grad else None
         work = torch.empty(B * 5 * H, dtype=torch.float32, device=gi.device)
         b32 = b_hh.detach().float().contiguous()
-        call("mar_gru_fwd", gi.data_ptr(), wc.data_ptr(), b32.data_ptr(), hseq.data_ptr(), _p(saved), work.data_ptr(),
-             B, T, H, _dt(gi), _eng(), _stream())
+        call("mar_gru_fwd", gi.data_ptr(), wc.data_ptr(), b32.data_ptr(), hseq.data_ptr(), _p(hprev), _p(saved),
+             work.data_ptr(), B, T, H, _dt(gi), _eng(), _stream())
         ctx.dims = (B, T, H)
         ctx.wc = wc
         ctx.eng = _eng()
-        ctx.save_for_backward(hseq, saved)
+        ctx.save_for_backward(hprev, saved)
         return hseq
 
     @staticmethod
     def backward(ctx, dhseq):
-        hseq, saved = ctx.saved_tensors
+        hprev, saved = ctx.saved_tensors
         B, T, H = ctx.dims
-        cd = hseq.dtype
+        cd = hprev.dtype
+        hseq = hprev
         st = _stream()
         if dhseq.dtype != cd:
             dhseq = _Cast.apply(dhseq, cd)
@@ -580,49 +582,49 @@ class _GRU(torch.autograd.Function):
         dgi = torch.empty((B, T, 3 * H), dtype=cd, device=hseq.device)
         dgh = torch.empty((B, T, 3 * H), dtype=cd, device=hseq.device)
         work = torch.empty(B * 5 * H, dtype=torch.float32, device=hseq.device)
-        call("mar_gru_bwd", dhseq.data_ptr(), hseq.data_ptr(), saved.data_ptr(), ctx.wc.data_ptr(), dgi.data_ptr(),
+        call("mar_gru_bwd", dhseq.data_ptr(), saved.data_ptr(), ctx.wc.data_ptr(), dgi.data_ptr(),
              dgh.data_ptr(), work.data_ptr(), B, T, H, _dt(hseq), ctx.eng, st)
         dw = torch.empty((3 * H, H), dtype=torch.float32, device=hseq.device)
-        hprev = saved.view(B * T, 5 * H)[:, 4 * H:]
-        call("mar_linear_wgrad", dgh.data_ptr(), hprev.data_ptr(), 5 * H, dw.data_ptr(), B * T, 3 * H, H, _dt(dgh), 0,
+        call("mar_linear_wgrad", dgh.data_ptr(), hprev.data_ptr(), H, dw.data_ptr(), B * T, 3 * H, H, _dt(dgh), 0,
              ctx.eng, st)
         db = torch.zeros(3 * H, dtype=torch.float32, device=hseq.device)
         call("mar_linear_bwd_epilogue", dgh.data_ptr(), None, None, db.data_ptr(), B * T, 3 * H, _dt(dgh), _dt(dgh), 0,
              0.0, None, 0, st)
-        return dgi, dw, db
+        return dgi, dw, db, None
 
 
 def gru(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh) -> torch.Tensor:
     """1-layer batch_first GRU with h0 = 0 → (B,T,H) (nn.GRU as used at models.py:110,122)."""
     gi = linear(x, w_ih, b_ih)
-    return _GRU.apply(gi.contiguous(), w_hh, b_hh)
+    need = torch.is_grad_enabled() and (gi.requires_grad or w_hh.requires_grad or b_hh.requires_grad)
+    return _GRU.apply(gi.contiguous(), w_hh, b_hh, need)
 
 
 class _LSTM(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gi, w_hh, b_hh):
+    def forward(ctx, gi, w_hh, b_hh, need_grad):
         B, T, H4 = gi.shape
         H = H4 // 4
         cd = gi.dtype
         wc, _ = compute_weight(w_hh, cd, False)
-        need_grad = gi.requires_grad or w_hh.requires_grad or b_hh.requires_grad
         hseq = torch.empty((B, T, H), dtype=cd, device=gi.device)
-        saved = torch.empty((B, T, 6 * H), dtype=cd, device=gi.device) if need_grad else None
+        saved = torch.empty((B, T, 5 * H), dtype=torch.float32, device=gi.device) if need_grad else None
+        hprev = torch.empty((B, T, H), dtype=cd, device=gi.device) if need_grad else None
         work = torch.empty(B * 5 * H, dtype=torch.float32, device=gi.device)
         b32 = b_hh.detach().float().contiguous()
-        call("mar_lstm_fwd", gi.data_ptr(), wc.data_ptr(), b32.data_ptr(), hseq.data_ptr(), _p(saved), work.data_ptr(),
-             B, T, H, _dt(gi), _eng(), _stream())
+        call("mar_lstm_fwd", gi.data_ptr(), wc.data_ptr(), b32.data_ptr(), hseq.data_ptr(), _p(hprev), _p(saved),
+             work.data_ptr(), B, T, H, _dt(gi), _eng(), _stream())
         ctx.dims = (B, T, H)
         ctx.wc = wc
         ctx.eng = _eng()
-        ctx.save_for_backward(saved)
+        ctx.save_for_backward(hprev, saved)
         return hseq
 
     @staticmethod
     def backward(ctx, dhseq):
-        (saved,) = ctx.saved_tensors
+        hprev, saved = ctx.saved_tensors
         B, T, H = ctx.dims
-        cd = saved.dtype
+        cd = hprev.dtype
         st = _stream()
         if dhseq.dtype != cd:
             dhseq = _Cast.apply(dhseq, cd)
@@ -630,18 +632,18 @@ class _LSTM(torch.autograd.Function):
         dg = torch.empty((B, T, 4 * H), dtype=cd, device=saved.device)
         work = torch.empty(B * 2 * H, dtype=torch.float32, device=saved.device)
         call("mar_lstm_bwd", dhseq.data_ptr(), saved.data_ptr(), ctx.wc.data_ptr(), dg.data_ptr(), work.data_ptr(),
-             B, T, H, _dt(saved), ctx.eng, st)
+             B, T, H, _dt(hprev), ctx.eng, st)
         dw = torch.empty((4 * H, H), dtype=torch.float32, device=saved.device)
-        hprev = saved.view(B * T, 6 * H)[:, 5 * H:]
-        call("mar_linear_wgrad", dg.data_ptr(), hprev.data_ptr(), 6 * H, dw.data_ptr(), B * T, 4 * H, H, _dt(dg), 0,
+        call("mar_linear_wgrad", dg.data_ptr(), hprev.data_ptr(), H, dw.data_ptr(), B * T, 4 * H, H, _dt(dg), 0,
              ctx.eng, st)
         db = torch.zeros(4 * H, dtype=torch.float32, device=saved.device)
         call("mar_linear_bwd_epilogue", dg.data_ptr(), None, None, db.data_ptr(), B * T, 4 * H, _dt(dg), _dt(dg), 0,
              0.0, None, 0, st)
-        return dg, dw, db
+        return dg, dw, db, None
 
 
 def lstm(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh) -> torch.Tensor:
     """1-layer batch_first LSTM with (h0,c0) = 0 → (B,T,H) (train_video_rnn.py:94-106)."""
     gi = linear(x, w_ih, b_ih)
-    return _LSTM.apply(gi.contiguous(), w_hh, b_hh)
+    need = torch.is_grad_enabled() and (gi.requires_grad or w_hh.requires_grad or b_hh.requires_grad)
+    return _LSTM.apply(gi.contiguous(), w_hh, b_hh, need)

@@ -1,0 +1,288 @@
+"""Step driver for the hot path: flat parameter/gradient buffers, one fused Adam launch, bucketed gradient
+all-reduce overlapped with backward (data parallel, one process per GPU), and optional whole-step CUDA-graph
+capture.  This is the sync-free equivalent of `TorchSupervisedTrainer.train_step` (trainer.py:110-163):
+zero_grad → model(data) → criterion → loss.backward() → optimizer.step(), without the per-step `.item()` /
+`.cpu()` host syncs (trainer.py:731-737, :718-729) — losses and predictions stay on the device until asked for.
+
+The reference has no distributed code; data parallelism is this repo's addition (§8e):
+every op on the path is per-clip, so the batch shards across ranks and the only exchange is the parameter
+gradient all-reduce (NCCL over NVLink; gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+from ._lib import call
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class FlatParams:
+    """Moves a model's parameters into ONE contiguous fp32 buffer (params become views, state_dict keys and
+    shapes are unchanged) and gives every parameter a persistent .grad view into ONE flat gradient buffer."""
+
+    def __init__(self, params: Sequence[nn.Parameter], align: int = 64):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev = self.params[0].device
+        self.offsets, off = [], 0
+        for p in self.params:
+            assert p.dtype == torch.float32 and p.device == dev
+            self.offsets.append(off)
+            off += (p.numel() + align - 1) // align * align
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                self.flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
+                p.data = self.flat[o:o + p.numel()].view(p.shape)
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):       # re-attach if something set .grad = None
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+class FlatAdam:
+    """torch.optim.Adam defaults (train_multimodal.py:444: lr 1e-3, betas (0.9, 0.999), eps 1e-8, no weight
+    decay) as ONE kernel launch over the flat buffers; the step counter lives on the device so the update is
+    CUDA-graph capturable.  Deviation from torch: parameters that received no gradient this step still see an
+    update from their running moments (torch skips params whose .grad is None); with a zero gradient and zero
+    moments that update is exactly 0, so it only differs once a head has trained and is then inactive."""
+
+    def __init__(self, flat: FlatParams, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.flat, self.lr, self.betas, self.eps = flat, lr, betas, eps
+        self.exp_avg = torch.zeros_like(flat.flat)
+        self.exp_avg_sq = torch.zeros_like(flat.flat)
+        self.step_dev = torch.zeros(1, dtype=torch.float32, device=flat.flat.device)
+
+    def step(self) -> None:
+        f = self.flat
+        if f.flat.is_cuda:
+            st = _stream()
+            call("mar_adam_tick", self.step_dev.data_ptr(), st)
+            call("mar_adam_step", f.flat.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
+                 self.exp_avg_sq.data_ptr(), self.step_dev.data_ptr(), f.numel, self.lr, self.betas[0], self.betas[1],
+                 self.eps, st)
+        else:  # host-side logic tests (gloo, no GPU): same arithmetic in torch
+            self.step_dev += 1
+            t = float(self.step_dev)
+            b1, b2 = self.betas
+            self.exp_avg.mul_(b1).add_(f.grad, alpha=1 - b1)
+            self.exp_avg_sq.mul_(b2).addcmul_(f.grad, f.grad, value=1 - b2)
+            denom = (self.exp_avg_sq.sqrt() / (1 - b2 ** t) ** 0.5).add_(self.eps)
+            f.flat.addcdiv_(self.exp_avg, denom, value=-self.lr / (1 - b1 ** t))
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.flat.zero_grad()
+
+
+class GradSync:
+    """Bucketed gradient all-reduce (mean over ranks) over slices of the flat gradient buffer, launched from
+    post-accumulate-grad hooks as soon as every parameter of a bucket has its gradient, on a side stream so the
+    exchange overlaps the rest of backward.  Buckets are contiguous slices taken from the END of the buffer
+    (backward produces gradients in roughly reverse parameter order).  `finish()` reduces whatever did not fire
+    (parameters of a head that was inactive in this batch keep zero gradients but are reduced all the same, so
+    ranks never diverge) and makes the compute stream wait for the exchange."""
+
+    def __init__(self, flat: FlatParams, group=None, num_buckets: int = 4):
+        self.flat = flat
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.cuda = flat.grad.is_cuda
+        self.comm_stream = torch.cuda.Stream() if (self.cuda and self.world > 1) else None
+        n = len(flat.params)
+        total = flat.numel
+        # split by element count, aligned to parameter boundaries
+        bounds, target, acc = [n], total / max(1, num_buckets), 0
+        for i in range(n - 1, -1, -1):
+            acc += flat.params[i].numel()
+            if acc >= target and i > 0:
+                bounds.append(i)
+                acc = 0
+        bounds.append(0)
+        self.buckets = []           # (param index range [lo, hi), element range [e0, e1))
+        for hi, lo in zip(bounds[:-1], bounds[1:]):
+            if lo < hi:
+                e0 = flat.offsets[lo]
+                e1 = flat.offsets[hi] if hi < n else total
+                self.buckets.append((lo, hi, e0, e1))
+        self.bucket_of = {}
+        for b, (lo, hi, _, _) in enumerate(self.buckets):
+            for i in range(lo, hi):
+                self.bucket_of[i] = b
+        self.pending = [0] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
+        self.handles = []
+        self.order: List[int] = []
+        if self.world > 1:
+            for i, p in enumerate(flat.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+        self.reset()
+
+    def reset(self) -> None:
+        for b, (lo, hi, _, _) in enumerate(self.buckets):
+            self.pending[b] = hi - lo
+            self.launched[b] = False
+        self.handles = []
+        self.order = []
+
+    def _make_hook(self, i: int) -> Callable:
+        def hook(_param):
+            b = self.bucket_of[i]
+            self.pending[b] -= 1
+            if self.pending[b] == 0 and not self.launched[b]:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b: int) -> None:
+        self.launched[b] = True
+        self.order.append(b)
+        _, _, e0, e1 = self.buckets[b]
+        view = self.flat.grad[e0:e1]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+            view.div_(self.world)
+
+    def finish(self) -> None:
+        if self.world > 1:
+            for b in range(len(self.buckets)):
+                if not self.launched[b]:
+                    self._launch(b)
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.reset()
+
+
+class TrainStep:
+    """One optimizer step of the hot path as a single call:  losses = step(data, labels).
+
+    model(data) → criterion(pred, labels) → LossesDict.backward() → gradient all-reduce (if world > 1) → Adam.
+    Returns the dict of per-head losses as 0-d DEVICE tensors (no host sync).  With `graph=True` (single GPU)
+    the whole step is captured into a CUDA graph on first use and replayed afterwards: inputs are copied into
+    static buffers (H2D directly from pinned host memory when given CPU tensors), dropout masks advance on the
+    device, ~250 kernel launches collapse into one graph launch."""
+
+    def __init__(self, model: nn.Module, criterion: Callable, lr: float = 1e-3, graph: bool = False,
+                 group=None, num_buckets: int = 4, precision: Optional[str] = None):
+        self.model, self.criterion = model, criterion
+        self.flat = FlatParams(list(model.parameters()))
+        self.opt = FlatAdam(self.flat, lr=lr)
+        self.sync = GradSync(self.flat, group=group, num_buckets=num_buckets)
+        self.use_graph = graph and self.sync.world == 1
+        self.precision = precision
+        self._graph = None
+        self._static_in = None
+        self._static_out = None
+        self._warm = 0
+        self.captured_launches = 0
+        self.last_pred = None
+
+    # -- helpers ------------------------------------------------------------------------------
+    @staticmethod
+    def _tensors(batch) -> List[torch.Tensor]:
+        out = []
+        def walk(x):
+            if isinstance(x, torch.Tensor):
+                out.append(x)
+            elif isinstance(x, (list, tuple)) and not (x and isinstance(x[0], str)):
+                for y in x:
+                    walk(y)
+        walk(batch)
+        return out
+
+    @staticmethod
+    def _like(batch, tensors):
+        it = iter(tensors)
+        def walk(x):
+            if isinstance(x, torch.Tensor):
+                return next(it)
+            if isinstance(x, (list, tuple)) and not (x and isinstance(x[0], str)):
+                return [walk(y) for y in x]
+            return x
+        return walk(batch)
+
+    def _eager(self, data, labels):
+        self.opt.zero_grad()
+        if self.flat.flat.is_cuda:
+            ops.rng_advance(self.flat.flat.device)
+        pred = self.model(data)
+        losses = self.criterion(pred, labels)
+        if hasattr(losses, "backward") and not isinstance(losses, torch.Tensor):
+            losses.backward()
+        else:
+            losses.backward()
+            losses = {"loss": losses}
+        self.sync.finish()
+        self.opt.step()
+        self.last_pred = pred
+        return {k: v.detach() for k, v in losses.items()}
+
+    def __call__(self, data, labels):
+        ctx = ops.precision(self.precision) if self.precision else _null()
+        with ctx:
+            if not self.use_graph:
+                dev = self.flat.flat.device
+                if dev.type == "cuda":
+                    data = self._to_dev(data, dev)
+                    labels = self._to_dev(labels, dev)
+                return self._eager(data, labels)
+            return self._graphed(data, labels)
+
+    @staticmethod
+    def _to_dev(batch, dev):
+        def walk(x):
+            if isinstance(x, torch.Tensor):
+                return x.to(dev, non_blocking=True)
+            if isinstance(x, (list, tuple)) and not (x and isinstance(x[0], str)):
+                return [walk(y) for y in x]
+            return x
+        return walk(batch)
+
+    def _graphed(self, data, labels):
+        dev = self.flat.flat.device
+        src = self._tensors([data, labels])
+        if self._static_in is None:
+            self._static_in = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in src]
+        for s, t in zip(self._static_in, src):
+            s.copy_(t, non_blocking=True)
+        sdata, slabels = self._like([data, labels], self._static_in)
+        if self._graph is None:
+            if self._warm < 3:                      # eager warm-up steps on a side stream before capture
+                self._warm += 1
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    out = self._eager(sdata, slabels)
+                torch.cuda.current_stream().wait_stream(side)
+                return out
+            ops.clear_weight_cache()
+            g = torch.cuda.CUDAGraph()
+            before = ops.launch_count()
+            with torch.cuda.graph(g):
+                self._static_out = self._eager(sdata, slabels)
+            self.captured_launches = ops.launch_count() - before   # libmar kernels per replay
+            self._graph = g                         # capture records but does not execute: fall through to replay
+        self._graph.replay()
+        return self._static_out
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) GPU; run with -m gpu on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import torch
+    path = os.path.join(ROOT, "tests", "golden", "golden_v1.pt")
+    return torch.load(path, weights_only=False)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The C-ABI library is built in-tree (git-ignored, shipped to the GPU box).  Build it if absent so the
+    CPU suite can check that it loads and exports the header's symbols."""
+    lib = os.path.join(ROOT, "multimodalaggressionrecognition_b200", "libmar.so")
+    if not os.path.exists(lib):
+        import __graft_entry__ as g
+        g.build()
+    yield

@@ -1,0 +1,352 @@
+"""GPU: every kernel through the C ABI against the CPU oracle's primitive of the same op.
+
+Tolerances (BASELINE.json north_star): fp32 mode 1e-4; bf16 mode ~1e-2 relative against fp32
+(measured as ||a-b||/||b||; written in tests/helpers.py)."""
+import math
+
+import pytest
+import torch
+
+import multimodalaggressionrecognition_b200 as mar
+from multimodalaggressionrecognition_b200 import ops
+from oracle import oracle as O
+from tests.helpers import BF16_TOL, FP32_TOL, assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(0)
+    O.DROPOUT_ENABLED = False
+    yield
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+# ------------------------------------------------------------------------------------------
+# linear: forward / dgrad / wgrad, all engines
+# ------------------------------------------------------------------------------------------
+LINEAR_SHAPES = [(128, 256, 64), (200, 768, 768), (1000, 2304, 768), (333, 768, 2048), (64, 2, 256), (37, 256, 512),
+                 (4096, 1536, 512), (256, 512, 1536), (130, 72, 136)]
+
+
+def _linear_ref(x, w, b, res, relu_pre, relu_post):
+    y = O.linear(x, w, b)
+    if relu_pre or relu_post:
+        y = O.relu(y)
+    if res is not None:
+        y = y + res
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", LINEAR_SHAPES)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_linear_fwd_bwd(M, N, K, mode):
+    x = torch.randn(M, K)
+    w = torch.randn(N, K) / math.sqrt(K)
+    b = torch.randn(N)
+    res = torch.randn(M, N)
+    gy = torch.randn(M, N)
+    if mode == "bf16":
+        x, res, gy = bf16_round(x), bf16_round(res), bf16_round(gy)
+    tol = FP32_TOL if mode == "fp32" else BF16_TOL
+    for relu_pre, use_res in ((False, False), (True, False), (False, True)):
+        xr, wr, br = x.clone().requires_grad_(True), (bf16_round(w) if mode == "bf16" else w.clone()).requires_grad_(True), b.clone().requires_grad_(True)
+        rr = res.clone().requires_grad_(True) if use_res else None
+        yr = _linear_ref(xr, wr, br, rr, relu_pre, False)
+        yr.backward(gy)
+        xg = x.to(DEV).requires_grad_(True)
+        wg = w.to(DEV).requires_grad_(True)
+        bg = b.to(DEV).requires_grad_(True)
+        rg = res.to(DEV).requires_grad_(True) if use_res else None
+        with mar.precision(mode):
+            y = ops.linear(xg, wg, bg, residual=rg, relu_pre=relu_pre)
+            y.backward(gy.to(DEV).to(y.dtype))
+        what = f"linear {mode} M={M} N={N} K={K} relu={relu_pre} res={use_res}"
+        assert_close(y.float().cpu(), yr, tol, what + " y")
+        assert_close(xg.grad.cpu(), xr.grad, tol, what + " dx")
+        assert_close(wg.grad.cpu(), wr.grad, tol, what + " dw")
+        assert_close(bg.grad.cpu(), br.grad, tol, what + " db")
+        if use_res:
+            assert_close(rg.grad.cpu(), gy, 1e-6, what + " dres")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 128), (200, 768, 768), (8000, 2304, 768), (1024, 768, 2048),
+                                   (130, 72, 136), (4096, 1536, 512), (640, 2048, 768)])
+def test_tcgen05_gemm_engine(M, N, K):
+    """The tcgen05/TMA kernel specifically (engine='tensor' raises if it cannot run): fwd, dgrad, wgrad
+    against an fp32 matmul of the same bf16 operands."""
+    x = bf16_round(torch.randn(M, K))
+    w = bf16_round(torch.randn(N, K) / math.sqrt(K))
+    b = torch.randn(N)
+    gy = bf16_round(torch.randn(M, N))
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = O.linear(xr, wr, br)
+    yr.backward(gy)
+    xg, wg, bg = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    with mar.precision("bf16"), mar.engine("tensor"):
+        y = ops.linear(xg, wg, bg)
+        assert ops.last_engine() == "tensor"
+        y.backward(gy.to(DEV).to(y.dtype))
+    assert_close(y.float().cpu(), yr, 4e-3, "tcgen05 fwd")          # one bf16 rounding of the output
+    assert_close(xg.grad.cpu(), xr.grad, 4e-3, "tcgen05 dgrad")
+    assert_close(wg.grad.cpu(), wr.grad, 1e-4, "tcgen05 wgrad (fp32 out)")
+    assert_close(bg.grad.cpu(), br.grad, 1e-4, "bias grad")
+
+
+def test_tcgen05_matches_simt_bitwise_dropout_mask():
+    """Both GEMM engines draw the same dropout mask (same counter-hash function), forward and backward."""
+    M, N, K = 512, 768, 256
+    x = bf16_round(torch.randn(M, K)).to(DEV)
+    w = (torch.randn(N, K) / math.sqrt(K)).to(DEV)
+    outs = {}
+    for eng in ("simt", "tensor"):
+        ops.manual_seed(123)
+        with mar.precision("bf16"), mar.engine(eng):
+            outs[eng] = ops.linear(x, w, None, dropout_p=0.3).float()
+    za, zb = outs["simt"] == 0, outs["tensor"] == 0
+    assert torch.equal(za, zb)
+    frac = float(za.float().mean())
+    assert abs(frac - 0.3) < 0.01
+    assert_close(outs["tensor"], outs["simt"], 4e-3, "dropout epilogue values")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_linear_dropout_backward_uses_same_mask(mode):
+    M, N, K = 256, 512, 128
+    x = torch.randn(M, K, device=DEV, requires_grad=True)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).requires_grad_(True)
+    for kw in (dict(relu_pre=True, dropout_p=0.5), dict(dropout_p=0.3, relu_post=True), dict(dropout_p=0.1)):
+        with mar.precision(mode):
+            y = ops.linear(x, w, None, **kw)
+            (gx,) = torch.autograd.grad(y.float().sum(), x, retain_graph=False)
+        # d(sum y)/dx = mask_scale @ W  => recompute from the observed zero pattern of y
+        p = kw["dropout_p"]
+        if kw.get("relu_pre") or kw.get("relu_post"):
+            f = (y != 0).float() / (1 - p)
+        else:
+            f = (y != 0).float() / (1 - p)       # y == 0 exactly only where dropped (measure-zero otherwise)
+        wq = w.detach().to(y.dtype).float()
+        expect = f @ wq
+        assert_close(gx.float(), expect, FP32_TOL if mode == "fp32" else BF16_TOL, f"dropout bwd {kw}")
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+def _attn_ref(qkv, mask, H):
+    B, T, d3 = qkv.shape
+    d = d3 // 3
+    dh = d // H
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    sp = lambda t: t.reshape(B, T, H, dh).permute(0, 2, 1, 3)
+    s = torch.matmul(sp(q), sp(k).transpose(-1, -2)) / math.sqrt(dh)
+    if mask is not None:
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    p = O.softmax_lastdim_safe(s)
+    return torch.matmul(p, sp(v)).permute(0, 2, 1, 3).reshape(B, T, d)
+
+
+@pytest.mark.parametrize("B,T,H,dh", [(2, 50, 8, 96), (3, 37, 4, 64), (2, 130, 2, 32), (1, 314, 8, 96), (2, 64, 8, 96), (2, 33, 1, 128)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_attention_fwd_bwd(B, T, H, dh, mode, masked):
+    d = H * dh
+    qkv = torch.randn(B, T, 3 * d)
+    go = torch.randn(B, T, d)
+    if mode == "bf16":
+        qkv, go = bf16_round(qkv), bf16_round(go)
+    mask = None
+    if masked:
+        mask = torch.rand(B, T) < 0.3
+        mask[0, : T // 2] = False
+        mask[-1, T // 3:] = True          # a long masked tail
+    qr = qkv.clone().requires_grad_(True)
+    outr = _attn_ref(qr, mask, H)
+    outr.backward(go)
+    qg = qkv.to(DEV).requires_grad_(True)
+    with mar.precision(mode):
+        out = ops.attention(qg, None if mask is None else mask.to(DEV), H, 0.0)
+        out.backward(go.to(DEV).to(out.dtype))
+    tol = FP32_TOL if mode == "fp32" else BF16_TOL
+    assert_close(out.float().cpu(), outr, tol, "attention out")
+    assert_close(qg.grad.float().cpu(), qr.grad, tol, "attention dqkv")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_attention_fully_masked_rows_give_zero(mode):
+    """All keys masked (all-EMPTY batch): P = 0, O = 0, finite grads (torch 2.11 safe softmax)."""
+    B, T, H, dh = 2, 40, 8, 96
+    qkv = torch.randn(B, T, 3 * H * dh, device=DEV, requires_grad=True)
+    mask = torch.zeros(B, T, dtype=torch.bool, device=DEV)
+    mask[1] = True
+    with mar.precision(mode):
+        out = ops.attention(qkv, mask, H, 0.0)
+        out.float().sum().backward()
+    assert torch.isfinite(out).all() and torch.isfinite(qkv.grad).all()
+    assert float(out[1].abs().max()) == 0.0
+    assert float(qkv.grad[1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_attention_dropout_statistics_and_grad_consistency(mode):
+    """With V = 1 the output is rowsum(P~) whose mean is 1; d(sum O)/dV = P~ᵀ·1 shares the forward mask."""
+    B, T, H, dh = 2, 128, 4, 64
+    d = H * dh
+    qkv = torch.randn(B, T, 3 * d, device=DEV)
+    qkv[..., 2 * d:] = 1.0
+    qkv.requires_grad_(True)
+    with mar.precision(mode):
+        out = ops.attention(qkv, None, H, 0.25)
+        out.float().sum().backward()
+    o = out.float()
+    assert abs(float(o.mean()) - 1.0) < 0.02
+    assert float(o.std()) > 0.01                       # masks are actually applied
+    # column sums of P~ (via dV) must add up to the row sums of P~ (via O)
+    dv = qkv.grad[..., 2 * d:].float()                 # (B,T,d): dV[k, c] = Σ_q P~[q,k]
+    total_from_dv = dv.reshape(B, T, H, dh)[..., 0].sum(dim=1)      # (B,H)
+    total_from_o = o.reshape(B, T, H, dh)[..., 0].sum(dim=1)
+    assert_close(total_from_dv, total_from_o, 2e-2 if mode == "bf16" else 1e-4, "dropout mask fwd/bwd consistency")
+
+
+# ------------------------------------------------------------------------------------------
+# layer norm / pooling / masks / concat / loss / adam
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,D", [(100, 768), (7, 512), (1000, 1280), (33, 64), (64, 2048)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_layernorm(rows, D, mode):
+    x = torch.randn(rows, D) * 2 + 0.5
+    g, b, gy = torch.randn(D), torch.randn(D), torch.randn(rows, D)
+    if mode == "bf16":
+        x, gy = bf16_round(x), bf16_round(gy)
+    xr, gr, br = x.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = O.layer_norm(xr, gr, br)
+    yr.backward(gy)
+    xg, gg, bg = x.to(DEV).requires_grad_(True), g.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    with mar.precision(mode):
+        y = ops.layer_norm(xg, gg, bg)
+        y.backward(gy.to(DEV).to(y.dtype))
+    tol = FP32_TOL if mode == "fp32" else BF16_TOL
+    assert_close(y.float().cpu(), yr, tol, "ln y")
+    assert_close(xg.grad.float().cpu(), xr.grad, tol, "ln dx")
+    assert_close(gg.grad.cpu(), gr.grad, tol, "ln dgamma")
+    assert_close(bg.grad.cpu(), br.grad, tol, "ln dbeta")
+
+
+def test_layernorm_zero_rows_is_beta():
+    x = torch.randn(10, 768, device=DEV)
+    g, b = torch.randn(768, device=DEV), torch.randn(768, device=DEV)
+    z = torch.zeros(10, dtype=torch.uint8, device=DEV)
+    z[3] = 1
+    with mar.precision("fp32"), torch.no_grad():
+        y = ops.layer_norm(x, g, b, zero_rows=z)
+    assert_close(y[3], b, 1e-6, "LN(0) = beta")
+    assert_close(y[4].cpu(), O.layer_norm(x[4].cpu(), g.cpu(), b.cpu()), 1e-5, "other rows untouched")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_meanpool_rowzero_concat(mode):
+    B, T, D = 5, 37, 768
+    x = torch.randn(B, T, D)
+    if mode == "bf16":
+        x = bf16_round(x)
+    x[1, 5] = 0.0
+    x[4, 36] = 0.0
+    xg = x.to(DEV).requires_grad_(True)
+    with mar.precision(mode):
+        m = ops.mean_pool(xg)
+        m.float().sum().backward()
+        mask = ops.rowzero_mask(xg.detach())
+    assert_close(m.float().cpu(), x.mean(dim=1), FP32_TOL if mode == "fp32" else 4e-3, "mean_pool")
+    assert_close(xg.grad.float().cpu(), torch.full_like(x, 1.0 / T), 4e-3, "mean_pool bwd")
+    assert torch.equal(mask.cpu().bool(), x.sum(dim=2) == 0)
+    y = torch.randn(B, 11, D)
+    if mode == "bf16":
+        y = bf16_round(y)
+    yg = y.to(DEV).requires_grad_(True)
+    with mar.precision(mode):
+        cat = ops.concat_time([xg, yg])
+        sl = ops.slice_time(cat, T, T + 11)
+        (sl.float() * 2).sum().backward()
+    assert torch.equal(cat.float().cpu(), torch.cat([x, y], dim=1))
+    assert torch.equal(sl.float().cpu(), y)
+    assert float((yg.grad.float() - 2).abs().max()) == 0.0
+
+
+def test_cross_entropy_weighted_and_ignored():
+    B, C = 37, 2
+    logits = torch.randn(B, C)
+    labels = torch.randint(0, C, (B,))
+    w = torch.tensor([0.3, 1.7])
+    lr = logits.clone().requires_grad_(True)
+    ref = O.cross_entropy(lr, labels, w)
+    ref.backward()
+    lg = logits.to(DEV).requires_grad_(True)
+    loss = ops.cross_entropy(lg, labels.to(DEV), w.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < 1e-6
+    assert_close(lg.grad.cpu(), lr.grad, 1e-5, "CE grad")
+    # ignored rows (label -1 = EMPTY)
+    keep = torch.rand(B) < 0.6
+    lab2 = labels.masked_fill(~keep, -1)
+    ref2 = O.cross_entropy(logits[keep], labels[keep])
+    got2 = ops.cross_entropy(logits.to(DEV), lab2.to(DEV))
+    assert abs(float(got2) - float(ref2)) < 1e-6
+    assert torch.equal(ops.argmax_rows(logits.to(DEV)).cpu(), logits.argmax(dim=1))
+
+
+# ------------------------------------------------------------------------------------------
+# recurrences
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["gru", "lstm"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,T,I,H", [(8, 16, 512, 512), (3, 7, 64, 96)])
+def test_rnn_fwd_bwd(kind, mode, B, T, I, H):
+    G = 3 if kind == "gru" else 4
+    x = torch.randn(B, T, I)
+    k = 1 / math.sqrt(H)
+    w_ih, w_hh = (torch.rand(G * H, I) * 2 - 1) * k, (torch.rand(G * H, H) * 2 - 1) * k
+    b_ih, b_hh = (torch.rand(G * H) * 2 - 1) * k, (torch.rand(G * H) * 2 - 1) * k
+    gy = torch.randn(B, T, H)
+    if mode == "bf16":
+        x, gy = bf16_round(x), bf16_round(gy)
+    ps = [t.clone().requires_grad_(True) for t in (x, w_ih, w_hh, b_ih, b_hh)]
+    yr = (O.gru if kind == "gru" else O.lstm)(*ps)
+    yr.backward(gy)
+    pg = [t.to(DEV).requires_grad_(True) for t in (x, w_ih, w_hh, b_ih, b_hh)]
+    with mar.precision(mode):
+        y = (ops.gru if kind == "gru" else ops.lstm)(*pg)
+        y.backward(gy.to(DEV).to(y.dtype))
+    tol = FP32_TOL if mode == "fp32" else 3e-2
+    assert_close(y.float().cpu(), yr, tol, f"{kind} hseq")
+    for name, a, b in zip(("dx", "dw_ih", "dw_hh", "db_ih", "db_hh"), pg, ps):
+        assert_close(a.grad.float().cpu(), b.grad, tol, f"{kind} {name}")
+
+
+def test_adam_kernel_matches_oracle():
+    n = 10007
+    p0, g = torch.randn(n), torch.randn(n)
+    p, m, v = p0.clone(), torch.zeros(n), torch.zeros(n)
+    pg, mg, vg = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step = torch.zeros(1, device=DEV)
+    from multimodalaggressionrecognition_b200._lib import call
+    st = torch.cuda.current_stream().cuda_stream
+    for t in range(1, 4):
+        O.adam_step([p], [g], [m], [v], t)
+        call("mar_adam_tick", step.data_ptr(), st)
+        call("mar_adam_step", pg.data_ptr(), g.to(DEV).data_ptr(), mg.data_ptr(), vg.data_ptr(), step.data_ptr(), n,
+             1e-3, 0.9, 0.999, 1e-8, st)
+    assert_close(pg.cpu(), p, 1e-6, "adam")
+
+
+def test_error_reporting_through_abi():
+    from multimodalaggressionrecognition_b200._lib import call
+    with pytest.raises(RuntimeError, match="mar_layernorm_fwd"):
+        call("mar_layernorm_fwd", None, None, None, None, None, None, None, 4, 768, 1e-5, 0, 0)
+    x = torch.randn(4, 100, device=DEV)     # D not a multiple of 8
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        ops.layer_norm(x, torch.ones(100, device=DEV), torch.zeros(100, device=DEV))

@@ -1,0 +1,292 @@
+"""GPU: the drop-in modules, through the reference-facing nn.Module API, against (a) the golden vectors
+recorded from the live reference and (b) the CPU oracle on fresh seeded inputs, in fp32 and bf16 mode;
+plus size-independent properties at BASELINE.json's full sizes."""
+import copy
+
+import pytest
+import torch
+
+import multimodalaggressionrecognition_b200 as mar
+from multimodalaggressionrecognition_b200 import models as M, ops, workloads as W
+from oracle import oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+CASES = ["c1_small", "c1_odd", "c2_small", "c3_small", "c3_video_empty", "c3_audio_empty", "c3_audio_padded"]
+
+
+@pytest.fixture(autouse=True)
+def _no_dropout():
+    O.DROPOUT_ENABLED = False
+    ops.clear_weight_cache()
+    yield
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_golden_parity(golden, name, mode):
+    """eval outputs (incl. the nested-tensor zero-fill path), train logits, per-head losses, every parameter
+    gradient — against what the reference itself produced."""
+    case = golden["cases"][name]
+    spec = case["spec"]
+    tol = H.FP32_TOL if mode == "fp32" else H.BF16_TOL
+    model, batch = H.build_case(spec, M, DEV)
+    with mar.precision(mode):
+        model.eval()
+        if "eval" in case:
+            with torch.no_grad():
+                pred = model(batch[0])
+            pred = pred if isinstance(pred, dict) else {"logits": pred}
+            for k, v in case["eval"].items():
+                assert pred[k].dtype == torch.float32
+                H.assert_close(pred[k].cpu(), v, tol, f"{name}/{mode}/eval/{k}")
+        else:
+            with torch.no_grad(), pytest.raises(RuntimeError):
+                model(batch[0])
+        model.train()
+        model.zero_grad()
+        pred, losses = H.model_losses(spec, M, model, batch)
+        assert set(losses) == set(case["losses"])
+        losses.backward()
+    for k, v in case["train"].items():
+        H.assert_close(pred[k].cpu(), v, tol, f"{name}/{mode}/train/{k}")
+    for k, v in case["losses"].items():
+        assert abs(float(losses[k]) - v) <= (2e-5 if mode == "fp32" else 5e-3), f"{name}/{mode}/loss/{k}"
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    for k, n in case["grad_norms"].items():
+        g = grads[k]
+        if n is None:
+            assert g is None or float(g.abs().max()) == 0.0, f"{name}: {k} must have no gradient"
+        else:
+            assert g is not None, f"{name}: {k} has no gradient"
+            lim = 2e-3 * n if mode == "fp32" else H.BF16_TENSOR_TOL * n + 5e-4
+            assert abs(float(g.norm()) - n) <= lim, f"{name}/{mode}: |grad {k}| = {float(g.norm())} vs {n}"
+    # the norm of the whole gradient
+    tot = sum(n * n for n in case["grad_norms"].values() if n is not None) ** 0.5
+    got = sum(float(g.norm()) ** 2 for g in grads.values() if g is not None) ** 0.5
+    assert abs(got - tot) <= (1e-3 if mode == "fp32" else H.BF16_TOL) * tot
+    for k, v in case["grads"].items():
+        H.assert_grad_close(grads[k].cpu(), v, tol if mode == "fp32" else H.BF16_TENSOR_TOL, f"{name}/{mode}/grad/{k}")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["c1_small", "c2_small", "c3_small"])
+def test_all_gradients_against_oracle(golden, name, mode):
+    """Every parameter gradient (not only the recorded ones) against the oracle run here on the same weights."""
+    spec = golden["cases"][name]["spec"]
+    model, batch = H.build_case(spec, M, DEV)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    data, labels = getattr(W, spec["batch"])(**spec["dkw"])
+    po = H.oracle_forward(spec, sd, data, True, True)
+    sum(H.oracle_losses(spec, po, labels).values()).backward()
+    with mar.precision(mode):
+        model.train()
+        _, losses = H.model_losses(spec, M, model, batch)
+        losses.backward()
+    tol = H.FP32_TOL if mode == "fp32" else H.BF16_TENSOR_TOL
+    got = {k: p.grad for k, p in model.named_parameters()}
+    ref = {k: v.grad for k, v in sd.items()}
+    for k, r in ref.items():
+        if r is not None:
+            H.assert_grad_close(got[k].cpu(), r, tol, f"{name}/{mode}/{k}")
+    e = H.global_rel_err(got, ref)
+    assert e <= (H.FP32_TOL * 3 if mode == "fp32" else H.BF16_TOL), f"{name}/{mode}: whole-gradient relative error {e:.3e}"
+
+
+def test_bf16_error_vs_torch_bf16():
+    """Calibration of the bf16 tolerance: the same C1 model in torch's own bf16 kernels (plain torch.nn modules
+    cast to bfloat16 on this GPU) against the fp32 oracle, beside ours.  Ours must not be worse than 1.5x torch's
+    (+ a small floor)."""
+    import torch.nn as nn
+    torch.manual_seed(5)
+    model = W.perturb_norms(W.disable_dropout(W.build_c1(M))).to(DEV).train()
+    x, y = W.batch_c1(B=8, T=100, seed=1003)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    O.cross_entropy(O.output_classifier(O.transformer_sequence_processor(x, sd, "0.", 2, 8, "identity", True), sd, "1.", True), y).backward()
+    ref = {k: v.grad for k, v in sd.items()}
+    with mar.precision("bf16"):
+        M.MultiCrossEntropyLoss()({"loss": model(x.to(DEV))}, y.to(DEV)).backward()
+    ours = H.global_rel_err({k: p.grad for k, p in model.named_parameters()}, ref)
+
+    enc_layer = nn.TransformerEncoderLayer(768, 8, batch_first=True)
+    tmodel = nn.Sequential()
+    tmodel.enc = nn.TransformerEncoder(enc_layer, 2, norm=nn.LayerNorm(768))
+    tmodel.l1, tmodel.l2 = nn.Linear(768, 256), nn.Linear(256, 2)
+    remap = {}
+    for k, v in model.state_dict().items():
+        k2 = k.replace("0.transformer_squence_processing.", "enc.").replace("1.classifier.1.", "l1.").replace("1.classifier.4.", "l2.")
+        remap[k2] = v
+    tmodel.load_state_dict(remap)
+    W.disable_dropout(tmodel)
+    tmodel = tmodel.to(DEV).to(torch.bfloat16).train()
+    h = tmodel.enc(x.to(DEV).to(torch.bfloat16)).mean(dim=1)
+    logits = tmodel.l2(torch.relu(tmodel.l1(h)))
+    nn.functional.cross_entropy(logits.float(), y.to(DEV)).backward()
+    tg = {}
+    for k2, p in tmodel.named_parameters():
+        k = k2.replace("enc.", "0.transformer_squence_processing.").replace("l1.", "1.classifier.1.").replace("l2.", "1.classifier.4.")
+        tg[k] = p.grad.float()
+    theirs = H.global_rel_err(tg, ref)
+    print(f"whole-gradient bf16 error vs fp32 oracle: ours {ours:.3e}, torch bf16 {theirs:.3e}")
+    assert ours <= 1.5 * theirs + 5e-3
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_adam_loss_curve(golden, mode):
+    """3 Adam steps through torch.optim.Adam on the drop-in's parameters reproduce the reference's loss curve."""
+    for name in ("c2_small", "c3_small"):
+        case = golden["cases"][name]
+        spec = case["spec"]
+        model, batch = H.build_case(spec, M, DEV)
+        model.train()
+        opt = torch.optim.Adam(model.parameters())
+        with mar.precision(mode):
+            for ref_step in case["adam_curve"]:
+                opt.zero_grad()
+                _, losses = H.model_losses(spec, M, model, batch)
+                losses.backward()
+                opt.step()
+                for k, v in ref_step.items():
+                    assert abs(float(losses[k]) - v) <= (1e-3 if mode == "fp32" else 5e-2) * max(1.0, abs(v)), \
+                        f"{name}/{mode}: loss curve {k}: {float(losses[k])} vs {v}"
+
+
+def test_train_eval_asymmetry_of_masked_tokens(golden):
+    """with a left-aligned padding mask, eval re-inserts padded tokens as zeros before the final
+    LayerNorm (output = beta), train computes them as ordinary queries."""
+    fusion = M.EqualSizedTransformerModalitiesFusion(1, 768, 8).to(DEV)
+    W.perturb_norms(W.disable_dropout(fusion))
+    a = torch.randn(2, 10, 768, device=DEV)
+    v = torch.zeros(2, 4, 768, device=DEV)      # EMPTY modality → zero rows → masked keys, left-aligned
+    beta = fusion.modality_fusion_transformer.norm.bias
+    with mar.precision("fp32"):
+        fusion.eval()
+        with torch.no_grad():
+            out_eval = fusion({"audio": a, "video": v})
+        fusion.train()
+        out_train = fusion({"audio": a, "video": v})
+    H.assert_close(out_eval["video"][0, 0], beta, 1e-5, "eval: padded token = LN(0) = beta")
+    assert float((out_train["video"][0, 0] - beta).abs().max()) > 1e-2
+    H.assert_close(out_eval["audio"], out_train["audio"].detach(), 1e-5, "valid tokens agree between train and eval")
+
+
+def test_per_head_backward_equals_reference_semantics(golden):
+    """LossesDict.backward() (one pass over all heads) = the reference's per-head backward with retain_graph."""
+    spec = golden["cases"]["c3_small"]["spec"]
+    model, batch = H.build_case(spec, M, DEV)
+    model.train()
+    with mar.precision("fp32"):
+        _, losses = H.model_losses(spec, M, model, batch)
+        losses.backward()
+        g1 = {k: p.grad.clone() for k, p in model.named_parameters()}
+        model.zero_grad()
+        _, losses = H.model_losses(spec, M, model, batch)
+        items = list(losses.items())
+        for i, (_, l) in enumerate(items):
+            l.backward(retain_graph=i != len(items) - 1)
+    for k, p in model.named_parameters():
+        H.assert_close(p.grad, g1[k], 1e-5, k)
+
+
+def test_dropout_training_mode_runs_and_is_stochastic():
+    model = W.build_c3(M, t_audio=24, t_video=8).to(DEV).train()
+    batch = W.to_device(W.batch_c3(B=8, t_audio=24, t_video=8), DEV)
+    with mar.precision("bf16"):
+        a = model(batch[0])
+        b = model(batch[0])
+        model.eval()
+        with torch.no_grad():
+            c = model(batch[0])
+            d = model(batch[0])
+    assert float((a["phys"] - b["phys"]).abs().max()) > 0      # fresh masks per call
+    assert torch.equal(c["phys"], d["phys"])                    # eval is deterministic
+    assert all(torch.isfinite(t).all() for t in a.values())
+
+
+def test_mixed_empty_rows_in_one_batch():
+    """Non-homogeneous batch (some samples lack video): extractor runs on the present rows only."""
+    kw = dict(t_audio=24, t_video=8)
+    torch.manual_seed(3)
+    model = W.perturb_norms(W.disable_dropout(W.build_c3(M, **kw))).to(DEV).eval()
+    data, labels = W.batch_c3(B=6, **kw)
+    names = list(data[1][0])
+    for i in (1, 4):
+        names[i] = "video_EMPTY"
+        data[1][1][i] = -1.0
+    data[1][0] = tuple(names)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = O.physverb_model(data, sd, W.c3_oracle_cfg(**kw), False, False)
+        with mar.precision("fp32"):
+            got = model(W.to_device(data, DEV))
+    for k in ref:
+        H.assert_close(got[k].cpu(), ref[k], H.FP32_TOL, f"mixed EMPTY {k}")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_full_size_c3_properties(mode):
+    """BASELINE config 3 at full size (B=256 is too slow for the CPU oracle): size-independent properties.
+    (1) batch independence: logits of clip i do not depend on the other clips;
+    (2) linearity of the loss gradient in the upstream gradient (grad of 2·loss = 2·grad);
+    (3) the first 8 clips reproduce the oracle run on those 8 clips alone."""
+    B = 256 if mode == "bf16" else 64
+    torch.manual_seed(0)
+    model = W.perturb_norms(W.disable_dropout(W.build_c3(M))).to(DEV).train()
+    data, labels = W.batch_c3(B=B)
+    gdata, glabels = W.to_device(data, DEV), W.to_device(labels, DEV)
+    crit = M.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(), "verb": torch.nn.CrossEntropyLoss()})
+    with mar.precision(mode):
+        pred = model(gdata)
+        sub = [[n[:8], t[:8]] for n, t in gdata]
+        pred8 = model(sub)
+        for k in pred:
+            H.assert_close(pred[k][:8], pred8[k], 1e-5 if mode == "fp32" else 1e-2, f"batch independence {k}")
+        model.zero_grad()
+        crit(pred, glabels).backward()
+        g1 = {k: p.grad.clone() for k, p in model.named_parameters()}
+        model.zero_grad()
+        losses = crit(model(gdata), glabels)
+        (2.0 * losses.total()).backward()
+        for k, p in model.named_parameters():
+            H.assert_close(p.grad, 2.0 * g1[k], 1e-4 if mode == "fp32" else 2e-2, f"linearity {k}")
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = O.physverb_model([[n[:8], t[:8]] for n, t in data], sd, W.c3_oracle_cfg(), True, True)
+    for k in ref:
+        H.assert_close(pred8[k].float().cpu(), ref[k], H.FP32_TOL if mode == "fp32" else H.BF16_TOL, f"full-size weights, 8 clips {k}")
+
+
+def test_full_size_c1_c2_against_oracle():
+    """C1 (B=32,T=250,d=768, 2 layers) and C2 (B=64,T=64,d=512 GRU) at BASELINE sizes, forward, vs the oracle."""
+    torch.manual_seed(0)
+    m1 = W.perturb_norms(W.disable_dropout(W.build_c1(M))).to(DEV).eval()
+    x, _ = W.batch_c1()
+    sd = {k: v.detach().cpu() for k, v in m1.state_dict().items()}
+    with torch.no_grad():
+        ref = O.output_classifier(O.transformer_sequence_processor(x, sd, "0.", 2, 8), sd, "1.")
+        for mode, tol in (("fp32", H.FP32_TOL), ("bf16", H.BF16_TOL)):
+            with mar.precision(mode):
+                H.assert_close(m1(x.to(DEV)).cpu(), ref, tol, f"C1 {mode}")
+    m2 = W.build_c2(M, heads=("GRU_1L", "LSTM_1L", "Avg_features")).to(DEV).eval()
+    x, _ = W.batch_c2()
+    sd = {k: v.detach().cpu() for k, v in m2.state_dict().items()}
+    with torch.no_grad():
+        ref = O.video_multi_nn(x, sd, {"GRU_1L": "gru", "LSTM_1L": "lstm", "Avg_features": "avg"})
+        for mode, tol in (("fp32", H.FP32_TOL), ("bf16", 3e-2)):
+            with mar.precision(mode):
+                got = m2(x.to(DEV))
+            for k in ref:
+                H.assert_close(got[k].cpu(), ref[k], tol, f"C2 {mode} {k}")
+
+
+def test_reference_state_dict_round_trip():
+    """Checkpoints interchange with the reference: same keys, load_state_dict strict."""
+    a = W.build_c3(M, t_audio=24, t_video=8)
+    b = W.build_c3(M, t_audio=24, t_video=8)
+    b.load_state_dict(copy.deepcopy(a.state_dict()), strict=True)
+    a, b = a.to(DEV).eval(), b.to(DEV).eval()
+    batch = W.to_device(W.batch_c3(B=4, t_audio=24, t_video=8), DEV)
+    with torch.no_grad(), mar.precision("fp32"):
+        pa, pb = a(batch[0]), b(batch[0])
+    assert all(torch.equal(pa[k], pb[k]) for k in pa)

@@ -1,0 +1,88 @@
+"""CPU: the oracle restatement against the golden vectors recorded from the LIVE reference
+(oracle/make_golden.py).  This is the oracle's pin; it runs anywhere (no /root/reference needed)."""
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests import helpers as H
+import multimodalaggressionrecognition_b200.models as mine
+
+CASES = ["c1_small", "c1_odd", "c2_small", "c3_small", "c3_video_empty", "c3_audio_empty", "c3_audio_padded"]
+
+
+@pytest.fixture(autouse=True)
+def _no_dropout():
+    old = O.DROPOUT_ENABLED
+    O.DROPOUT_ENABLED = False
+    yield
+    O.DROPOUT_ENABLED = old
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(golden, name):
+    case = golden["cases"][name]
+    spec = case["spec"]
+    model, (data, labels) = H.build_case(spec, mine)        # same seed => same weights as the reference
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    chk = float(sum(v.double().abs().sum() for v in sd.values()))
+    assert abs(chk - case["weights_checksum"]) <= 1e-9 * case["weights_checksum"], "same seed must give the reference's weights"
+
+    if "eval" in case:
+        with torch.no_grad():
+            pred = H.oracle_forward(spec, sd, data, False, False)
+        for k, v in case["eval"].items():
+            H.assert_close(pred[k], v, 2e-5, f"{name}/eval/{k}")
+    else:
+        with pytest.raises(RuntimeError):
+            H.oracle_forward(spec, sd, data, False, False)
+
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    pred = H.oracle_forward(spec, sdg, data, True, True)
+    losses = H.oracle_losses(spec, pred, labels)
+    assert set(losses) == set(case["losses"])
+    for k, v in case["train"].items():
+        H.assert_close(pred[k], v, 2e-5, f"{name}/train/{k}")
+    for k, v in case["losses"].items():
+        assert abs(float(losses[k].detach()) - v) < 2e-5
+    sum(losses.values()).backward()
+    for k, n in case["grad_norms"].items():
+        g = sdg[k].grad
+        if n is None:
+            assert g is None or float(g.abs().max()) == 0.0
+        else:
+            assert abs(float(g.norm()) - n) <= 2e-4 * max(n, 1e-6), f"{name}: grad norm of {k}"
+    for k, v in case["grads"].items():
+        H.assert_close(sdg[k].grad, v, 1e-4, f"{name}/grad/{k}")
+
+
+def test_oracle_adam_curve(golden):
+    case = golden["cases"]["c2_small"]
+    spec = case["spec"]
+    model, (data, labels) = H.build_case(spec, mine)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    tr = O.OracleTrainer(sd, lambda s, d, t: H.oracle_forward(spec, s, d, t, True), lambda p, t: H.oracle_losses(spec, p, t))
+    for ref_step in case["adam_curve"]:
+        got = tr.step(data, labels, training=True)
+        for k, v in ref_step.items():
+            assert abs(got[k] - v) <= 1e-4 * max(1.0, abs(v))
+
+
+def test_adam_matches_torch():
+    torch.manual_seed(0)
+    p0 = torch.randn(1000)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref])
+    p, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    for t in range(1, 6):
+        g = torch.randn(1000)
+        p_ref.grad = g.clone()
+        opt.step()
+        O.adam_step([p], [g], [m], [v], t)
+        assert torch.allclose(p, p_ref.detach(), atol=1e-6)
+
+
+def test_safe_softmax_all_masked_row():
+    s = torch.full((2, 4), float("-inf"))
+    s[1, 2] = 0.5
+    p = O.softmax_lastdim_safe(s)
+    assert torch.equal(p[0], torch.zeros(4)) and float(p[1, 2]) == 1.0
