@@ -4,6 +4,7 @@
 #include <atomic>
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_skinny.cuh"
 #include "gemm_tcgen05.cuh"
 #include "attention.cuh"
 #include "rnn.cuh"
@@ -91,6 +92,8 @@ int mar_linear_fwd(const void* x, int64_t ldx, const void* w, const float* bias,
   const bool use_tc = engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && tc_ok && M >= 64 && N >= 64 && !env_flag("MAR_FORCE_SIMT"));
   if (use_tc) return gemm_tcgen05(a, S(stream));
 
+  if (skinny_supported(N) && flags == 0 && residual == nullptr && !(in_dtype == MAR_F32 && out_dtype == MAR_BF16))
+    return skinny_fwd(x, ldx, w, bias, out, ldo, M, N, K, in_dtype, out_dtype, S(stream));
   SimtEpilogue epi;
   epi.bias = bias; epi.residual = residual; epi.ldr = ldr; epi.res_is_bf16 = in_dtype == MAR_BF16;
   epi.flags = flags; epi.p = p_drop; epi.rng = rng_state; epi.site = site;
@@ -110,6 +113,7 @@ int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* 
   if (engine == MAR_ENGINE_TCGEN05 && !tc_ok) MAR_UNSUPPORTED("mar_linear_dgrad: tcgen05 engine cannot take M=%lld N=%lld K=%lld (needs bf16 and wt)", (long long)M, (long long)N, (long long)K);
   const bool use_tc = engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && tc_ok && M >= 64 && K >= 64 && !env_flag("MAR_FORCE_SIMT"));
   if (use_tc) return gemm_tcgen05(a, S(stream));
+  if (skinny_supported(N) && w != nullptr) return skinny_dgrad(dz, w, add, dx, lddx, M, N, K, dtype, S(stream));
   SimtEpilogue epi;
   epi.residual = add; epi.ldr = lddx; epi.res_is_bf16 = dtype == MAR_BF16;
   if (w != nullptr)   // dx(m,k) = Σ_n dz(m,n) W(n,k):  B(kr=n, col=k) = w[n*K + k]
@@ -134,6 +138,7 @@ int mar_linear_wgrad(const void* dz, const void* x, int64_t ldx, float* dw, int6
   if (engine == MAR_ENGINE_TCGEN05 && !tc_ok) MAR_UNSUPPORTED("mar_linear_wgrad: tcgen05 engine cannot take M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   const bool use_tc = engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && tc_ok && N >= 64 && K >= 64 && M >= 64 && !env_flag("MAR_FORCE_SIMT"));
   if (use_tc) return gemm_tcgen05(a, S(stream));
+  if (skinny_supported(N)) return skinny_wgrad(dz, x, ldx, dw, M, N, K, dtype, accumulate, S(stream));
   SimtEpilogue epi;
   epi.accumulate = accumulate; epi.allow_split = 1;
   // A(m=n, kr=row) = dz[row*N + n] ; B(kr=row, col=k) = x[row*ldx + k]

@@ -108,6 +108,11 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sam, int64_t sak,
       if (epi.flags & MAR_EPI_RELU_PRE) v = fmaxf(v, 0.f);
       if (do_drop) v = drop_keep(dk, (uint64_t)gm * (uint64_t)N + (uint64_t)gn) ? v * dk.scale : 0.f;
       if (epi.flags & MAR_EPI_RELU_POST) v = fmaxf(v, 0.f);
+      if (epi.aux) {
+        const float a = epi.res_is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(epi.aux)[(int64_t)gm * epi.ldaux + gn])
+                                        : reinterpret_cast<const float*>(epi.aux)[(int64_t)gm * epi.ldaux + gn];
+        v = a > 0.f ? v * epi.aux_scale : 0.f;
+      }
       if (epi.residual) {
         v += epi.res_is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(epi.residual)[(int64_t)gm * epi.ldr + gn])
                              : reinterpret_cast<const float*>(epi.residual)[(int64_t)gm * epi.ldr + gn];

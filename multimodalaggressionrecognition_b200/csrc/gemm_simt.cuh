@@ -6,6 +6,9 @@ struct SimtEpilogue {
   const void* residual = nullptr;  // same logical shape as C
   int64_t ldr = 0;
   int res_is_bf16 = 0;
+  const void* aux = nullptr;       // (M,N) ldaux, same dtype as residual: result *= (aux > 0 ? aux_scale : 0)
+  int64_t ldaux = 0;
+  float aux_scale = 1.f;
   int flags = 0;
   float p = 0.f;
   const uint64_t* rng = nullptr;

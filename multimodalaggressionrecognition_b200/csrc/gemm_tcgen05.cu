@@ -1,7 +1,7 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA (128 B swizzle) -> smem ring ->
-// tcgen05.mma (cta_group::1, 128 x BN x 16) with fp32 accumulators in TMEM (double buffered) ->
-// tcgen05.ld epilogue with the fused linear epilogue (bias / ReLU / dropout / residual) or fp32
-// split-K reduction (wgrad).
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA (128 B swizzle, multicast across a 2-CTA
+// cluster) -> smem ring -> tcgen05.mma (cta_group::1, 128 x BN x 16) with fp32 accumulators in TMEM
+// (double buffered) -> tcgen05.ld epilogue with the fused linear epilogue (bias / ReLU / dropout /
+// aux mask / residual) -> swizzled smem staging -> TMA store;  or fp32 split-K reduction (wgrad).
 //
 //   D[M,N] = epilogue( A · B ),  reduction length Kr
 //   A: K-major  = row-major (M, Kr)         or MN-major = row-major (Kr, M)
@@ -11,8 +11,16 @@
 //   dgrad    dx = dz·W   : A = dz (M,N) K-major,       B = Wᵀ (K,N) K-major (bf16 transposed copy)
 //   wgrad    dW = dzᵀ·x  : A = dz (rows,N) MN-major,   B = x (rows,K) MN-major, fp32 out, split-K
 //
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 epilogue (warp w reads TMEM lanes 32*(w%4)..+31; one accumulator row per thread).
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11
+// epilogue (warp w reads TMEM lanes 32*(w%4)..+31, one accumulator row per thread; warps 4-7 take
+// the left half of the tile's columns, warps 8-11 the right half).
+//
+// Epilogue (bf16 out): measured with ncu, per-thread 16 B global stores of an accumulator row touch 32
+// different lines per instruction (2x the ideal sector count) and held the K=768 GEMMs at 0.95 PFLOP/s
+// while the bare main loop ran at 1.2-1.4.  So every epilogue warp owns a 4 KB [32 rows x 64 cols]
+// 128 B-swizzled staging box: the residual / mask tile is TMA-LOADED into it, combined in place with the
+// accumulator, and the result TMA-STORED (full 128 B lines, clipped at the matrix edge by the hardware).
+//
 // Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2·M·N·Kr.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -27,24 +35,26 @@ constexpr int BLOCK_K = 64;            // 64 bf16 = 128 B = one swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int ATOM_BYTES = BLOCK_K * 128;              // one MN-major box: 64 k-rows x 128 B = 8 KB
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_BOX_BYTES = 32 * 128;                // [32 rows][64 bf16]
 
 template <int BN> struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;   // 512 or 256: power of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_BOX_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 struct TcParams {
   int M, N, Kr;
   int splits, kb_per_split;
-  void* out;
+  void* out;              // fp32 path only (bf16 goes through the TMA store map)
   int64_t ldo;
   const float* bias;
-  const void* residual;   // bf16, row stride ldr
-  int64_t ldr;
+  int staged_mode;        // 0 none, 1 residual add, 2 aux mask (result *= staged > 0 ? aux_scale : 0)
+  float aux_scale;
   int flags;
   float p_drop;
   const uint64_t* rng;
@@ -57,35 +67,44 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, typename OutT>
+template <int BN, bool A_MN, bool B_MN, typename OutT, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_o, const __grid_constant__ CUtensorMap tma_s, const TcParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* smem_e = smem + C::STAGES * C::STAGE_BYTES;                       // epilogue staging boxes (1024 B aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_e + EPI_WARPS * EPI_BOX_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full = bars + 2 * C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* epi_bar = tmem_empty + 2;                                        // [EPI_WARPS] staged-input arrival
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + EPI_WARPS);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_groups = (m_blocks + CL - 1) / CL;        // CL consecutive M-blocks share one B tile
   const int n_blocks = (p.N + BN - 1) / BN;
-  const int num_tiles = m_blocks * n_blocks;
+  const int num_tiles = m_groups * n_blocks;
   const int num_work = num_tiles * p.splits;
   const int kb_total = (p.Kr + BLOCK_K - 1) / BLOCK_K;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tma_a);
     prefetch_tensormap(&tma_b);
+    if (sizeof(OutT) == 2) { prefetch_tensormap(&tma_o); if (p.staged_mode) prefetch_tensormap(&tma_s); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < C::STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }
+    for (int i = 0; i < EPI_WARPS; i++) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -93,7 +112,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -101,13 +120,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
         const int tile = w % num_tiles, split = w / num_tiles;
-        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        const int m_blk = (tile / n_blocks) * CL + rank, n_blk = tile % n_blocks;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);       // both CTAs of the cluster have drained this stage
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
@@ -118,12 +137,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             for (int i = 0; i < BLOCK_M / 64; i++)
               tma_load_2d(sa + i * ATOM_BYTES, &tma_a, &full_bar[stage], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
           }
+          // B: this CTA fetches its 1/CL share of the tile and multicasts it to the whole cluster
           if (!B_MN) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+            constexpr int ROWS = BN / CL;
+            uint8_t* dst = sb + rank * ROWS * 128;
+            if (CL > 1) tma_load_2d_mc(dst, &tma_b, &full_bar[stage], kb * BLOCK_K, n_blk * BN + rank * ROWS, MC_MASK);
+            else tma_load_2d(dst, &tma_b, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
           } else {
+            constexpr int ATOMS = BN / 64 / CL;
 #pragma unroll
-            for (int i = 0; i < BN / 64; i++)
-              tma_load_2d(sb + i * ATOM_BYTES, &tma_b, &full_bar[stage], n_blk * BN + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < ATOMS; i++) {
+              const int a = rank * ATOMS + i;
+              if (CL > 1) tma_load_2d_mc(sb + a * ATOM_BYTES, &tma_b, &full_bar[stage], n_blk * BN + a * 64, kb * BLOCK_K, MC_MASK);
+              else tma_load_2d(sb + a * ATOM_BYTES, &tma_b, &full_bar[stage], n_blk * BN + a * 64, kb * BLOCK_K);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -135,7 +162,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, it++) {
+      for (int w = cluster_id; w < num_work; w += num_clusters, it++) {
         const int split = w / num_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb_total, kb0 + p.kb_per_split);
@@ -155,7 +182,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             const uint64_t bdesc = B_MN ? make_desc_mnmajor(sb, k, ATOM_BYTES) : make_desc_kmajor(sb, k);
             umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          // free the stage in EVERY CTA of the cluster (the peer multicasts into our smem too)
+          if (CL > 1) umma_commit_mc(&empty_bar[stage], MC_MASK); else umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[as]);
@@ -163,28 +191,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp - 4;   // TMEM lane quarter
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int ew = warp - 4;                // epilogue warp index
+    const int half = ew >> 2;               // column half of the tile
     const bool do_drop = (p.flags & MAR_EPI_DROPOUT) && p.p_drop > 0.f;
     DropKey dk;
     if (do_drop) dk = make_drop_key(p.rng, p.site, p.p_drop);
+    uint8_t* box = smem_e + ew * EPI_BOX_BYTES;
+    uint64_t* sbar = &epi_bar[ew];
+    uint32_t sphase = 0;
+    constexpr int CHUNKS = BN / 64;         // 32-column TMEM chunks handled by this warp
     int it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, it++) {
+    for (int w = cluster_id; w < num_work; w += num_clusters, it++) {
       const int tile = w % num_tiles, split = w / num_tiles;
-      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      const int m_blk = (tile / n_blocks) * CL + rank, n_blk = tile % n_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int row = row0 + lane;
+      const bool first_split = split == 0;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const bool first_split = split == 0;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
+      for (int cc = 0; cc < CHUNKS; cc++) {
+        const int c = half * CHUNKS + cc;
         const int col0 = n_blk * BN + c * 32;
-        if (col0 >= p.N) break;   // warp-uniform
+        const bool col_ok = col0 < p.N;                        // warp-uniform
+        const bool box_start = (cc & 1) == 0 || CHUNKS == 1;
+        const int bcol0 = (CHUNKS == 1) ? col0 : col0 - (cc & 1) * 32;   // first column of the 64-wide staging box
+        if (sizeof(OutT) == 2 && box_start && col_ok && row0 < p.M) {
+          // the box is free once the previous TMA store has finished reading it; then fetch the staged input
+          if (lane == 0) {
+            tma_store_wait_read();
+            if (p.staged_mode) {
+              mbar_expect_tx(sbar, EPI_BOX_BYTES);
+              tma_load_2d(box, &tma_s, sbar, bcol0, row0);
+            }
+          }
+          __syncwarp();
+        }
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
         tmem_ld_wait();
+        if (cc == CHUNKS - 1) {             // accumulator fully read: hand the TMEM stage back to the MMA warp now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        if (!col_ok || row0 >= p.M) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
@@ -215,33 +269,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
         }
-        if (!row_ok) continue;
-        if (p.residual != nullptr) {
-          const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + (int64_t)row * p.ldr + col0;
+        if (sizeof(OutT) == 2) {
+          // this thread's row of the staging box: 8 x 16 B chunks, physical chunk = logical ^ (row & 7)
+          uint8_t* rowp = box + lane * 128;
+          const int ch0 = (CHUNKS == 1) ? 0 : (cc & 1) * 4;
+          if (p.staged_mode) {
+            if (box_start) { mbar_wait(sbar, sphase); sphase ^= 1; }
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
-            if (col0 + g * 8 < p.N) {
-              float t8[8];
-              Vec8<bf16>::load(rp + g * 8, t8);
+            for (int g = 0; g < 4; g++) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rowp + (((ch0 + g) ^ (lane & 7)) << 4));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-              for (int j = 0; j < 8; j++) v[g * 8 + j] += t8[j];
+              for (int j = 0; j < 4; j++) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                if (p.staged_mode == 1) { v[g * 8 + 2 * j] += f.x; v[g * 8 + 2 * j + 1] += f.y; }
+                else {
+                  v[g * 8 + 2 * j] = f.x > 0.f ? v[g * 8 + 2 * j] * p.aux_scale : 0.f;
+                  v[g * 8 + 2 * j + 1] = f.y > 0.f ? v[g * 8 + 2 * j + 1] * p.aux_scale : 0.f;
+                }
+              }
             }
           }
-        }
-        if (sizeof(OutT) == 2) {
-          bf16* op = reinterpret_cast<bf16*>(p.out) + (int64_t)row * p.ldo + col0;
 #pragma unroll
           for (int g = 0; g < 4; g++) {
-            if (col0 + g * 8 < p.N) {
-              uint4 u;
-              u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-              u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-              u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-              u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-              *reinterpret_cast<uint4*>(op + g * 8) = u;
-            }
+            uint4 u;
+            u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+            u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+            u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+            u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(rowp + (((ch0 + g) ^ (lane & 7)) << 4)) = u;
+          }
+          const bool box_end = (cc & 1) == 1 || CHUNKS == 1 || col0 + 32 >= p.N;
+          if (box_end) {
+            fence_proxy_async();            // generic-proxy smem writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tma_o, box, bcol0, row0); tma_store_commit(); }
           }
         } else {
+          if (row >= p.M) continue;
           float* op = reinterpret_cast<float*>(p.out) + (int64_t)row * p.ldo + col0;
 #pragma unroll
           for (int g = 0; g < 8; g++) {
@@ -260,14 +325,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
+    if (sizeof(OutT) == 2 && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // nobody leaves while a peer may still write into its smem
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -315,21 +378,38 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
   return MAR_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, typename OutT>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, typename OutT, int CL>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& ms, const TcParams& p,
+           cudaStream_t st) {
   using C = Cfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, OutT>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, OutT, CL>;
   static bool configured = false;
   if (!configured) {
     MAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (p.N + BN - 1) / BN;
-  const int64_t work = (int64_t)m_blocks * n_blocks * p.splits;
-  const int grid = (int)(work < mar_sm_count() ? work : mar_sm_count());
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+  const int m_groups = (int)ceil_div(ceil_div(p.M, BLOCK_M), CL), n_blocks = (p.N + BN - 1) / BN;
+  const int64_t work = (int64_t)m_groups * n_blocks * p.splits;
+  const int max_clusters = mar_sm_count() / CL;
+  const int clusters = (int)(work < max_clusters ? work : max_clusters);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CL), 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MAR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, ms, p));
   MAR_LAUNCH_CHECK("gemm_tcgen05");
   return MAR_OK;
+}
+
+template <int BN, bool MN, typename OutT>
+int launch_cl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& ms, const TcParams& p,
+              int cl, cudaStream_t st) {
+  return cl == 2 ? launch<BN, MN, MN, OutT, 2>(ma, mb, mo, ms, p, st) : launch<BN, MN, MN, OutT, 1>(ma, mb, mo, ms, p, st);
 }
 
 }  // namespace
@@ -342,6 +422,9 @@ bool gemm_tcgen05_supported(const TcGemmArgs& a) {
   if (!al16(a.A) || !al16(a.B) || !al16(a.out)) return false;
   if ((a.lda * 2) % 16 != 0 || (a.ldb * 2) % 16 != 0) return false;
   if (a.residual != nullptr && (!al16(a.residual) || (a.ldr * 2) % 16 != 0)) return false;
+  if (a.aux != nullptr && (!al16(a.aux) || (a.ldaux * 2) % 16 != 0)) return false;
+  if (a.aux != nullptr && a.residual != nullptr) return false;   // one staged input per launch
+  if ((a.aux != nullptr || a.residual != nullptr) && a.out_fp32) return false;
   const int64_t osz = a.out_fp32 ? 4 : 2;
   if ((a.ldo * osz) % 16 != 0) return false;
   if (a.a_mn_major != a.b_mn_major) return false;   // TN (fwd/dgrad) and NT-on-rows (wgrad) only
@@ -355,15 +438,22 @@ int gemm_tcgen05(const TcGemmArgs& a, cudaStream_t st) {
   mar_set_engine(MAR_ENGINE_TCGEN05);
   TcParams p;
   p.M = (int)a.M; p.N = (int)a.N; p.Kr = (int)a.Kr;
-  p.out = a.out; p.ldo = a.ldo; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr;
+  p.out = a.out; p.ldo = a.ldo; p.bias = a.bias;
+  p.staged_mode = a.residual != nullptr ? 1 : (a.aux != nullptr ? 2 : 0);
+  p.aux_scale = a.aux_scale;
   p.flags = a.flags; p.p_drop = a.p_drop; p.rng = a.rng; p.site = a.site;
   p.atomic_out = 0; p.accumulate = a.accumulate;
   const int BN = (a.N > 128) ? 256 : 128;
+  const int64_t m_blocks = ceil_div(a.M, BLOCK_M);
+  // cluster of 2 when there are at least two M-blocks to pair (MAR_TC_CLUSTER=1 disables, for A/B measurements)
+  static int env_cl = -1;
+  if (env_cl < 0) { const char* e = getenv("MAR_TC_CLUSTER"); env_cl = e ? atoi(e) : 2; }
+  const int cl = (m_blocks >= 2 && env_cl >= 2) ? 2 : 1;
   const int kb_total = (int)ceil_div(a.Kr, BLOCK_K);
   p.splits = 1; p.kb_per_split = kb_total;
-  if (a.allow_split && a.out_fp32 && a.flags == 0 && a.residual == nullptr) {
-    const int64_t tiles = ceil_div(a.M, BLOCK_M) * ceil_div(a.N, BN);
-    int64_t want = ceil_div((int64_t)mar_sm_count(), tiles);
+  if (a.allow_split && a.out_fp32 && a.flags == 0 && a.residual == nullptr && a.aux == nullptr) {
+    const int64_t tiles = ceil_div(m_blocks, cl) * ceil_div(a.N, BN);
+    int64_t want = ceil_div((int64_t)(mar_sm_count() / cl), tiles);
     int64_t max_split = kb_total / 8 > 0 ? kb_total / 8 : 1;   // at least 8 k-blocks (512 rows) per split
     int64_t splits = want < max_split ? want : max_split;
     if (splits > 1) {
@@ -376,18 +466,26 @@ int gemm_tcgen05(const TcGemmArgs& a, cudaStream_t st) {
       }
     }
   }
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo, ms;
   int rc;
   if (!a.a_mn_major) {
     rc = make_map(&ma, a.A, a.M, a.Kr, a.lda, BLOCK_M); if (rc) return rc;
-    rc = make_map(&mb, a.B, a.N, a.Kr, a.ldb, BN); if (rc) return rc;
+    rc = make_map(&mb, a.B, a.N, a.Kr, a.ldb, BN / cl); if (rc) return rc;
   } else {
     rc = make_map(&ma, a.A, a.Kr, a.M, a.lda, BLOCK_K); if (rc) return rc;
     rc = make_map(&mb, a.B, a.Kr, a.N, a.ldb, BLOCK_K); if (rc) return rc;
   }
-  if (!a.a_mn_major) {
-    if (a.out_fp32) return BN == 256 ? launch<256, false, false, float>(ma, mb, p, st) : launch<128, false, false, float>(ma, mb, p, st);
-    return BN == 256 ? launch<256, false, false, bf16>(ma, mb, p, st) : launch<128, false, false, bf16>(ma, mb, p, st);
+  if (!a.out_fp32) {
+    rc = make_map(&mo, a.out, a.M, a.N, a.ldo, 32); if (rc) return rc;
+    const void* sp = a.residual != nullptr ? a.residual : a.aux;
+    if (sp != nullptr) { rc = make_map(&ms, sp, a.M, a.N, a.residual != nullptr ? a.ldr : a.ldaux, 32); if (rc) return rc; }
+    else ms = mo;
+  } else {
+    mo = ma; ms = ma;   // unused by the fp32 epilogue
   }
-  return BN == 256 ? launch<256, true, true, float>(ma, mb, p, st) : launch<128, true, true, float>(ma, mb, p, st);
+  if (!a.a_mn_major) {
+    if (a.out_fp32) return BN == 256 ? launch_cl<256, false, float>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, float>(ma, mb, mo, ms, p, cl, st);
+    return BN == 256 ? launch_cl<256, false, bf16>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, bf16>(ma, mb, mo, ms, p, cl, st);
+  }
+  return BN == 256 ? launch_cl<256, true, float>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, true, float>(ma, mb, mo, ms, p, cl, st);
 }

@@ -15,6 +15,9 @@ struct TcGemmArgs {
   const float* bias = nullptr;
   const void* residual = nullptr;  // bf16 (M,N), ldr
   int64_t ldr = 0;
+  const void* aux = nullptr;       // bf16 (M,N), ldaux: result *= (aux > 0 ? aux_scale : 0)  (activation backward)
+  int64_t ldaux = 0;
+  float aux_scale = 1.f;
   int flags = 0;
   float p_drop = 0.f;
   const uint64_t* rng = nullptr;
