@@ -235,6 +235,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel: events around every GEMM launch of one eager step --------
     roof = None
     if rank == 0:
+        step.sync.enabled = False          # this extra backward runs on rank 0 only: no collectives
         roof = gemm_roofline(model, crit, gdata, glabels, args, ops, training)
 
     if world > 1:

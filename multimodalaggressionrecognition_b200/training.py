@@ -124,6 +124,7 @@ class GradSync:
         self.launched = [False] * len(self.buckets)
         self.handles = []
         self.order: List[int] = []
+        self.enabled = True          # False: hooks do nothing (backward passes outside a TrainStep, e.g. profiling)
         if self.world > 1:
             for i, p in enumerate(flat.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
@@ -138,6 +139,8 @@ class GradSync:
 
     def _make_hook(self, i: int) -> Callable:
         def hook(_param):
+            if not self.enabled:
+                return
             b = self.bucket_of[i]
             self.pending[b] -= 1
             if self.pending[b] == 0 and not self.launched[b]:
