@@ -66,8 +66,12 @@ def test_golden_parity(golden, name, mode):
     tot = sum(n * n for n in case["grad_norms"].values() if n is not None) ** 0.5
     got = sum(float(g.norm()) ** 2 for g in grads.values() if g is not None) ** 0.5
     assert abs(got - tot) <= (1e-3 if mode == "fp32" else H.BF16_TOL) * tot
-    for k, v in case["grads"].items():
-        H.assert_grad_close(grads[k].cpu(), v, tol if mode == "fp32" else H.BF16_TENSOR_TOL, f"{name}/{mode}/grad/{k}")
+    if mode == "fp32":
+        for k, v in case["grads"].items():
+            H.assert_grad_close(grads[k].cpu(), v, tol, f"{name}/{mode}/grad/{k}")
+    else:
+        floor = H.bf16_floor(spec, model, getattr(W, spec["batch"])(**spec["dkw"]))
+        H.assert_bf16_grads({k: grads[k] for k in case["grads"]}, case["grads"], floor, f"{name}/bf16/grad")
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
@@ -84,14 +88,18 @@ def test_all_gradients_against_oracle(golden, name, mode):
         model.train()
         _, losses = H.model_losses(spec, M, model, batch)
         losses.backward()
-    tol = H.FP32_TOL if mode == "fp32" else H.BF16_TENSOR_TOL
     got = {k: p.grad for k, p in model.named_parameters()}
     ref = {k: v.grad for k, v in sd.items()}
+    if mode == "bf16":
+        floor = H.bf16_floor(spec, model, (data, labels))
+        e = H.assert_bf16_grads(got, ref, floor, f"{name}/bf16")
+        print(f"{name}: whole-gradient bf16 error vs fp32 oracle: ours {e:.3e}, torch bf16 arithmetic {floor['global']:.3e}")
+        return
     for k, r in ref.items():
         if r is not None:
-            H.assert_grad_close(got[k].cpu(), r, tol, f"{name}/{mode}/{k}")
+            H.assert_grad_close(got[k].cpu(), r, H.FP32_TOL, f"{name}/{mode}/{k}")
     e = H.global_rel_err(got, ref)
-    assert e <= (H.FP32_TOL * 3 if mode == "fp32" else H.BF16_TOL), f"{name}/{mode}: whole-gradient relative error {e:.3e}"
+    assert e <= H.FP32_TOL * 3, f"{name}/{mode}: whole-gradient relative error {e:.3e}"
 
 
 def test_bf16_error_vs_torch_bf16():
