@@ -159,6 +159,9 @@ int mar_attention_fwd(const void* qkv, const uint8_t* key_mask, void* out, float
   if (engine == MAR_ENGINE_TCGEN05 && !mma_ok) MAR_UNSUPPORTED("mar_attention_fwd: tensor-core engine cannot take dh=%lld dtype=%d", (long long)dh, dtype);
   if (engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && mma_ok && !env_flag("MAR_FORCE_SIMT"))) {
     mar_set_engine(MAR_ENGINE_TCGEN05);
+    // tcgen05/TMEM kernel where it applies; the mma.sync kernel covers the remaining head dims (MAR_ATTN_MMA=1 forces it)
+    if (attention_tc_supported(B, T, H, dh, dtype) && !env_flag("MAR_ATTN_MMA"))
+      return attention_fwd_tc(qkv, key_mask, out, lse, B, T, H, dh, p_drop, rng_state, site, S(stream));
     return attention_fwd_mma(qkv, key_mask, out, lse, B, T, H, dh, p_drop, rng_state, site, S(stream));
   }
   mar_set_engine(MAR_ENGINE_SIMT);

@@ -15,3 +15,8 @@ int attention_fwd_mma(const void* qkv, const uint8_t* key_mask, void* out, float
 int attention_bwd_mma(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
                       float* delta, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, float p,
                       const uint64_t* rng, uint32_t site, cudaStream_t st);
+
+// tcgen05 / TMEM / TMA engine (attention_tc.cu), bf16, dh in {64, 96, 128}
+bool attention_tc_supported(int64_t B, int64_t T, int64_t H, int64_t dh, int dtype);
+int attention_fwd_tc(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
+                     int64_t dh, float p, const uint64_t* rng, uint32_t site, cudaStream_t st);

@@ -1,0 +1,414 @@
+// tcgen05 / TMEM / TMA attention over the packed in-projection output (B,T,3d): forward.
+//
+//   O = softmax(Q·Kᵀ/√dh + key mask)·V   per (batch b, head h), flash-style (scores never reach HBM).
+//
+// One CTA owns 128 query rows of one (b,h); two CTAs are resident per SM (96 KB smem, 256 TMEM columns each)
+// so one CTA's softmax overlaps the other CTA's MMAs.  192 threads:
+//   warp 0   lane 0: TMA producer + MMA issuer.  Q / K / V tiles are [128 rows x dh] bf16, staged by TMA
+//            (3-D tensor map (col, t, b): rows t >= T are ZERO-filled by the hardware, so tiles never read the
+//            next batch element) as 128 B-swizzled boxes of 64 columns.
+//            S = Q·Kᵀ      : tcgen05.mma  M=128, N=keys (16..128), K=dh     A,B from smem (K-major)
+//            O += P̃·V      : tcgen05.mma  M=128, N=dh,             K=keys   A = P̃ from TMEM, B = V from smem (MN-major)
+//   warp 1   TMEM allocator; packs the key-padding mask into 128-bit validity words per key tile.
+//   warps 2-5 softmax: thread r owns query row r (TMEM lane r).  Two passes over the S row in TMEM
+//            (tcgen05.ld 32 columns at a time): row max, then exp2 / row sum / dropout / bf16 pack and
+//            tcgen05.st of P̃ into the columns S occupied.  The running max is only raised when the tile max
+//            exceeds it by 2^8 (lazy rescaling), in which case the O accumulator row is rescaled in TMEM.
+//
+// Dropout on P uses the shared counter hash (common.cuh) with the element index ((b·H+h)·T + q)·Tp + k, the
+// same function as the SIMT and mma.sync engines, so any engine's backward regenerates this forward's mask.
+// Fully masked rows give O = 0 and LSE = -inf (torch 2.11 safe softmax).
+//
+// Roofline: tensor pipe (4·T²·dh FLOP per (b,h)); the softmax's exp2 (16/clk/SM) and the dropout hash
+// (integer ALU) bound it below the MMA rate — see DESIGN.md §4.2.
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "attention.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BQ = 128;                 // query rows per CTA
+constexpr int BKV = 128;                // keys per tile
+constexpr int BOX_BYTES = 128 * 128;    // one TMA box: 128 rows x 64 bf16 (128 B, swizzled)
+constexpr int MAX_KV_TILES = 128;       // T <= 16384
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr float RESCALE_THRESHOLD = 8.f;   // log2 units: P̃ <= 2^8 before the reference max is raised
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// D[tmem] (+)= A[tmem] · B[smem desc]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct FwdParams {
+  const uint8_t* key_mask;
+  bf16* out;
+  float* lse;
+  int B, T, H;
+  float p_drop;
+  const uint64_t* rng;
+  uint32_t site;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
+  constexpr int NBOX = (DH + 63) / 64;
+  constexpr int OP_BYTES = NBOX * BOX_BYTES;
+  constexpr int KSTEPS = DH / 16;
+  constexpr uint32_t TMEM_COLS = 256;
+  constexpr uint32_t COL_S = 0, COL_P = 0, COL_O = 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + OP_BYTES;
+  uint8_t* sV = smem + 2 * OP_BYTES;
+  uint32_t* sValid = reinterpret_cast<uint32_t*>(smem + 3 * OP_BYTES);        // [MAX_KV_TILES][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sValid + MAX_KV_TILES * 4);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;     // S tile complete in TMEM (and the K smem tile is free)
+  uint64_t* bar_p = bars + 4;     // P̃ written to TMEM by the 4 softmax warps
+  uint64_t* bar_pv = bars + 5;    // P̃·V complete (O updated, V smem tile free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = p.T, H = p.H;
+  const int q_tiles = (T + BQ - 1) / BQ;
+  const int n_kv = (T + BKV - 1) / BKV;
+  const int bh = blockIdx.x / q_tiles, qt = blockIdx.x % q_tiles;
+  const int b = bh / H, h = bh % H;
+  const int d = H * DH;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm_qkv);
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 4); mbar_init(bar_pv, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+    // validity words: bit i of word w of tile j <=> key j*128 + w*32 + i is attended to
+    for (int w = 0; w < n_kv * 4; w++) {
+      const int k = w * 32 + lane;
+      const bool v = k < T && !(p.key_mask != nullptr && p.key_mask[(int64_t)b * T + k] != 0);
+      const uint32_t word = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) sValid[w] = word;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer + MMA issuer
+      auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col0, int row0) {
+        mbar_expect_tx(bar, OP_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < NBOX; bx++) tma_load_3d(dst + bx * BOX_BYTES, &tm_qkv, bar, col0 + bx * 64, row0, b);
+      };
+      auto issue_s = [&](int j) {
+        const int nk = min(BKV, T - j * BKV);
+        const uint32_t idesc = make_idesc_bf16(BQ, (nk + 15) & ~15, 0, 0);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ks++) {
+          const uint32_t qa = smem_u32(sQ + (ks / 4) * BOX_BYTES), ka = smem_u32(sK + (ks / 4) * BOX_BYTES);
+          umma_f16(tmem_base + COL_S, make_desc_kmajor(qa, ks % 4), make_desc_kmajor(ka, ks % 4), idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_s);
+      };
+      load_tile(sQ, bar_q, h * DH, qt * BQ);
+      load_tile(sK, bar_k, d + h * DH, 0);
+      load_tile(sV, bar_v, 2 * d + h * DH, 0);
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, 0);
+      tc_fence_after();
+      issue_s(0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 0, 1);
+      for (int j = 0; j < n_kv; j++) {
+        const uint32_t ph = j & 1;
+        if (j + 1 < n_kv) {                 // K tile is free once S_j is complete
+          mbar_wait(bar_s, ph);
+          load_tile(sK, bar_k, d + h * DH, (j + 1) * BKV);
+        }
+        mbar_wait(bar_p, ph);
+        mbar_wait(bar_v, ph);
+        tc_fence_after();
+        const int nk = min(BKV, T - j * BKV);
+        const int pv_steps = (nk + 15) / 16;
+        const uint32_t va = smem_u32(sV);
+        for (int ks = 0; ks < pv_steps; ks++)
+          umma_f16_ts(tmem_base + COL_O, tmem_base + COL_P + ks * 8, make_desc_mnmajor(va, ks, BOX_BYTES), idesc_pv,
+                      (j > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(bar_pv);
+        if (j + 1 < n_kv) {
+          mbar_wait(bar_k, ph ^ 1);
+          tc_fence_after();
+          issue_s(j + 1);                   // executes after P̃·V_j (in-order tensor pipe): S may overwrite P̃_j
+          mbar_wait(bar_pv, ph);            // V tile free
+          load_tile(sV, bar_v, 2 * d + h * DH, (j + 1) * BKV);
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    // ---------------------------------------------------------------- softmax: thread <-> query row
+    const int quarter = warp & 3;                        // TMEM lanes this warp may access
+    const int row = quarter * 32 + lane;
+    const int q = qt * BQ + row;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float scale2 = rsqrtf((float)DH) * LOG2E;
+    const bool drop = p.p_drop > 0.f;
+    DropKey dk;
+    dk.key = 0; dk.thr16 = 0; dk.scale = 1.f;
+    if (drop) dk = make_drop_key(p.rng, p.site, p.p_drop);
+    const uint64_t Tp = (uint64_t)((T + 1) & ~1);
+    const uint64_t pair_row0 = (((uint64_t)bh * (uint64_t)T + (uint64_t)q) * Tp) >> 1;
+    float m_ref = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < n_kv; j++) {
+      const uint32_t ph = j & 1;
+      const int nk = min(BKV, T - j * BKV);
+      const int nchunk = (nk + 31) / 32;
+      const uint32_t* vw = sValid + j * 4;
+      const bool full = (vw[0] & vw[1] & vw[2] & vw[3]) == 0xffffffffu;
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+
+      // pass 1: tile max of the raw scores
+      float mx = -INFINITY;
+      for (int c = 0; c < nchunk; c++) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(lane_addr + COL_S + c * 32, r);
+        tmem_ld_wait();
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+          const uint32_t word = vw[c];
+#pragma unroll
+          for (int i = 0; i < 32; i++) mx = fmaxf(mx, ((word >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY);
+        }
+      }
+      const float mt = mx * scale2;                      // -inf if every key of the tile is masked
+      const bool raise = mt > m_ref + RESCALE_THRESHOLD; // first finite tile: m_ref = -inf -> true
+      if (__any_sync(0xffffffffu, raise)) {
+        float factor = 1.f;
+        if (raise) {
+          factor = (m_ref == -INFINITY) ? 0.f : ex2f(m_ref - mt);
+          m_ref = mt;
+          l_run *= factor;
+        }
+        if (j > 0) {                                     // O holds the previous tiles' sum (P̃·V_{j-1} is complete)
+#pragma unroll
+          for (int c = 0; c < DH / 32; c++) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(lane_addr + COL_O + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
+            tmem_st_32x32b_x32(lane_addr + COL_O + c * 32, r);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+
+      // pass 2: P = exp2(s*scale2 - m), row sum, dropout, bf16 pack -> TMEM
+      const uint64_t pair_tile = pair_row0 + (uint64_t)(j * (BKV / 2));
+      for (int c = 0; c < nchunk; c++) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(lane_addr + COL_S + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+        const uint32_t word = vw[c];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          float e = ex2f(fmaf(__uint_as_float(r[i]), scale2, -m_use));
+          if (!full) e = ((word >> i) & 1u) ? e : 0.f;
+          pv[i] = e;
+          l_run += e;
+        }
+        uint32_t pk[16];
+        if (drop) {
+          const uint64_t pair0 = pair_tile + (uint64_t)(c * 16);
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            bool k0, k1;
+            drop_keep2(dk, pair0 + (uint64_t)i, k0, k1);
+            pk[i] = pack_bf16x2(k0 ? pv[2 * i] * dk.scale : 0.f, k1 ? pv[2 * i + 1] * dk.scale : 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i++) pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+        }
+        tmem_st_32x32b_x16(lane_addr + COL_P + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+    }
+
+    // epilogue: O / l -> bf16 -> global ; LSE
+    mbar_wait(bar_pv, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    bf16* orow = p.out + ((int64_t)b * T + q) * d + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 32; c++) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(lane_addr + COL_O + c * 32, r);
+      tmem_ld_wait();
+      if (q < T) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = u;
+        }
+      }
+    }
+    if (q < T) p.lse[(int64_t)bh * T + q] = l_run > 0.f ? (m_ref + log2f(l_run)) * LN2 : -INFINITY;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 3-D bf16 map over a (B, T, cols) tensor: box = 64 columns x box_rows tokens x 1 batch element, 128 B swizzle,
+// out-of-bounds (t >= T, col >= cols) reads as zero.
+int make_map_btc(CUtensorMap* map, const void* base, int64_t B, int64_t T, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) { mar_set_error("cuTensorMapEncodeTiled not available from the driver"); return MAR_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstride[2] = {(cuuint64_t)cols * 2, (cuuint64_t)T * (cuuint64_t)cols * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mar_set_error("cuTensorMapEncodeTiled (attention) failed (%d): B=%lld T=%lld cols=%lld base=%p", (int)r, (long long)B,
+                  (long long)T, (long long)cols, base);
+    return MAR_ERR_CUDA;
+  }
+  return MAR_OK;
+}
+
+template <int DH>
+int fwd_launch(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H, float p,
+               const uint64_t* rng, uint32_t site, cudaStream_t st) {
+  constexpr int NBOX = (DH + 63) / 64;
+  constexpr int SMEM = 3 * NBOX * BOX_BYTES + MAX_KV_TILES * 16 + 64 + 1024;
+  static bool cfg = false;
+  if (!cfg) {
+    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    cfg = true;
+  }
+  CUtensorMap tm;
+  int rc = make_map_btc(&tm, qkv, B, T, 3 * H * DH, BQ);
+  if (rc) return rc;
+  FwdParams prm;
+  prm.key_mask = key_mask; prm.out = (bf16*)out; prm.lse = lse; prm.B = (int)B; prm.T = (int)T; prm.H = (int)H;
+  prm.p_drop = p; prm.rng = rng; prm.site = site;
+  const int64_t q_tiles = ceil_div(T, BQ);
+  attn_fwd_tc_kernel<DH><<<(unsigned)(B * H * q_tiles), 192, SMEM, st>>>(tm, prm);
+  MAR_LAUNCH_CHECK("attn_fwd_tc");
+  return MAR_OK;
+}
+
+}  // namespace
+
+bool attention_tc_supported(int64_t B, int64_t T, int64_t H, int64_t dh, int dtype) {
+  if (dtype != MAR_BF16) return false;
+  if (!(dh == 64 || dh == 96 || dh == 128)) return false;
+  if (T < 1 || T > (int64_t)MAX_KV_TILES * BKV) return false;
+  if (B * H * ceil_div(T, BQ) >= (1ll << 31)) return false;
+  if ((3 * H * dh * 2) % 16 != 0) return false;
+  return true;
+}
+
+int attention_fwd_tc(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
+                     int64_t dh, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
+  MAR_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), "attention: pointers must be 16 B aligned");
+  switch (dh) {
+    case 64: return fwd_launch<64>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
+    case 96: return fwd_launch<96>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
+    case 128: return fwd_launch<128>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
+  }
+  MAR_UNSUPPORTED("attention (tcgen05 engine): head dim %lld", (long long)dh);
+}

@@ -62,8 +62,31 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, c
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma ; dgamma += Σ dy*xhat ; dbeta += Σ dy
+// Register diet (ncu: the first version held gamma, g and xhat in registers -> 158 regs, ONE 8-warp block per
+// SM, 24 KB of loads in flight per SM and 1/3 of HBM speed): the row is kept as the raw 16 B vectors it was loaded
+// as and decoded twice, gamma is re-read through L1 (3 KB, hot) -> <= 128 regs, 2 blocks = 16 warps per SM.
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 template <typename T, int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int D) {
@@ -73,55 +96,57 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
   const int64_t warp_stride = (int64_t)gridDim.x * warps_per_block;
   const float invD = 1.f / (float)D;
 
-  float gam[NCH][8], dg[NCH][8], db[NCH][8];
+  float dg[NCH][8], db[NCH][8];
 #pragma unroll
   for (int c = 0; c < NCH; c++) {
-    int col = (c * 32 + lane) * 8;
-    if (col < D) Vec8<float>::load(gamma + col, gam[c]);
 #pragma unroll
-    for (int j = 0; j < 8; j++) { dg[c][j] = 0.f; db[c][j] = 0.f; if (col >= D) gam[c][j] = 0.f; }
+    for (int j = 0; j < 8; j++) { dg[c][j] = 0.f; db[c][j] = 0.f; }
   }
 
   for (int64_t row = warp_global; row < rows; row += warp_stride) {
+    Raw8<T> ra[NCH], rb[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < D) { ra[c].load(dy + row * D + col); rb[c].load(x + row * D + col); }
+    }
     const float mu = mean[row], rs = rstd[row];
-    float g[NCH][8], xh[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
-      int col = (c * 32 + lane) * 8;
+      const int col = (c * 32 + lane) * 8;
       if (col < D) {
-        float a[8], b[8];
-        Vec8<T>::load(dy + row * D + col, a);
-        Vec8<T>::load(x + row * D + col, b);
+        float a[8], b[8], gm[8];
+        ra[c].get(a); rb[c].get(b);
+        Vec8<float>::load(gamma + col, gm);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          xh[c][j] = (b[j] - mu) * rs;
-          dg[c][j] += a[j] * xh[c][j];
+          const float xh = (b[j] - mu) * rs;
+          const float g = a[j] * gm[j];
+          dg[c][j] += a[j] * xh;
           db[c][j] += a[j];
-          g[c][j] = a[j] * gam[c][j];
-          s1 += g[c][j];
-          s2 += g[c][j] * xh[c][j];
+          s1 += g;
+          s2 += g * xh;
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++) { g[c][j] = 0.f; xh[c][j] = 0.f; }
       }
     }
     s1 = warp_sum(s1) * invD;
     s2 = warp_sum(s2) * invD;
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
-      int col = (c * 32 + lane) * 8;
+      const int col = (c * 32 + lane) * 8;
       if (col < D) {
-        float o[8];
+        float a[8], b[8], gm[8], o[8];
+        ra[c].get(a); rb[c].get(b);
+        Vec8<float>::load(gamma + col, gm);
 #pragma unroll
-        for (int j = 0; j < 8; j++) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
+        for (int j = 0; j < 8; j++) o[j] = rs * (a[j] * gm[j] - s1 - (b[j] - mu) * rs * s2);
         Vec8<T>::store(dx + row * D + col, o);
       }
     }
   }
 
-  // block reduction of the column partials: 8 warps -> 1, then one atomicAdd per column per block
+  // block reduction of the column partials: 8 warps -> 1, then one vector atomicAdd per 4 columns per block
   extern __shared__ float red[];  // [warps][D] reused for dgamma then dbeta
   for (int pass = 0; pass < 2; pass++) {
 #pragma unroll
@@ -176,7 +201,7 @@ int launch_bwd(const void* dy, const void* x, const float* mean, const float* rs
                float* dgamma, float* dbeta, int64_t rows, int64_t D, cudaStream_t st) {
   const int nch = (int)ceil_div(D, 256);
   int64_t blocks = ceil_div(rows, 8 * 4);
-  int64_t cap = (int64_t)mar_sm_count() * 2;    // few blocks: the column partials end in one atomic per block
+  int64_t cap = (int64_t)mar_sm_count() * 2;    // one resident wave (2 blocks/SM): the column partials end in one atomic per block
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   size_t smem = (size_t)8 * D * sizeof(float);
