@@ -116,9 +116,11 @@ int mar_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n
 int mar_attention_fwd(const void* qkv, const uint8_t* key_mask, void* out, float* lse,
                       int64_t B, int64_t T, int64_t H, int64_t dh, int dtype, float p_drop,
                       const uint64_t* rng_state, uint32_t site, int engine, void* stream);
-/* dqkv (B,T,3d) from dout (B,T,d).  delta (B,H,T) fp32 is workspace. */
+/* dqkv (B,T,3d) from dout (B,T,d).  work: mar_attention_bwd_work_floats() floats of 16 B-aligned scratch
+ * (delta = rowsum(dO ⊙ O) (B,H,T), then the tcgen05 engine's fp32 dQ accumulator (B,T,d) when T > 128). */
+int64_t mar_attention_bwd_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh);
 int mar_attention_bwd(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout,
-                      const float* lse, float* delta, void* dqkv, int64_t B, int64_t T, int64_t H,
+                      const float* lse, float* work, void* dqkv, int64_t B, int64_t T, int64_t H,
                       int64_t dh, int dtype, float p_drop, const uint64_t* rng_state, uint32_t site,
                       int engine, void* stream);
 

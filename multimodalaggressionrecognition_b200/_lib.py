@@ -39,6 +39,7 @@ PROTOTYPES = {
     "mar_attention_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, c_uint32, c_int, P]),
     "mar_attention_bwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P,
                                   c_uint32, c_int, P]),
+    "mar_attention_bwd_work_floats": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
     "mar_layernorm_fwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_float, c_int, P]),
     "mar_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, P]),
     "mar_meanpool_fwd": (c_int, [P, P, c_int64, c_int64, c_int64, c_int, P]),

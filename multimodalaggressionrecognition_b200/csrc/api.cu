@@ -180,10 +180,17 @@ int mar_attention_bwd(const void* qkv, const uint8_t* key_mask, const void* out,
   if (engine == MAR_ENGINE_TCGEN05 && !mma_ok) MAR_UNSUPPORTED("mar_attention_bwd: tensor-core engine cannot take dh=%lld dtype=%d", (long long)dh, dtype);
   if (engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && mma_ok && !env_flag("MAR_FORCE_SIMT"))) {
     mar_set_engine(MAR_ENGINE_TCGEN05);
+    if (attention_tc_supported(B, T, H, dh, dtype) && !env_flag("MAR_ATTN_MMA") && !env_flag("MAR_ATTN_BWD_MMA"))
+      return attention_bwd_tc(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p_drop, rng_state, site, S(stream));
     return attention_bwd_mma(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p_drop, rng_state, site, S(stream));
   }
   mar_set_engine(MAR_ENGINE_SIMT);
   return attention_bwd_simt(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, dtype, p_drop, rng_state, site, S(stream));
+}
+
+int64_t mar_attention_bwd_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh) {
+  if (B <= 0 || T <= 0 || H <= 0 || dh <= 0) return 0;
+  return attention_bwd_tc_work_floats(B, T, H, dh);   // >= B*H*T, which is all the other engines need
 }
 
 // ------------------------------------------------------------------------------------------

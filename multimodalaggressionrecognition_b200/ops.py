@@ -353,9 +353,10 @@ class _Attention(torch.autograd.Function):
             dout = _Cast.apply(dout, qkv.dtype)
         dout = dout.contiguous()
         dqkv = torch.empty_like(qkv)
-        delta = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+        nwork = int(_lib.load().mar_attention_bwd_work_floats(B, T, H, dh))
+        work = torch.empty(nwork, dtype=torch.float32, device=qkv.device)
         call("mar_attention_bwd", qkv.data_ptr(), _p(key_mask), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-             delta.data_ptr(), dqkv.data_ptr(), B, T, H, dh, _dt(qkv), ctx.p, _p(ctx.rng), ctx.site, ctx.eng, _stream())
+             work.data_ptr(), dqkv.data_ptr(), B, T, H, dh, _dt(qkv), ctx.p, _p(ctx.rng), ctx.site, ctx.eng, _stream())
         return dqkv, None, None, None
 
 

@@ -177,6 +177,33 @@ def test_attention_fwd_bwd(B, T, H, dh, mode, masked):
     assert_close(qg.grad.float().cpu(), qr.grad, tol, "attention dqkv")
 
 
+@pytest.mark.parametrize("B,T,H,dh", [(2, 128, 2, 96), (2, 129, 2, 64), (1, 256, 8, 96), (2, 700, 2, 128), (1, 1100, 1, 96),
+                                      (5, 17, 3, 64)])
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_attention_bwd_tcgen05_matches_mma_engine(B, T, H, dh, p, monkeypatch):
+    """The one-kernel tcgen05 backward (fp32 dQ reduction across key tiles) against the mma.sync engine on the same
+    forward, the same dropout mask (both regenerate it from the counter hash) and a key-padding mask."""
+    d = H * dh
+    qkv = (torch.randn(B, T, 3 * d, device=DEV)).to(torch.bfloat16)
+    go = torch.randn(B, T, d, device=DEV).to(torch.bfloat16)
+    mask = torch.rand(B, T, device=DEV) < 0.2
+    mask[0, : max(1, T // 2)] = False
+    mask[-1, T - T // 4:] = True
+    grads = {}
+    for eng in ("tc", "mma"):
+        monkeypatch.setenv("MAR_ATTN_BWD_MMA", "1" if eng == "mma" else "0")
+        mar.manual_seed(1234)
+        q = qkv.clone().requires_grad_(True)
+        with mar.precision("bf16"):
+            out = ops.attention(q, mask, H, p)
+            out.backward(go)
+        grads[eng] = q.grad.float()
+    assert torch.isfinite(grads["tc"]).all()
+    for name, sl in (("dQ", slice(0, d)), ("dK", slice(d, 2 * d)), ("dV", slice(2 * d, 3 * d))):
+        assert_close(grads["tc"][..., sl], grads["mma"][..., sl], 6e-3, f"tcgen05 vs mma backward {name}")
+    assert float(grads["tc"][-1, T - T // 4:, d:].abs().max()) == 0.0       # masked keys get no dK / dV
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_attention_fully_masked_rows_give_zero(mode):
     """All keys masked (all-EMPTY batch): P = 0, O = 0, finite grads (torch 2.11 safe softmax)."""
