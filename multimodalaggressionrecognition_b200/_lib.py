@@ -12,7 +12,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmar.so")
+LIB_PATH = os.environ.get("MAR_LIB", os.path.join(_HERE, "libmar.so"))   # MAR_LIB: debugging builds of the same ABI
 
 MAR_F32, MAR_BF16 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2

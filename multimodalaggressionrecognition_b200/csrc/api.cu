@@ -25,6 +25,10 @@ void mar_set_error(const char* fmt, ...) {
 }
 void mar_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void mar_set_engine(int e) { g_engine = e; }
+bool mar_debug_sync() {
+  static const bool on = [] { const char* v = getenv("MAR_DEBUG_SYNC"); return v != nullptr && v[0] != '\0' && v[0] != '0'; }();
+  return on;
+}
 
 int mar_sm_count() {
   if (g_sm_count == 0) {

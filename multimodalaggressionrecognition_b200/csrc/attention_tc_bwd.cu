@@ -3,25 +3,31 @@
 //   P = exp(S - LSE),  P̃ = dropout(P),  dV = P̃ᵀ·dO,  dP = dropoutᵀ(dO·Vᵀ),  dS = P ⊙ (dP - delta),
 //   dQ = dS·K / √dh,   dK = dSᵀ·Q / √dh                          delta = rowsum(dO ⊙ O)
 //
-// One CTA owns 128 KEYS of one (b,h) and walks over the query tiles (128 rows each); everything is computed on
+// One CTA owns 128 KEYS of one (b,h) and walks over the query tiles (64 rows each); everything is computed on
 // the TRANSPOSED score tile so that the probability operands sit in TMEM with keys as lanes:
-//   Sᵀ  = K·Qᵀ       tcgen05.mma  M=128 keys, N=queries, K=dh    A = K tile, B = Q tile (both K-major smem)
-//   dPᵀ = V·dOᵀ      tcgen05.mma  same shape                     A = V tile, B = dO tile
-//   dV += P̃ᵀ·dO      tcgen05.mma  M=128 keys, N=dh, K=queries    A = P̃ᵀ bf16 in TMEM,  B = dO tile (MN-major)
-//   dK += dSᵀ·Q      tcgen05.mma  same shape                     A = dSᵀ bf16 in TMEM, B = Q tile  (MN-major)
-//   dQ  = dS·K       tcgen05.mma  M=128 queries, N=dh, K=keys    A = dSᵀ bf16 in smem (MN-major), B = K tile (MN-major)
-// dK / dV accumulate in TMEM over the whole walk; dQ tiles are reduced across the key tiles of a (b,h) with
-// red.global.add.v4.f32 into an fp32 (B,T,d) workspace (converted to bf16 by attn_dq_convert_kernel), or
-// written straight to dqkv when T <= 128 (one key tile).  5 contractions per tile pair, nothing recomputed.
+//   Sᵀ  = K·Qᵀ       tcgen05.mma  M=128 keys, N=64 queries, K=dh   A = K tile, B = Q tile (both K-major smem)
+//   dPᵀ = V·dOᵀ      tcgen05.mma  same shape                       A = V tile, B = dO tile
+//   dV += P̃ᵀ·dO      tcgen05.mma  M=128 keys, N=dh, K=64 queries   A = P̃ᵀ bf16 in TMEM,  B = dO tile (MN-major)
+//   dK += dSᵀ·Q      tcgen05.mma  same shape                       A = dSᵀ bf16 in TMEM, B = Q tile  (MN-major)
+//   dQᵀ = Kᵀ·dSᵀ     tcgen05.mma  M=128 (dh, padded), N=64 queries, K=keys
+//                                                                  A = K tile (MN-major), B = dSᵀ bf16 in smem (MN-major)
+// dK / dV accumulate in TMEM over the whole walk.  dQ is produced TRANSPOSED so that it costs 64 TMEM columns
+// instead of dh, which leaves room for a DOUBLE-BUFFERED Sᵀ/dPᵀ (dh <= 96): the MMAs of tile i+1 run under
+// the softmax-gradient arithmetic of tile i, and the accumulating MMAs + dQ read-out of tile i under tile i+1.
+// dQᵀ tiles are reduced across the key tiles of a (b,h) with coalesced red.global.add.f32 (lane <-> dh
+// column) into an fp32 (B,T,d) workspace (converted to bf16 by attn_dq_convert_kernel), or written straight
+// to dqkv when T <= 128 (one key tile).  5 contractions per tile pair, nothing recomputed.
 //
-// 18 warps: warp 0 lane 0 = TMA producer + MMA issuer; warp 1 = TMEM allocator + LSE/delta stager;
-// warps 2-17 = 16 compute warps, thread <-> key row (TMEM lane), each warp owns one 32-query column chunk of one
-// TMEM lane quarter.  Q / dO tiles are double-buffered by TMA (3-D maps, rows >= T zero-filled).
+// 22 warps: warp 0 (one elected lane) = TMA producer + MMA issuer; warp 1 = TMEM allocator + LSE/delta stager;
+// warps 2-17 = 16 compute warps, thread <-> key row (TMEM lane), each warp owns one 16-query column chunk of one
+// TMEM lane quarter; warps 18-21 = dQᵀ read-out (one per lane quarter).  Q / dO tiles ride a 3-stage TMA ring
+// (3-D maps, rows >= T zero-filled).
 //
-// TMEM columns (512): Sᵀ [0,128) (P̃ᵀ packed bf16 in [0,64)) | dPᵀ [128,256) (dSᵀ packed bf16 in [192,256)) |
-//                     dQ [64,64+dh) (aliases the dead halves of Sᵀ/dPᵀ) | dK [256,256+dh) | dV [384,384+dh).
+// TMEM columns: dK [0,dh) | dV [dh,2dh) | dQᵀ [2dh,2dh+64) | stage s: Sᵀ 64 (P̃ᵀ packed bf16 in its first 32)
+//               + dPᵀ 64 (dSᵀ packed in its first 32).   dh=96: 192+64+2·128 = 512.   dh=128: one stage.
 // Dropout: the shared counter hash with element index ((b·H+h)·T + q)·Tp + k (common.cuh), i.e. the mask the
 // forward of ANY engine drew.  Fully masked rows (LSE = -inf) contribute nothing.
+#include <algorithm>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "attention.cuh"
@@ -32,10 +38,14 @@ using namespace attn_tc;
 
 namespace {
 
-constexpr int BT = 128;                 // keys per CTA and queries per step
+constexpr int BT = 128;                 // keys per CTA
+constexpr int BQ = 64;                  // queries per step
 constexpr int NCOMPUTE = 16;            // compute warps
-constexpr int NTHREADS = (2 + NCOMPUTE) * 32;
-constexpr uint32_t COL_S = 0, COL_P = 0, COL_DP = 128, COL_DS = 192, COL_DQ = 64, COL_DK = 256, COL_DV = 384;
+constexpr int NREAD = 4;                // dQᵀ read-out warps
+constexpr int NTHREADS = (2 + NCOMPUTE + NREAD) * 32;
+constexpr int QSTAGES = 3;              // Q / dO smem ring
+constexpr int LSTAGES = 4;              // LSE / delta smem ring
+constexpr int QBOX_BYTES = BQ * 128;    // one 64-row x 64-column box
 
 struct BwdParams {
   const uint8_t* key_mask;
@@ -50,65 +60,78 @@ struct BwdParams {
   int smem_bytes;
 };
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void red_add_f32(float* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 
 template <int DH>
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const BwdParams p) {
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
+                   const __grid_constant__ CUtensorMap tm_do, const BwdParams p) {
   constexpr int NBOX = (DH + 63) / 64;
-  constexpr int OP_BYTES = NBOX * BOX_BYTES;
+  constexpr int KV_BYTES = NBOX * BOX_BYTES;        // 128-row operand tile
+  constexpr int Q_BYTES = NBOX * QBOX_BYTES;        // 64-row operand tile
   constexpr int KSTEPS = DH / 16;
-  constexpr int DS_BYTES = 2 * BOX_BYTES;
+  constexpr int DS_BYTES = BT * 128;                // dSᵀ bf16 [128 keys][64 queries], 128 B swizzle
+  constexpr int NST = (2 * DH + 64 + 2 * 128 <= 512) ? 2 : 1;     // Sᵀ/dPᵀ TMEM stages
+  constexpr int LOOK = NST - 1;
+  constexpr uint32_t COL_DK = 0, COL_DV = DH, COL_DQ = 2 * DH, COL_ST = 2 * DH + 64;   // stage s at COL_ST + 128 s
+  constexpr uint32_t TMEM_COLS = 512;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
-  uint8_t* sV = sK + OP_BYTES;
-  uint8_t* sQ = sV + OP_BYTES;            // [2][OP_BYTES]
-  uint8_t* sDO = sQ + 2 * OP_BYTES;       // [2][OP_BYTES]
-  uint8_t* sDS = sDO + 2 * OP_BYTES;      // dSᵀ bf16 [2 atoms of 64 queries][128 keys][64], 128 B swizzle
-  float* sL = reinterpret_cast<float*>(sDS + DS_BYTES);   // [2][128] LSE in log2 units (+inf = no contribution)
-  float* sD = sL + 2 * BT;                                // [2][128] delta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * BT);
+  uint8_t* sV = sK + KV_BYTES;
+  uint8_t* sQ = sV + KV_BYTES;                  // [QSTAGES][Q_BYTES]
+  uint8_t* sDO = sQ + QSTAGES * Q_BYTES;        // [QSTAGES][Q_BYTES]
+  uint8_t* sDS = sDO + QSTAGES * Q_BYTES;       // [2][DS_BYTES]
+  float* sL = reinterpret_cast<float*>(sDS + 2 * DS_BYTES);   // [LSTAGES][64] LSE in log2 units (+inf = no contribution)
+  float* sD = sL + LSTAGES * BQ;                              // [LSTAGES][64] delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + LSTAGES * BQ);
   uint64_t* bar_kv = bars + 0;
-  uint64_t* bar_qdo = bars + 1;       // [2] Q_i / dO_i tiles landed
-  uint64_t* bar_ld = bars + 3;        // [2] LSE / delta of tile i staged
-  uint64_t* bar_ldfree = bars + 5;    // [2] compute warps are done with that LSE / delta stage
-  uint64_t* bar_s = bars + 7;         // Sᵀ, dPᵀ complete in TMEM
-  uint64_t* bar_pds = bars + 8;       // P̃ᵀ, dSᵀ written (TMEM + smem) by the compute warps
-  uint64_t* bar_mma2 = bars + 9;      // dV, dK, dQ MMAs complete (Q_i / dO_i smem stage free)
-  uint64_t* bar_dqr = bars + 10;      // dQ tile read out of TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* bar_qdo = bars + 1;                 // [QSTAGES] Q_i / dO_i tiles landed
+  uint64_t* bar_ld = bars + 4;                  // [LSTAGES] LSE / delta of tile i staged
+  uint64_t* bar_ldfree = bars + 8;              // [LSTAGES] compute warps are done with that stage
+  uint64_t* bar_s = bars + 12;                  // [2] Sᵀ, dPᵀ of a TMEM stage complete
+  uint64_t* bar_pds = bars + 14;                // [2] P̃ᵀ, dSᵀ written (TMEM + smem) by the compute warps
+  uint64_t* bar_mma2 = bars + 16;               // dV, dK, dQᵀ MMAs of tile i complete
+  uint64_t* bar_dqr = bars + 17;                // dQᵀ tile read out of TMEM
+  uint64_t* bar_done = bars + 18;               // every MMA of this CTA complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   if (reinterpret_cast<uint8_t*>(tmem_slot + 2) > smem_raw + p.smem_bytes) __trap();   // dynamic smem base less aligned than assumed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T, H = p.H;
-  const int n_t = (T + BT - 1) / BT;      // key tiles == query tiles
-  const int bh = blockIdx.x / n_t, kt = blockIdx.x % n_t;
+  const int n_kt = (T + BT - 1) / BT;     // key tiles
+  const int n_q = (T + BQ - 1) / BQ;      // query tiles
+  const int bh = blockIdx.x / n_kt, kt = blockIdx.x % n_kt;
   const int b = bh / H, h = bh % H;
   const int d = H * DH;
   const int nk = min(BT, T - kt * BT);    // keys of this tile inside the sequence
 
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tm_qkv);
+    prefetch_tensormap(&tm_kv);
+    prefetch_tensormap(&tm_q);
     prefetch_tensormap(&tm_do);
     mbar_init(bar_kv, 1);
-    mbar_init(bar_qdo + 0, 1); mbar_init(bar_qdo + 1, 1);
-    mbar_init(bar_ld + 0, 1); mbar_init(bar_ld + 1, 1);
-    mbar_init(bar_ldfree + 0, NCOMPUTE); mbar_init(bar_ldfree + 1, NCOMPUTE);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_pds, NCOMPUTE);
+    for (int i = 0; i < QSTAGES; i++) mbar_init(bar_qdo + i, 1);
+    for (int i = 0; i < LSTAGES; i++) { mbar_init(bar_ld + i, 1); mbar_init(bar_ldfree + i, NCOMPUTE); }
+    for (int i = 0; i < 2; i++) { mbar_init(bar_s + i, 1); mbar_init(bar_pds + i, NCOMPUTE); }
     mbar_init(bar_mma2, 1);
-    mbar_init(bar_dqr, NCOMPUTE);
+    mbar_init(bar_dqr, NREAD);
+    mbar_init(bar_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -117,89 +140,121 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer + MMA issuer
-      auto load_tile = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int col0, int row0) {
+    // ---------------------------------------------------------------- TMA producer + MMA issuer
+    // The whole warp walks this code converged and waits on the mbarriers together; one elected lane issues the
+    // TMA / tcgen05 instructions, so every operand is warp-uniform (no per-thread operand marshalling loops).
+    auto load_qdo = [&](int i) {
+      const int s = i % QSTAGES;
+      mbar_expect_tx(bar_qdo + s, 2 * Q_BYTES);
 #pragma unroll
-        for (int bx = 0; bx < NBOX; bx++) tma_load_3d(dst + bx * BOX_BYTES, map, bar, col0 + bx * 64, row0, b);
-      };
-      auto load_qdo = [&](int i) {
-        const int s = i & 1;
-        mbar_expect_tx(bar_qdo + s, 2 * OP_BYTES);
-        load_tile(sQ + s * OP_BYTES, &tm_qkv, bar_qdo + s, h * DH, i * BT);
-        load_tile(sDO + s * OP_BYTES, &tm_do, bar_qdo + s, h * DH, i * BT);
-      };
-      mbar_expect_tx(bar_kv, 2 * OP_BYTES);
-      load_tile(sK, &tm_qkv, bar_kv, d + h * DH, kt * BT);
-      load_tile(sV, &tm_qkv, bar_kv, 2 * d + h * DH, kt * BT);
-      load_qdo(0);
-      if (n_t > 1) load_qdo(1);
-      mbar_wait(bar_kv, 0);
+      for (int bx = 0; bx < NBOX; bx++) {
+        tma_load_3d(sQ + s * Q_BYTES + bx * QBOX_BYTES, &tm_q, bar_qdo + s, h * DH + bx * 64, i * BQ, b);
+        tma_load_3d(sDO + s * Q_BYTES + bx * QBOX_BYTES, &tm_do, bar_qdo + s, h * DH + bx * 64, i * BQ, b);
+      }
+    };
+    if (elect_one()) {
+      mbar_expect_tx(bar_kv, 2 * KV_BYTES);
+#pragma unroll
+      for (int bx = 0; bx < NBOX; bx++) {
+        tma_load_3d(sK + bx * BOX_BYTES, &tm_kv, bar_kv, d + h * DH + bx * 64, kt * BT, b);
+        tma_load_3d(sV + bx * BOX_BYTES, &tm_kv, bar_kv, 2 * d + h * DH + bx * 64, kt * BT, b);
+      }
+      for (int i = 0; i < QSTAGES && i < n_q; i++) load_qdo(i);
+    }
+    __syncwarp();
 
-      constexpr uint32_t idesc_acc = make_idesc_bf16(BT, DH, 0, 1);   // dV, dK: A in TMEM, B MN-major
-      constexpr uint32_t idesc_dq = make_idesc_bf16(BT, DH, 1, 1);    // dQ: A and B MN-major smem
-      const int ksteps_keys = (nk + 15) / 16;
-      for (int i = 0; i < n_t; i++) {
-        const int s = i & 1;
-        const int nq = min(BT, T - i * BT);
-        mbar_wait(bar_qdo + s, (i >> 1) & 1);
-        if (i > 0) mbar_wait(bar_dqr, (i - 1) & 1);     // dQ_{i-1} has left the columns Sᵀ_i will overwrite
-        tc_fence_after();
-        const uint32_t idesc_s = make_idesc_bf16(BT, (nq + 15) & ~15, 0, 0);
-        const uint8_t* q_s = sQ + s * OP_BYTES;
-        const uint8_t* do_s = sDO + s * OP_BYTES;
+    constexpr uint32_t idesc_acc = make_idesc_bf16(BT, DH, 0, 1);   // dV, dK: A in TMEM, B MN-major
+    constexpr uint32_t idesc_dq = make_idesc_bf16(128, BQ, 1, 1);   // dQᵀ: A = K tile MN-major, B = dSᵀ MN-major
+    const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO), sDS_a = smem_u32(sDS);
+    const int ksteps_keys = (nk + 15) / 16;
+    mbar_wait(bar_kv, 0);
+
+    int issued = 0;
+    auto issue_s = [&](int i) {           // Sᵀ_i and dPᵀ_i into TMEM stage i % NST
+      const int s = i % QSTAGES;
+      const int nq = min(BQ, T - i * BQ);
+      const uint32_t col = tmem_base + COL_ST + (uint32_t)(i % NST) * 128;
+      const uint32_t idesc_s = make_idesc_bf16(BT, (nq + 15) & ~15, 0, 0);
+      mbar_wait(bar_qdo + s, (i / QSTAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ks++)
-          umma_f16(tmem_base + COL_S, make_desc_kmajor(smem_u32(sK + (ks / 4) * BOX_BYTES), ks % 4),
-                   make_desc_kmajor(smem_u32(q_s + (ks / 4) * BOX_BYTES), ks % 4), idesc_s, ks > 0 ? 1u : 0u);
+          umma_f16(col, make_desc_kmajor(sK_a + (ks / 4) * BOX_BYTES, ks % 4),
+                   make_desc_kmajor(sQ_a + s * Q_BYTES + (ks / 4) * QBOX_BYTES, ks % 4), idesc_s, ks > 0 ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ks++)
-          umma_f16(tmem_base + COL_DP, make_desc_kmajor(smem_u32(sV + (ks / 4) * BOX_BYTES), ks % 4),
-                   make_desc_kmajor(smem_u32(do_s + (ks / 4) * BOX_BYTES), ks % 4), idesc_s, ks > 0 ? 1u : 0u);
-        umma_commit(bar_s);
-
-        mbar_wait(bar_pds, i & 1);
+          umma_f16(col + 64, make_desc_kmajor(sV_a + (ks / 4) * BOX_BYTES, ks % 4),
+                   make_desc_kmajor(sDO_a + s * Q_BYTES + (ks / 4) * QBOX_BYTES, ks % 4), idesc_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_s + (i % NST));
+      }
+      __syncwarp();
+    };
+    auto ensure_s = [&](int upto) {
+      while (issued <= upto && issued < n_q) { issue_s(issued); issued++; }
+    };
+    ensure_s(LOOK);
+    for (int i = 0; i < n_q; i++) {
+      const int s = i % QSTAGES;
+      const int nq = min(BQ, T - i * BQ);
+      const int qsteps = (nq + 15) / 16;
+      const uint32_t col = tmem_base + COL_ST + (uint32_t)(i % NST) * 128;
+      mbar_wait(bar_pds + (i % NST), (i / NST) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll 1
+        for (int ks = 0; ks < qsteps; ks++)
+          umma_f16_ts(tmem_base + COL_DV, col + ks * 8, make_desc_mnmajor(sDO_a + s * Q_BYTES, ks, QBOX_BYTES), idesc_acc,
+                      (i > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll 1
+        for (int ks = 0; ks < qsteps; ks++)
+          umma_f16_ts(tmem_base + COL_DK, col + 64 + ks * 8, make_desc_mnmajor(sQ_a + s * Q_BYTES, ks, QBOX_BYTES), idesc_acc,
+                      (i > 0 || ks > 0) ? 1u : 0u);
+      }
+      __syncwarp();
+      if (i > 0) {                            // dQᵀ_{i-1} has left its TMEM columns
+        mbar_wait(bar_dqr, (i - 1) & 1);
         tc_fence_after();
-        const int qsteps = (nq + 15) / 16;
-        for (int ks = 0; ks < qsteps; ks++)
-          umma_f16_ts(tmem_base + COL_DV, tmem_base + COL_P + ks * 8, make_desc_mnmajor(smem_u32(do_s), ks, BOX_BYTES),
-                      idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
-        for (int ks = 0; ks < qsteps; ks++)
-          umma_f16_ts(tmem_base + COL_DK, tmem_base + COL_DS + ks * 8, make_desc_mnmajor(smem_u32(q_s), ks, BOX_BYTES),
-                      idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
+      }
+      if (elect_one()) {
+#pragma unroll 1
         for (int ks = 0; ks < ksteps_keys; ks++)
-          umma_f16(tmem_base + COL_DQ, make_desc_mnmajor(smem_u32(sDS), ks, BOX_BYTES),
-                   make_desc_mnmajor(smem_u32(sK), ks, BOX_BYTES), idesc_dq, ks > 0 ? 1u : 0u);
+          umma_f16(tmem_base + COL_DQ, make_desc_mnmajor(sK_a, ks, BOX_BYTES),
+                   make_desc_mnmajor(sDS_a + (i & 1) * DS_BYTES, ks, DS_BYTES), idesc_dq, ks > 0 ? 1u : 0u);
         umma_commit(bar_mma2);
-        if (i + 2 < n_t) {
-          mbar_wait(bar_mma2, i & 1);       // stage s is free again
-          load_qdo(i + 2);
-        }
+        if (i == n_q - 1) umma_commit(bar_done);
+      }
+      __syncwarp();
+      ensure_s(i + 1 + LOOK);                 // its TMEM stage was freed by the (in-order) dV/dK MMAs just issued
+      if (i + QSTAGES < n_q) {
+        mbar_wait(bar_mma2, i & 1);           // Q_i / dO_i smem stage is free again
+        if (elect_one()) load_qdo(i + QSTAGES);
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- LSE / delta stager
-    for (int i = 0; i < n_t; i++) {
-      const int s = i & 1;
-      if (i >= 2) mbar_wait(bar_ldfree + s, ((i >> 1) - 1) & 1);
-      for (int k = lane; k < BT; k += 32) {
-        const int q = i * BT + k;
+    for (int i = 0; i < n_q; i++) {
+      const int s = i % LSTAGES;
+      if (i >= LSTAGES) mbar_wait(bar_ldfree + s, ((i / LSTAGES) - 1) & 1);
+      for (int k = lane; k < BQ; k += 32) {
+        const int q = i * BQ + k;
         float l = INFINITY, dl = 0.f;
         if (q < T) {
           l = p.lse[(int64_t)bh * T + q] * LOG2E;
           if (l == -INFINITY) l = INFINITY;        // fully masked row: P = 0
           dl = p.delta[(int64_t)bh * T + q];
         }
-        sL[s * BT + k] = l;
-        sD[s * BT + k] = dl;
+        sL[s * BQ + k] = l;
+        sD[s * BQ + k] = dl;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ld + s);
     }
-  } else {
+  } else if (warp < 2 + NCOMPUTE) {
     // ---------------------------------------------------------------- compute warps: thread <-> key row
     const int quarter = warp & 3;                       // TMEM lanes this warp may access
-    const int chunk = (warp - 2) >> 2;                  // 32-query column chunk
+    const int chunk = (warp - 2) >> 2;                  // 16-query column chunk
     const int row = quarter * 32 + lane;
     const int key = kt * BT + row;
     const bool kvalid = key < T && !(p.key_mask != nullptr && p.key_mask[(int64_t)b * T + key] != 0);
@@ -212,107 +267,72 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const uint64_t Tp = (uint64_t)((T + 1) & ~1);
     const uint64_t half_tp = Tp >> 1;
     const bool hi_half = (key & 1) != 0;
-    // dSᵀ smem row of this key: [atom = chunk/2][row][64 queries], 16 B chunks XOR-swizzled by (row % 8)
-    uint8_t* ds_row = sDS + (chunk >> 1) * BOX_BYTES + row * 128;
-    const int ds_c0 = (chunk & 1) * 4;
+    // dSᵀ smem row of this key: [row][64 queries], 16 B chunks XOR-swizzled by (row % 8)
+    const int ds_off0 = row * 128 + (((chunk * 2) ^ (row & 7)) << 4);
+    const int ds_off1 = row * 128 + (((chunk * 2 + 1) ^ (row & 7)) << 4);
     const int d3 = 3 * d;
 
-    for (int i = 0; i < n_t; i++) {
-      const int s = i & 1;
-      const int nq = min(BT, T - i * BT);
-      const bool active = chunk * 32 < nq;
-      const float* l_s = sL + s * BT + chunk * 32;
-      const float* d_s = sD + s * BT + chunk * 32;
-      uint32_t pk[16], dsk[16];
-      mbar_wait(bar_ld + s, (i >> 1) & 1);
-      mbar_wait(bar_s, i & 1);
+    for (int i = 0; i < n_q; i++) {
+      const int ls = i % LSTAGES, st = i % NST;
+      const int nq = min(BQ, T - i * BQ);
+      const bool active = chunk * 16 < nq;
+      const float* l_s = sL + ls * BQ + chunk * 16;
+      const float* d_s = sD + ls * BQ + chunk * 16;
+      const uint32_t col = lane_addr + COL_ST + (uint32_t)st * 128;
+      uint32_t pk[8], dsk[8];
+      mbar_wait(bar_ld + ls, (i / LSTAGES) & 1);
+      mbar_wait(bar_s + st, (i / NST) & 1);
       tc_fence_after();
       if (active) {
+        uint32_t rs[16], rp[16];
+        tmem_ld_32x32b_x16(col + chunk * 16, rs);
+        tmem_ld_32x32b_x16(col + 64 + chunk * 16, rp);
         // pair index of element (q, key): (((bh*T + q) * Tp) >> 1) + (key >> 1)
-        uint64_t pair = (((uint64_t)bh * (uint64_t)T + (uint64_t)(i * BT + chunk * 32)) * Tp >> 1) + (uint64_t)(key >> 1);
+        uint64_t pair = (((uint64_t)bh * (uint64_t)T + (uint64_t)(i * BQ + chunk * 16)) * Tp >> 1) + (uint64_t)(key >> 1);
+        tmem_ld_wait();
 #pragma unroll
-        for (int hf = 0; hf < 2; hf++) {
-          uint32_t rs[16], rp[16];
-          tmem_ld_32x32b_x16(lane_addr + COL_S + chunk * 32 + hf * 16, rs);
-          tmem_ld_32x32b_x16(lane_addr + COL_DP + chunk * 32 + hf * 16, rp);
-          tmem_ld_wait();
+        for (int e = 0; e < 16; e += 2) {
+          float pd[2], ds[2];
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float pv[2], pd[2], ds[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-              const int ql = hf * 16 + e + u;
-              const bool ok = kvalid && (chunk * 32 + ql < nq);
-              const float pr = ok ? ex2f(fmaf(__uint_as_float(rs[e + u]), scale2, -l_s[ql])) : 0.f;
-              float dp = __uint_as_float(rp[e + u]);
-              float pdv = pr;
-              if (drop) {
-                const uint32_t r = drop_rand_pair(dk, pair);
-                const bool keep = (hi_half ? (r >> 16) : (r & 0xffffu)) >= dk.thr16;
-                pdv = keep ? pr * dk.scale : 0.f;
-                dp = keep ? dp * dk.scale : 0.f;
-                pair += half_tp;
-              }
-              pv[u] = pr; pd[u] = pdv;
-              ds[u] = ok ? pv[u] * (dp - d_s[ql]) : 0.f;
+          for (int u = 0; u < 2; u++) {
+            const int ql = e + u;
+            const bool ok = kvalid && (chunk * 16 + ql < nq);
+            const float pr = ok ? ex2f(fmaf(__uint_as_float(rs[ql]), scale2, -l_s[ql])) : 0.f;
+            float dp = __uint_as_float(rp[ql]);
+            float pdv = pr;
+            if (drop) {
+              const uint32_t r = drop_rand_pair(dk, pair);
+              const bool keep = (hi_half ? (r >> 16) : (r & 0xffffu)) >= dk.thr16;
+              pdv = keep ? pr * dk.scale : 0.f;
+              dp = keep ? dp * dk.scale : 0.f;
+              pair += half_tp;
             }
-            pk[hf * 8 + e / 2] = pack_bf16x2(pd[0], pd[1]);
-            dsk[hf * 8 + e / 2] = pack_bf16x2(ds[0], ds[1]);
+            pd[u] = pdv;
+            ds[u] = ok ? pr * (dp - d_s[ql]) : 0.f;
           }
+          pk[e / 2] = pack_bf16x2(pd[0], pd[1]);
+          dsk[e / 2] = pack_bf16x2(ds[0], ds[1]);
         }
       }
       // every warp of this lane quarter has read its Sᵀ / dPᵀ columns: the packed results may overwrite them
       named_bar_sync(1 + quarter, 128);
       if (active) {
-        tmem_st_32x32b_x16(lane_addr + COL_P + chunk * 16, pk);
-        tmem_st_32x32b_x16(lane_addr + COL_DS + chunk * 16, dsk);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-          const int phys = (ds_c0 + c4) ^ (row & 7);
-          *reinterpret_cast<uint4*>(ds_row + phys * 16) = make_uint4(dsk[c4 * 4], dsk[c4 * 4 + 1], dsk[c4 * 4 + 2], dsk[c4 * 4 + 3]);
-        }
+        tmem_st_32x32b_x8(col + chunk * 8, pk);
+        tmem_st_32x32b_x8(col + 64 + chunk * 8, dsk);
+        uint8_t* dsb = sDS + (i & 1) * DS_BYTES;
+        *reinterpret_cast<uint4*>(dsb + ds_off0) = make_uint4(dsk[0], dsk[1], dsk[2], dsk[3]);
+        *reinterpret_cast<uint4*>(dsb + ds_off1) = make_uint4(dsk[4], dsk[5], dsk[6], dsk[7]);
         tmem_st_wait();
         fence_proxy_async();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(bar_pds); mbar_arrive(bar_ldfree + s); }
-
-      // dQ tile: thread <-> query row
-      mbar_wait(bar_mma2, i & 1);
-      tc_fence_after();
-      if (chunk * 32 < DH) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_addr + COL_DQ + chunk * 32, r);
-        tmem_ld_wait();
-        const int q = i * BT + row;
-        if (q < T) {
-          if (p.dq_acc != nullptr) {
-            float* dst = p.dq_acc + ((int64_t)b * T + q) * d + h * DH + chunk * 32;
-#pragma unroll
-            for (int g = 0; g < 8; g++)
-              red_add_v4(dst + g * 4, __uint_as_float(r[g * 4]) * scale, __uint_as_float(r[g * 4 + 1]) * scale,
-                         __uint_as_float(r[g * 4 + 2]) * scale, __uint_as_float(r[g * 4 + 3]) * scale);
-          } else {
-            bf16* dst = p.dqkv + ((int64_t)b * T + q) * d3 + h * DH + chunk * 32;
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-              uint4 u;
-              u.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * scale, __uint_as_float(r[g * 8 + 1]) * scale);
-              u.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * scale, __uint_as_float(r[g * 8 + 3]) * scale);
-              u.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * scale, __uint_as_float(r[g * 8 + 5]) * scale);
-              u.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * scale, __uint_as_float(r[g * 8 + 7]) * scale);
-              *reinterpret_cast<uint4*>(dst + g * 8) = u;
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_dqr);
+      if (lane == 0) { mbar_arrive(bar_pds + st); mbar_arrive(bar_ldfree + ls); }
     }
 
-    // epilogue: dK (scaled) and dV of this key row -> dqkv   (the last bar_mma2 wait above covers them)
+    // epilogue: dK (scaled) and dV of this key row -> dqkv
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
     if (chunk * 32 < DH) {
       bf16* dst = p.dqkv + ((int64_t)b * T + key) * d3 + h * DH + chunk * 32;
 #pragma unroll
@@ -335,13 +355,53 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         }
       }
     }
+  } else {
+    // ---------------------------------------------------------------- dQᵀ read-out: lane <-> dh column
+    const int quarter = warp & 3;
+    const int c = quarter * 32 + lane;                  // column of this head's dQ
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float scale = rsqrtf((float)DH);
+    const bool live = quarter * 32 < DH;                // warp-uniform
+    for (int i = 0; i < n_q; i++) {
+      const int nq = min(BQ, T - i * BQ);
+      uint32_t r0[32], r1[32];
+      mbar_wait(bar_mma2, i & 1);
+      tc_fence_after();
+      if (live) {
+        tmem_ld_32x32b_x32(lane_addr + COL_DQ, r0);
+        tmem_ld_32x32b_x32(lane_addr + COL_DQ + 32, r1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dqr);      // the MMA issuer may overwrite dQᵀ while we drain the registers
+      if (live && c < DH) {
+        if (p.dq_acc != nullptr) {
+          float* dst = p.dq_acc + ((int64_t)b * T + (int64_t)i * BQ) * d + h * DH + c;
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (j < nq) red_add_f32(dst + (int64_t)j * d, __uint_as_float(r0[j]) * scale);
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (32 + j < nq) red_add_f32(dst + (int64_t)(32 + j) * d, __uint_as_float(r1[j]) * scale);
+        } else {
+          bf16* dst = p.dqkv + ((int64_t)b * T + (int64_t)i * BQ) * (3 * d) + h * DH + c;
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (j < nq) dst[(int64_t)j * 3 * d] = __float2bfloat16_rn(__uint_as_float(r0[j]) * scale);
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (32 + j < nq) dst[(int64_t)(32 + j) * 3 * d] = __float2bfloat16_rn(__uint_as_float(r1[j]) * scale);
+        }
+      }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -396,9 +456,9 @@ template <int DH>
 int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
                void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
   constexpr int NBOX = (DH + 63) / 64;
-  constexpr int USED = 6 * NBOX * BOX_BYTES + 2 * BOX_BYTES + 4 * BT * 4 + 96;
-  constexpr int SMEM = USED + 1024 <= 232448 ? USED + 1024 : 232448;   // dh >= 96: 928 B of alignment slack (kernel traps if short)
-  static_assert(USED <= 232448, "attention backward: shared memory budget");
+  constexpr int USED = 2 * NBOX * BOX_BYTES + 2 * QSTAGES * NBOX * QBOX_BYTES + 2 * BT * 128 + 2 * LSTAGES * BQ * 4 + 19 * 8 + 16;
+  constexpr int SMEM = USED + 1024;
+  static_assert(SMEM <= 232448, "attention backward: shared memory budget");
   static bool cfg = false;
   if (!cfg) {
     MAR_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -414,16 +474,18 @@ int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const 
     MAR_LAUNCH_CHECK("attn_delta_tc");
   }
   if (dq_acc != nullptr) MAR_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)(B * T * d) * sizeof(float), st));
-  CUtensorMap tm_qkv, tm_do;
-  int rc = make_map_btc(&tm_qkv, qkv, B, T, 3 * d, BT);
+  CUtensorMap tm_kv, tm_q, tm_do;
+  int rc = make_map_btc(&tm_kv, qkv, B, T, 3 * d, BT);
   if (rc) return rc;
-  rc = make_map_btc(&tm_do, dout, B, T, d, BT);
+  rc = make_map_btc(&tm_q, qkv, B, T, 3 * d, BQ);
+  if (rc) return rc;
+  rc = make_map_btc(&tm_do, dout, B, T, d, BQ);
   if (rc) return rc;
   BwdParams prm;
   prm.key_mask = key_mask; prm.lse = lse; prm.delta = delta; prm.dq_acc = dq_acc; prm.dqkv = (bf16*)dqkv;
   prm.B = (int)B; prm.T = (int)T; prm.H = (int)H; prm.p_drop = p; prm.rng = rng; prm.site = site; prm.smem_bytes = SMEM;
   const int64_t n_t = ceil_div(T, BT);
-  attn_bwd_tc_kernel<DH><<<(unsigned)(B * H * n_t), NTHREADS, SMEM, st>>>(tm_qkv, tm_do, prm);
+  attn_bwd_tc_kernel<DH><<<(unsigned)(B * H * n_t), NTHREADS, SMEM, st>>>(tm_kv, tm_q, tm_do, prm);
   MAR_LAUNCH_CHECK("attn_bwd_tc");
   if (dq_acc != nullptr) {
     const int64_t n = B * T * (d / 8);

@@ -13,6 +13,7 @@
 void mar_set_error(const char* fmt, ...);
 void mar_count_launch(int n = 1);
 void mar_set_engine(int e);
+bool mar_debug_sync();   // MAR_DEBUG_SYNC=1: synchronise after every launch and report the failing kernel by name
 
 #define MAR_CHECK_ARG(cond, ...)                  \
   do {                                            \
@@ -37,6 +38,13 @@ void mar_set_engine(int e);
       return MAR_ERR_CUDA;                                                            \
     }                                                                                 \
     mar_count_launch();                                                               \
+    if (mar_debug_sync()) {                                                           \
+      e_ = cudaDeviceSynchronize();                                                   \
+      if (e_ != cudaSuccess) {                                                        \
+        mar_set_error("%s: execution failed: %s", name, cudaGetErrorString(e_));      \
+        return MAR_ERR_CUDA;                                                          \
+      }                                                                               \
+    }                                                                                 \
   } while (0)
 
 #define MAR_CUDA(call)                                                                \

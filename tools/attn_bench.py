@@ -11,17 +11,19 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--p", type=float, default=0.1)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--B", type=int, default=256)
+ap.add_argument("--T", type=int, nargs="*", default=[64, 250, 314, 1024])
+ap.add_argument("--engines", nargs="*", default=["tc", "mma"])
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 H, dh = 8, 96
 d = H * dh
 res = {}
-for T in (64, 250, 314, 1024):
+for T in args.T:
     B = args.B if T <= 314 else max(1, args.B * 250 // T // 2)
     qkv = torch.randn(B, T, 3 * d, device=dev, dtype=torch.bfloat16, requires_grad=True)
     go = torch.randn(B, T, d, device=dev, dtype=torch.bfloat16)
     flops_f = 4.0 * T * T * dh * B * H
-    for eng in ("tc", "mma"):
+    for eng in args.engines:
         os.environ["MAR_ATTN_MMA"] = "1" if eng == "mma" else "0"
         with mar.precision("bf16"):
             outs = None
