@@ -1,8 +1,318 @@
-// Persistent cluster GRU engine (placeholder until the kernel lands).
+// Persistent cluster GRU forward (bf16): the whole T-step recurrence in ONE launch.
+//
+//   gh_t = h_{t-1}·W_hhᵀ + b_hh ;  r = σ(gi_r + gh_r), z = σ(gi_z + gh_z), n = tanh(gi_n + r·gh_n),
+//   h_t = (1 − z)·n + z·h_{t-1}                       (nn.GRU, gate order r,z,n, h0 = 0; models.py:110,122)
+//
+// W_hh (3H×H bf16, 1.5 MB at H = 512) does not fit one SM, so a CLUSTER of 16 CTAs shares it: CTA c keeps the
+// 3·U rows (U = H/16 hidden units × gates r,z,n) of W_hh resident in shared memory for all T steps (96 KB at
+// H = 512) and owns those U units of the state.  A cluster serves 8 or 16 batch rows (one or two n = 8 tiles of
+// mma.m16n8k16); the batch is spread over ceil(B/16) clusters (B = 64 → 4 clusters: measured, at most 4-5
+// clusters of 16 are co-resident on the 148 SMs, so 8 clusters of 8 rows would run in two waves).
+// Per step and CTA:
+//   1. wait for h_{t-1} (8 × H bf16) to have arrived in the local double buffer (mbarrier, transaction bytes);
+//   2. 12 warps: gh slice (3U × 8) = W_slice · h_{t-1}ᵀ with ldmatrix + mma.sync m16n8k16 (warp = one 16-row
+//      tile × one half of K), fp32 partials to shared memory;
+//   3. 8 warps (warp ↔ batch row, lane ↔ hidden unit): gates in fp32 (the state is carried in fp32 registers;
+//      only the GEMM operand is rounded to bf16, as in the step engine), hseq / saved / hprev to HBM;
+//   4. the new (batch × U) slice is staged in shared memory and pushed into the h buffer of ALL 16 CTAs with one
+//      cp.async.bulk shared::cta → shared::cluster per peer (DSMEM write + remote mbarrier complete_tx in one
+//      instruction; 16 mbarrier transactions per step instead of one per 16 B) — no cluster-wide barrier on
+//      the critical path; double buffering makes the data arrival the only synchronisation needed.
+// gi = x·W_ihᵀ + b_ih for all steps comes from the tcgen05 GEMM (mar_linear_fwd); gi_{t+1} is prefetched into
+// registers during step t.
+//
+// Bound: latency of the dependent chain (per step: smem-resident GEMV-like product, 96 KB of ldmatrix traffic,
+// one DSMEM exchange); algorithmic work T·2·B·3H·H FLOP.
+#include <cuda_runtime.h>
 #include "common.cuh"
 #include "rnn.cuh"
 
-bool gru_persistent_supported(int64_t, int64_t, int64_t, int) { return false; }
-int gru_fwd_persistent(const void*, const void*, const float*, void*, void*, float*, int64_t, int64_t, int64_t, cudaStream_t) {
-  MAR_UNSUPPORTED("persistent GRU engine not built");
+namespace {
+
+constexpr int CL = 16;          // CTAs per cluster
+constexpr int NWARPS = 12;
+constexpr int PAD = 8;          // bf16 elements of row padding (conflict-free ldmatrix)
+
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+// completion of the phase makes the peers' bulk-copied bytes visible (same contract as a TMA load); the default
+// CTA-scope acquire avoids the L1 invalidate a cluster-scope acquire costs on every step
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(s_addr(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+struct GruParams {
+  const bf16* gi;      // (B,T,3H)
+  const bf16* w_hh;    // (3H,H)
+  const float* b_hh;   // (3H)
+  bf16* hseq;          // (B,T,H)
+  bf16* hprev;         // (B,T,H) or null
+  float* saved;        // (B,T,5H) or null
+  int B, T, H;
+};
+
+// one bulk copy of `bytes` from local shared memory into a peer CTA's shared memory; the peer's mbarrier
+// receives complete_tx(bytes) when the data has landed
+__device__ __forceinline__ void bulk_push(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// U = hidden units per CTA = H / 16 (16 or 32);  NT = 8-row batch tiles per cluster (BG = 8·NT batch rows)
+template <int U, int NT>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+gru_fwd_persistent_kernel(const GruParams p) {
+  constexpr int H = U * CL;
+  constexpr int BGR = 8 * NT;               // batch rows per cluster
+  constexpr int LD = H + PAD;               // W smem row pitch in elements
+  constexpr int UP = U + 8;                 // h-slice row pitch in elements (conflict-free ldmatrix)
+  constexpr int SLICE = BGR * UP;           // elements of one CTA's (BGR x U) slice block
+  constexpr int ROWS = 3 * U;               // W_hh rows of this CTA (r, z, n blocks of U)
+  constexpr int MT = ROWS / 16;             // 16-row tiles
+  constexpr int KSPLIT = NWARPS / MT;       // warps per tile along K
+  constexpr int KSTEPS = H / 16 / KSPLIT;   // k-steps per warp
+  static_assert(NWARPS % MT == 0 && (H / 16) % KSPLIT == 0, "tile split");
+  static_assert(NT == 1 || NT == 2, "batch tiles");
+
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sW = reinterpret_cast<bf16*>(smem_raw);                 // [ROWS][LD]
+  bf16* sH = sW + ROWS * LD;                                    // [2][CL][BGR][UP]  h_{t-1}, slice-major
+  bf16* sOut = sH + 2 * CL * SLICE;                             // [2][BGR][UP]      this CTA's new slice (bulk-copy source)
+  float* sG = reinterpret_cast<float*>(sOut + 2 * SLICE);       // [KSPLIT][ROWS][BGR] partial gh
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + KSPLIT * ROWS * BGR);   // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t c = cluster_rank();
+  const int group = blockIdx.x / CL;
+  const int b0 = group * BGR;
+  const int T = p.T;
+
+  // ---- resident weights: rows g*H + c*U + u  ->  smem row g*U + u
+  for (int i = threadIdx.x; i < ROWS * (H / 8); i += blockDim.x) {
+    const int r = i / (H / 8), ch = i % (H / 8);
+    const int g = r / U, u = r % U;
+    const uint4 v = *reinterpret_cast<const uint4*>(p.w_hh + ((int64_t)g * H + c * U + u) * H + ch * 8);
+    *reinterpret_cast<uint4*>(sW + r * LD + ch * 8) = v;
+  }
+  for (int i = threadIdx.x; i < 2 * SLICE; i += blockDim.x) sOut[i] = __float2bfloat16_rn(0.f);   // padding is copied too
+  if (threadIdx.x == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync();                 // every CTA's barriers exist before anyone pushes data at them
+
+  // ---- gate-thread identity (warps 0 .. U*8/32-1): warp-major over batch rows, lane-major over units;
+  //      each gate thread owns NT batch rows (gb, gb + 8)
+  constexpr int GATE_WARPS = U * 8 / 32;
+  constexpr int ROWS_PER_WARP = 32 / U;                 // batch rows of one 8-row tile handled by one gate warp
+  const bool gate_thread = warp < GATE_WARPS;
+  const int gb = warp * ROWS_PER_WARP + lane / U;       // batch row within an 8-row tile
+  const int gu = lane % U;                              // unit within the CTA slice
+  const int j = c * U + gu;                             // hidden unit
+  float bh_r = 0.f, bh_z = 0.f, bh_n = 0.f;
+  float hp[NT];
+  unsigned short gi_r[NT], gi_z[NT], gi_n[NT];     // raw bf16 bits: converted at use, so the prefetch stays in flight
+  bool bvalid[NT];
+  if (gate_thread) { bh_r = p.b_hh[j]; bh_z = p.b_hh[H + j]; bh_n = p.b_hh[2 * H + j]; }
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) {
+    hp[nt] = 0.f; gi_r[nt] = gi_z[nt] = gi_n[nt] = 0;
+    bvalid[nt] = gate_thread && (b0 + nt * 8 + gb) < p.B;
+    if (bvalid[nt]) {
+      const unsigned short* g = reinterpret_cast<const unsigned short*>(p.gi) + ((int64_t)(b0 + nt * 8 + gb) * T) * 3 * H;
+      gi_r[nt] = __ldg(g + j); gi_z[nt] = __ldg(g + H + j); gi_n[nt] = __ldg(g + 2 * H + j);
+    }
+  }
+  const int mt = warp % MT, kq = warp / MT;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  // ldmatrix lane addresses: A = 16 rows of W_slice; B = h rows (lane&7) of batch tile (lane>>4), k chunk (lane>>3)&1
+  const uint32_t a_base = s_addr(sW + (mt * 16 + (lane & 15)) * LD + (lane >> 4) * 8);
+  const int b_row = (NT == 2 ? (lane >> 4) * 8 : 0) + (lane & 7);
+  const int b_chunk = ((lane >> 3) & 1) * 8;
+
+  for (int t = 0; t < T; t++) {
+    const int cur = t & 1;                 // h_{t-1} sits in buffer cur^1; the new h_t goes to buffer cur
+    // arm the barrier that will collect h_t from all 16 CTAs
+    if (threadIdx.x == 0 && t + 1 < T) mbar_expect_tx(bars + cur, CL * SLICE * 2);
+
+    float gh_r[NT], gh_z[NT], gh_n[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) { gh_r[nt] = bh_r; gh_z[nt] = bh_z; gh_n[nt] = bh_n; }
+    if (t > 0) {
+      mbar_wait_cluster(bars + (cur ^ 1), ((t - 1) >> 1) & 1);
+      // ---- partial product: tile mt (16 rows of W_slice) x K range kq, all batch tiles
+      const bf16* hbuf = sH + (cur ^ 1) * CL * SLICE;
+      float acc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ks++) {
+        const int k0 = (kq * KSTEPS + ks) * 16;
+        uint32_t a[4];
+        ldsm_x4(a, a_base + k0 * 2);
+        const uint32_t b_addr = s_addr(hbuf + (k0 / U) * SLICE + b_row * UP + (k0 % U) + b_chunk);
+        if (NT == 2) {
+          uint32_t b[4];
+          ldsm_x4(b, b_addr);
+          const uint32_t b0v[2] = {b[0], b[1]}, b1v[2] = {b[2], b[3]};
+          mma16816(acc[0], a, b0v);
+          mma16816(acc[NT - 1], a, b1v);
+        } else {
+          uint32_t b[2];
+          ldsm_x2(b, b_addr);
+          mma16816(acc[0], a, b);
+        }
+      }
+      float* part = sG + (kq * ROWS + mt * 16) * BGR;
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        *reinterpret_cast<float2*>(part + g8 * BGR + nt * 8 + t4 * 2) = make_float2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<float2*>(part + (g8 + 8) * BGR + nt * 8 + t4 * 2) = make_float2(acc[nt][2], acc[nt][3]);
+      }
+      if (threadIdx.x < CL) bulk_wait_read_1();      // the push of step t-2 has finished reading sOut[cur]
+      __syncthreads();
+      if (gate_thread) {
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+          for (int q = 0; q < KSPLIT; q++) {
+            gh_r[nt] += sG[(q * ROWS + gu) * BGR + nt * 8 + gb];
+            gh_z[nt] += sG[(q * ROWS + U + gu) * BGR + nt * 8 + gb];
+            gh_n[nt] += sG[(q * ROWS + 2 * U + gu) * BGR + nt * 8 + gb];
+          }
+      }
+    }
+
+    if (gate_thread) {
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        const float r = sigmoidf_(__uint_as_float((uint32_t)gi_r[nt] << 16) + gh_r[nt]);
+        const float z = sigmoidf_(__uint_as_float((uint32_t)gi_z[nt] << 16) + gh_z[nt]);
+        const float n = tanhf(__uint_as_float((uint32_t)gi_n[nt] << 16) + r * gh_n[nt]);
+        const float h = (1.f - z) * n + z * hp[nt];
+        const bf16 hb = __float2bfloat16_rn(h);
+        if (bvalid[nt]) {
+          const int64_t row = (int64_t)(b0 + nt * 8 + gb) * T + t;
+          p.hseq[row * H + j] = hb;
+          if (p.saved != nullptr) {
+            float* s = p.saved + row * 5 * H;
+            s[j] = r; s[H + j] = z; s[2 * H + j] = n; s[3 * H + j] = gh_n[nt]; s[4 * H + j] = hp[nt];
+            p.hprev[row * H + j] = __float2bfloat16_rn(hp[nt]);
+          }
+          if (t + 1 < T) {                 // prefetch the next step's input projection
+            const unsigned short* g = reinterpret_cast<const unsigned short*>(p.gi) + (row + 1) * 3 * H;
+            gi_r[nt] = __ldg(g + j); gi_z[nt] = __ldg(g + H + j); gi_n[nt] = __ldg(g + 2 * H + j);
+          }
+        }
+        hp[nt] = h;
+        sOut[cur * SLICE + (nt * 8 + gb) * UP + gu] = hb;
+      }
+      fence_async_smem();                  // the bulk copies below read sOut through the async proxy
+    }
+    __syncthreads();
+    // ---- push this CTA's (BGR x U) slice into the h buffer of all 16 CTAs: one bulk copy + one mbarrier
+    //      transaction per peer (DSMEM write and remote complete_tx in one instruction)
+    if (threadIdx.x < CL && t + 1 < T) {
+      const uint32_t dst = threadIdx.x;
+      const uint32_t local_dst = s_addr(sH + (cur * CL + c) * SLICE);
+      bulk_push(mapa(local_dst, dst), s_addr(sOut + cur * SLICE), SLICE * 2, mapa(s_addr(bars + cur), dst));
+      bulk_commit();
+    }
+  }
+  if (threadIdx.x < CL) bulk_wait_all();
+  cluster_sync();                 // no CTA exits while a peer may still write into its shared memory
+}
+
+template <int U, int NT>
+int launch(const GruParams& prm, cudaStream_t st) {
+  constexpr int H = U * CL, LD = H + PAD, ROWS = 3 * U, MT = ROWS / 16, KSPLIT = NWARPS / MT, BGR = 8 * NT, SLICE = BGR * (U + 8);
+  constexpr int SMEM = ROWS * LD * 2 + 2 * CL * SLICE * 2 + 2 * SLICE * 2 + KSPLIT * ROWS * BGR * 4 + 16;
+  static_assert(SMEM <= 232448, "persistent GRU: shared memory budget");
+  static bool cfg = false;
+  if (!cfg) {
+    MAR_CUDA(cudaFuncSetAttribute(gru_fwd_persistent_kernel<U, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(gru_fwd_persistent_kernel<U, NT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cfg = true;
+  }
+  const int groups = (int)ceil_div(prm.B, BGR);
+  cudaLaunchConfig_t cfgl = {};
+  cfgl.gridDim = dim3((unsigned)(groups * CL));
+  cfgl.blockDim = dim3(NWARPS * 32);
+  cfgl.dynamicSmemBytes = SMEM;
+  cfgl.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfgl.attrs = attr;
+  cfgl.numAttrs = 1;
+  MAR_CUDA(cudaLaunchKernelEx(&cfgl, gru_fwd_persistent_kernel<U, NT>, prm));
+  MAR_LAUNCH_CHECK("gru_fwd_persistent");
+  return MAR_OK;
+}
+
+}  // namespace
+
+bool gru_persistent_supported(int64_t B, int64_t T, int64_t H, int dtype) {
+  if (dtype != MAR_BF16) return false;
+  if (!(H == 512 || H == 256)) return false;
+  if (B < 1 || T < 1 || B > (1 << 20) || T > (1 << 24)) return false;
+  return true;
+}
+
+int gru_fwd_persistent(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, int64_t B,
+                       int64_t T, int64_t H, cudaStream_t st) {
+  MAR_CHECK_ARG(((uintptr_t)w_hh % 16 == 0), "gru (persistent engine): w_hh must be 16 B aligned");
+  GruParams prm;
+  prm.gi = (const bf16*)gi; prm.w_hh = (const bf16*)w_hh; prm.b_hh = b_hh; prm.hseq = (bf16*)hseq; prm.hprev = (bf16*)hprev;
+  prm.saved = saved; prm.B = (int)B; prm.T = (int)T; prm.H = (int)H;
+  // 16 batch rows per cluster once the batch would otherwise need more clusters than fit the chip at once
+  const bool wide = B > 32;
+  if (H == 512) return wide ? launch<32, 2>(prm, st) : launch<32, 1>(prm, st);
+  if (H == 256) return wide ? launch<16, 2>(prm, st) : launch<16, 1>(prm, st);
+  MAR_UNSUPPORTED("gru (persistent engine): hidden size %lld", (long long)H);
 }

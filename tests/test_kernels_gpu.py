@@ -354,6 +354,50 @@ def test_rnn_fwd_bwd(kind, mode, B, T, I, H):
         assert_close(a.grad.float().cpu(), b.grad, tol, f"{kind} {name}")
 
 
+@pytest.mark.parametrize("B,T,H", [(64, 64, 512), (8, 16, 512), (13, 9, 512), (5, 33, 256), (1, 1, 512)])
+@pytest.mark.parametrize("train", [False, True])
+def test_gru_persistent_cluster_engine_matches_step_engine(B, T, H, train):
+    """The one-launch 16-CTA-cluster GRU (W_hh resident in shared memory, DSMEM exchange of h_t) against the
+    step-per-launch engine on the same bf16 inputs: hseq, the saved gates and h_{t-1} that backward consumes."""
+    from multimodalaggressionrecognition_b200 import _lib
+    k = 1 / math.sqrt(H)
+    gi = (torch.randn(B, T, 3 * H, device=DEV)).to(torch.bfloat16)
+    w = ((torch.rand(3 * H, H, device=DEV) * 2 - 1) * k).to(torch.bfloat16)
+    bh = ((torch.rand(3 * H, device=DEV) * 2 - 1) * k).float()
+    outs = {}
+    for eng in (_lib.ENGINE_TCGEN05, _lib.ENGINE_SIMT):
+        hseq = torch.full((B, T, H), float("nan"), device=DEV, dtype=torch.bfloat16)
+        hprev = torch.full((B, T, H), float("nan"), device=DEV, dtype=torch.bfloat16) if train else None
+        saved = torch.full((B, T, 5 * H), float("nan"), device=DEV) if train else None
+        work = torch.empty(int(_lib.load().mar_gru_work_floats(B, T, H)), device=DEV)
+        _lib.call("mar_gru_fwd", gi.data_ptr(), w.data_ptr(), bh.data_ptr(), hseq.data_ptr(),
+                  None if hprev is None else hprev.data_ptr(), None if saved is None else saved.data_ptr(),
+                  work.data_ptr(), B, T, H, _lib.MAR_BF16, eng, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs[eng] = (hseq, hprev, saved)
+    a, b = outs[_lib.ENGINE_TCGEN05], outs[_lib.ENGINE_SIMT]
+    assert torch.isfinite(a[0].float()).all()
+    assert_close(a[0].float(), b[0].float(), 4e-3, "persistent GRU hseq")
+    if train:
+        assert_close(a[1].float(), b[1].float(), 4e-3, "persistent GRU hprev")
+        assert_close(a[2], b[2], 4e-3, "persistent GRU saved gates")
+
+
+def test_gru_auto_engine_is_persistent_in_bf16():
+    x = torch.randn(4, 6, 512, device=DEV)
+    ps = [torch.randn(3 * 512, 512, device=DEV) * 0.04, torch.randn(3 * 512, 512, device=DEV) * 0.04,
+          torch.zeros(3 * 512, device=DEV), torch.zeros(3 * 512, device=DEV)]
+    with mar.precision("bf16"):
+        ops.reset_launch_count()
+        ops.gru(x, *ps)
+        n_bf16 = ops.launch_count()
+    with mar.precision("fp32"):
+        ops.reset_launch_count()
+        ops.gru(x, *ps)
+        n_fp32 = ops.launch_count()
+    assert n_bf16 < n_fp32 and n_bf16 <= 6, (n_bf16, n_fp32)      # casts + input GEMM + ONE recurrence launch (fp32: one GEMM + one cell kernel per step)
+
+
 def test_adam_kernel_matches_oracle():
     n = 10007
     p0, g = torch.randn(n), torch.randn(n)
