@@ -221,7 +221,12 @@ int mar_gru_bwd(const void* dhseq, const float* saved, const void* w_hh, void* d
   MAR_CHECK_ARG(dhseq && saved && w_hh && dgi && dgh && work, "mar_gru_bwd: null pointer");
   MAR_CHECK_ARG(B > 0 && T > 0 && H > 0, "mar_gru_bwd: bad shape");
   MAR_CHECK_ARG(dtype == MAR_F32 || dtype == MAR_BF16, "mar_gru_bwd: bad dtype");
-  (void)engine;
+  const bool pers_ok = gru_persistent_supported(B, T, H, dtype);
+  if (engine == MAR_ENGINE_TCGEN05 && !pers_ok) MAR_UNSUPPORTED("mar_gru_bwd: persistent engine cannot take B=%lld T=%lld H=%lld dtype=%d", (long long)B, (long long)T, (long long)H, dtype);
+  if (engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && pers_ok && !env_flag("MAR_FORCE_SIMT"))) {
+    mar_set_engine(MAR_ENGINE_TCGEN05);
+    return gru_bwd_persistent(dhseq, saved, w_hh, dgi, dgh, B, T, H, S(stream));
+  }
   mar_set_engine(MAR_ENGINE_SIMT);
   return gru_bwd_steps(dhseq, saved, w_hh, dgi, dgh, work, B, T, H, dtype, S(stream));
 }

@@ -15,3 +15,5 @@ int lstm_bwd_steps(const void* dhseq, const float* saved, const void* w_hh, void
 bool gru_persistent_supported(int64_t B, int64_t T, int64_t H, int dtype);
 int gru_fwd_persistent(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, int64_t B,
                        int64_t T, int64_t H, cudaStream_t st);
+int gru_bwd_persistent(const void* dhseq, const float* saved, const void* w_hh, void* dgi, void* dgh, int64_t B, int64_t T,
+                       int64_t H, cudaStream_t st);

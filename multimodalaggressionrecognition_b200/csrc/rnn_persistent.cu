@@ -295,6 +295,216 @@ int launch(const GruParams& prm, cudaStream_t st) {
   return MAR_OK;
 }
 
+// ================================================================================================
+// Backward through time, same cluster decomposition.  Per step t (descending), CTA c (units k in its slice):
+//   dh    = dhseq[t] + dh_direct + Σ_src partial_src[·, k]        (partials of step t+1, received over DSMEM)
+//   dn~ = dh(1−z)(1−n²), dz~ = dh(hp−n)z(1−z), dr~ = dn~·hn·r(1−r);  dgi = (dr~,dz~,dn~), dgh = (dr~,dz~,dn~·r)
+//   dh_direct = dh·z ;   partial_c[b, k'] = Σ_{j ∈ slice c} dgh[b,j]·W_hh[j,k']  for ALL k' (the resident W slice
+//   read transposed with ldmatrix.trans), then reduce-scattered: block k' ∈ slice c' is bulk-pushed to CTA c'.
+// The carry stays fp32 end to end (fp32 partials on the wire); dgi / dgh leave as bf16 for the wgrad / dgrad GEMMs.
+// ================================================================================================
+constexpr int NWARPS_B = 16;
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+struct GruBwdParams {
+  const bf16* dhseq;   // (B,T,H)
+  const float* saved;  // (B,T,5H): r, z, n, hn, hp
+  const bf16* w_hh;    // (3H,H)
+  bf16* dgi;           // (B,T,3H)
+  bf16* dgh;           // (B,T,3H)
+  int B, T, H;
+};
+
+template <int U, int NT>
+__global__ void __launch_bounds__(NWARPS_B * 32, 1)
+gru_bwd_persistent_kernel(const GruBwdParams p) {
+  constexpr int H = U * CL;
+  constexpr int BGR = 8 * NT;
+  constexpr int LD = H + PAD;
+  constexpr int ROWS = 3 * U;               // local gate rows j (K of the transposed product)
+  constexpr int DLD = ROWS + 8;             // dgh slice row pitch (bf16)
+  constexpr int BLK = BGR * U;              // fp32 elements of one (batch x unit-slice) block
+  constexpr int MTILES = H / 16;            // 16-column tiles of the output k'
+  constexpr int MPW = MTILES / NWARPS_B;    // tiles per warp
+  static_assert(MTILES % NWARPS_B == 0, "tile split");
+
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sW = reinterpret_cast<bf16*>(smem_raw);                    // [ROWS][LD]
+  bf16* sD = sW + ROWS * LD;                                       // [BGR][DLD]  dgh slice of this step (MMA B operand)
+  float* sP = reinterpret_cast<float*>(sD + BGR * DLD);            // [CL][BGR][U] partials, block per destination CTA
+  float* sR = sP + CL * BLK;                                       // [2][CL][BGR][U] received partial blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 2 * CL * BLK); // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t c = cluster_rank();
+  const int b0 = (blockIdx.x / CL) * BGR;
+  const int T = p.T;
+
+  for (int i = threadIdx.x; i < ROWS * (H / 8); i += blockDim.x) {
+    const int r = i / (H / 8), ch = i % (H / 8);
+    const int g = r / U, u = r % U;
+    *reinterpret_cast<uint4*>(sW + r * LD + ch * 8) =
+        *reinterpret_cast<const uint4*>(p.w_hh + ((int64_t)g * H + c * U + u) * H + ch * 8);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync();
+
+  constexpr int GATE_WARPS = U * 8 / 32;
+  constexpr int ROWS_PER_WARP = 32 / U;
+  const bool gate_thread = warp < GATE_WARPS;
+  const int gb = warp * ROWS_PER_WARP + lane / U;
+  const int gu = lane % U;
+  const int j = c * U + gu;
+  float dh_direct[NT];
+  float sv[NT][5];
+  bool bvalid[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) {
+    dh_direct[nt] = 0.f;
+    bvalid[nt] = gate_thread && (b0 + nt * 8 + gb) < p.B;
+#pragma unroll
+    for (int q = 0; q < 5; q++) sv[nt][q] = 0.f;
+    if (bvalid[nt]) {
+      const float* s = p.saved + ((int64_t)(b0 + nt * 8 + gb) * T + (T - 1)) * 5 * H;
+#pragma unroll
+      for (int q = 0; q < 5; q++) sv[nt][q] = __ldg(s + q * H + j);
+    }
+  }
+  const int g8 = lane >> 2, t4 = lane & 3;
+  // ldmatrix.trans lane address of A = W_sliceᵀ: matrix q = lane>>3: K rows (q>>1)*8 + (lane&7), M columns (q&1)*8
+  const int a_krow = ((lane >> 4) & 1) * 8 + (lane & 7);
+  const int a_mcol = ((lane >> 3) & 1) * 8;
+  const int b_row = (NT == 2 ? (lane >> 4) * 8 : 0) + (lane & 7);
+  const int b_chunk = ((lane >> 3) & 1) * 8;
+
+  for (int t = T - 1; t >= 0; t--) {
+    const int it = T - 1 - t;              // iteration counter
+    const int cur = it & 1;                // partials produced in this iteration land in sR[cur] of the peers
+    if (threadIdx.x == 0 && t > 0) mbar_expect_tx(bars + cur, CL * BLK * 4);
+    if (gate_thread) {
+      if (it > 0) mbar_wait_cluster(bars + (cur ^ 1), ((it - 1) >> 1) & 1);
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        float dh = dh_direct[nt];
+        if (it > 0) {
+          const float* rb = sR + (cur ^ 1) * CL * BLK + (nt * 8 + gb) * U + gu;
+#pragma unroll
+          for (int src = 0; src < CL; src++) dh += rb[src * BLK];
+        }
+        const int64_t row = (int64_t)(b0 + nt * 8 + gb) * T + t;
+        if (bvalid[nt]) dh += __bfloat162float(p.dhseq[row * H + j]);
+        const float r = sv[nt][0], z = sv[nt][1], n = sv[nt][2], hn = sv[nt][3], hp = sv[nt][4];
+        const float dn_pre = dh * (1.f - z) * (1.f - n * n);
+        const float dz_pre = dh * (hp - n) * z * (1.f - z);
+        const float dr_pre = dn_pre * hn * r * (1.f - r);
+        const bf16 d_r = __float2bfloat16_rn(dr_pre), d_z = __float2bfloat16_rn(dz_pre);
+        const bf16 d_n = __float2bfloat16_rn(dn_pre), d_nr = __float2bfloat16_rn(dn_pre * r);
+        dh_direct[nt] = dh * z;
+        if (bvalid[nt]) {
+          bf16* a = p.dgi + row * 3 * H;
+          bf16* q = p.dgh + row * 3 * H;
+          a[j] = d_r; a[H + j] = d_z; a[2 * H + j] = d_n;
+          q[j] = d_r; q[H + j] = d_z; q[2 * H + j] = d_nr;
+          if (t > 0) {                     // prefetch the saved gates of the next (earlier) step
+            const float* s = p.saved + (row - 1) * 5 * H;
+#pragma unroll
+            for (int e = 0; e < 5; e++) sv[nt][e] = __ldg(s + e * H + j);
+          }
+        }
+        bf16* d = sD + (nt * 8 + gb) * DLD;
+        d[gu] = d_r; d[U + gu] = d_z; d[2 * U + gu] = d_nr;
+      }
+    }
+    if (t == 0) break;                     // no earlier step to carry into (uniform)
+    if (threadIdx.x < CL) bulk_wait_read_0();      // the previous pushes have finished reading sP
+    __syncthreads();
+    // ---- partialᵀ (k' x batch) = W_sliceᵀ (k' x 3U) · dghᵀ (3U x batch): warp owns MPW 16-column tiles of k'
+    {
+      float acc[MPW][NT][4];
+#pragma unroll
+      for (int mi = 0; mi < MPW; mi++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < ROWS / 16; ks++) {
+        uint32_t b[4];
+        const uint32_t b_addr = s_addr(sD + b_row * DLD + ks * 16 + b_chunk);
+        if (NT == 2) ldsm_x4(b, b_addr);
+        else { uint32_t b2[2]; ldsm_x2(b2, b_addr); b[0] = b2[0]; b[1] = b2[1]; b[2] = b[3] = 0; }
+        const uint32_t b0v[2] = {b[0], b[1]}, b1v[2] = {b[2], b[3]};
+#pragma unroll
+        for (int mi = 0; mi < MPW; mi++) {
+          const int m0 = (warp * MPW + mi) * 16;
+          uint32_t a[4];
+          ldsm_x4_t(a, s_addr(sW + (ks * 16 + a_krow) * LD + m0 + a_mcol));
+          mma16816(acc[mi][0], a, b0v);
+          if (NT == 2) mma16816(acc[mi][NT - 1], a, b1v);
+        }
+      }
+#pragma unroll
+      for (int mi = 0; mi < MPW; mi++) {
+        const int m0 = (warp * MPW + mi) * 16;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int m = m0 + g8 + (e >> 1) * 8;            // output unit k'
+            const int bb = nt * 8 + t4 * 2 + (e & 1);        // batch row
+            sP[((m / U) * BGR + bb) * U + (m % U)] = acc[mi][nt][e];
+          }
+        }
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x < CL) {
+      const uint32_t dst = threadIdx.x;
+      const uint32_t local_dst = s_addr(sR + (cur * CL + c) * BLK);
+      bulk_push(mapa(local_dst, dst), s_addr(sP + dst * BLK), BLK * 4, mapa(s_addr(bars + cur), dst));
+      bulk_commit();
+    }
+  }
+  if (threadIdx.x < CL) bulk_wait_all();
+  cluster_sync();
+}
+
+template <int U, int NT>
+int launch_bwd(const GruBwdParams& prm, cudaStream_t st) {
+  constexpr int H = U * CL, LD = H + PAD, ROWS = 3 * U, BGR = 8 * NT, BLK = BGR * U;
+  constexpr int SMEM = ROWS * LD * 2 + BGR * (ROWS + 8) * 2 + 3 * CL * BLK * 4 + 16;
+  static_assert(SMEM <= 232448, "persistent GRU backward: shared memory budget");
+  static bool cfg = false;
+  if (!cfg) {
+    MAR_CUDA(cudaFuncSetAttribute(gru_bwd_persistent_kernel<U, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(gru_bwd_persistent_kernel<U, NT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cfg = true;
+  }
+  const int groups = (int)ceil_div(prm.B, BGR);
+  cudaLaunchConfig_t cfgl = {};
+  cfgl.gridDim = dim3((unsigned)(groups * CL));
+  cfgl.blockDim = dim3(NWARPS_B * 32);
+  cfgl.dynamicSmemBytes = SMEM;
+  cfgl.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfgl.attrs = attr;
+  cfgl.numAttrs = 1;
+  MAR_CUDA(cudaLaunchKernelEx(&cfgl, gru_bwd_persistent_kernel<U, NT>, prm));
+  MAR_LAUNCH_CHECK("gru_bwd_persistent");
+  return MAR_OK;
+}
+
 }  // namespace
 
 bool gru_persistent_supported(int64_t B, int64_t T, int64_t H, int dtype) {
@@ -315,4 +525,16 @@ int gru_fwd_persistent(const void* gi, const void* w_hh, const float* b_hh, void
   if (H == 512) return wide ? launch<32, 2>(prm, st) : launch<32, 1>(prm, st);
   if (H == 256) return wide ? launch<16, 2>(prm, st) : launch<16, 1>(prm, st);
   MAR_UNSUPPORTED("gru (persistent engine): hidden size %lld", (long long)H);
+}
+
+int gru_bwd_persistent(const void* dhseq, const float* saved, const void* w_hh, void* dgi, void* dgh, int64_t B, int64_t T,
+                       int64_t H, cudaStream_t st) {
+  MAR_CHECK_ARG(((uintptr_t)w_hh % 16 == 0), "gru (persistent engine): w_hh must be 16 B aligned");
+  GruBwdParams prm;
+  prm.dhseq = (const bf16*)dhseq; prm.saved = saved; prm.w_hh = (const bf16*)w_hh; prm.dgi = (bf16*)dgi; prm.dgh = (bf16*)dgh;
+  prm.B = (int)B; prm.T = (int)T; prm.H = (int)H;
+  const bool wide = B > 32;
+  if (H == 512) return wide ? launch_bwd<32, 2>(prm, st) : launch_bwd<32, 1>(prm, st);
+  if (H == 256) return wide ? launch_bwd<16, 2>(prm, st) : launch_bwd<16, 1>(prm, st);
+  MAR_UNSUPPORTED("gru backward (persistent engine): hidden size %lld", (long long)H);
 }
