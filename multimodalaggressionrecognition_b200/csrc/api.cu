@@ -237,7 +237,12 @@ int mar_lstm_fwd(const void* gi, const void* w_hh, const float* b_hh, void* hseq
   MAR_CHECK_ARG((saved == nullptr) == (hprev == nullptr), "mar_lstm_fwd: saved and hprev go together");
   MAR_CHECK_ARG(B > 0 && T > 0 && H > 0, "mar_lstm_fwd: bad shape");
   MAR_CHECK_ARG(dtype == MAR_F32 || dtype == MAR_BF16, "mar_lstm_fwd: bad dtype");
-  (void)engine;
+  const bool pers_ok = gru_persistent_supported(B, T, H, dtype);
+  if (engine == MAR_ENGINE_TCGEN05 && !pers_ok) MAR_UNSUPPORTED("mar_lstm_fwd: persistent engine cannot take B=%lld T=%lld H=%lld dtype=%d", (long long)B, (long long)T, (long long)H, dtype);
+  if (engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && pers_ok && !env_flag("MAR_FORCE_SIMT"))) {
+    mar_set_engine(MAR_ENGINE_TCGEN05);
+    return lstm_fwd_persistent(gi, w_hh, b_hh, hseq, hprev, saved, B, T, H, S(stream));
+  }
   mar_set_engine(MAR_ENGINE_SIMT);
   return lstm_fwd_steps(gi, w_hh, b_hh, hseq, hprev, saved, work, B, T, H, dtype, S(stream));
 }
@@ -247,7 +252,12 @@ int mar_lstm_bwd(const void* dhseq, const float* saved, const void* w_hh, void* 
   MAR_CHECK_ARG(dhseq && saved && w_hh && dgates && work, "mar_lstm_bwd: null pointer");
   MAR_CHECK_ARG(B > 0 && T > 0 && H > 0, "mar_lstm_bwd: bad shape");
   MAR_CHECK_ARG(dtype == MAR_F32 || dtype == MAR_BF16, "mar_lstm_bwd: bad dtype");
-  (void)engine;
+  const bool pers_ok = gru_persistent_supported(B, T, H, dtype);
+  if (engine == MAR_ENGINE_TCGEN05 && !pers_ok) MAR_UNSUPPORTED("mar_lstm_bwd: persistent engine cannot take B=%lld T=%lld H=%lld dtype=%d", (long long)B, (long long)T, (long long)H, dtype);
+  if (engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && pers_ok && !env_flag("MAR_FORCE_SIMT"))) {
+    mar_set_engine(MAR_ENGINE_TCGEN05);
+    return lstm_bwd_persistent(dhseq, saved, w_hh, dgates, B, T, H, S(stream));
+  }
   mar_set_engine(MAR_ENGINE_SIMT);
   return lstm_bwd_steps(dhseq, saved, w_hh, dgates, work, B, T, H, dtype, S(stream));
 }

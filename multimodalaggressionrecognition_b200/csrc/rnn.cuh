@@ -17,3 +17,8 @@ int gru_fwd_persistent(const void* gi, const void* w_hh, const float* b_hh, void
                        int64_t T, int64_t H, cudaStream_t st);
 int gru_bwd_persistent(const void* dhseq, const float* saved, const void* w_hh, void* dgi, void* dgh, int64_t B, int64_t T,
                        int64_t H, cudaStream_t st);
+// LSTM on the same persistent cluster engine (4 gate blocks; saved = i,f,g,o,c)
+int lstm_fwd_persistent(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, int64_t B,
+                        int64_t T, int64_t H, cudaStream_t st);
+int lstm_bwd_persistent(const void* dhseq, const float* saved, const void* w_hh, void* dgates, int64_t B, int64_t T, int64_t H,
+                        cudaStream_t st);

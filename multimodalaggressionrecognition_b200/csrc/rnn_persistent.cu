@@ -30,7 +30,6 @@
 namespace {
 
 constexpr int CL = 16;          // CTAs per cluster
-constexpr int NWARPS = 12;
 constexpr int PAD = 8;          // bf16 elements of row padding (conflict-free ldmatrix)
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,13 +79,15 @@ __device__ __forceinline__ void cluster_sync() {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-struct GruParams {
-  const bf16* gi;      // (B,T,3H)
-  const bf16* w_hh;    // (3H,H)
-  const float* b_hh;   // (3H)
+enum { CELL_GRU = 0, CELL_LSTM = 1 };
+
+struct GruParams {     // G = 3 (GRU: r,z,n) or 4 (LSTM: i,f,g,o) gate blocks
+  const bf16* gi;      // (B,T,G·H)
+  const bf16* w_hh;    // (G·H,H)
+  const float* b_hh;   // (G·H)
   bf16* hseq;          // (B,T,H)
   bf16* hprev;         // (B,T,H) or null
-  float* saved;        // (B,T,5H) or null
+  float* saved;        // (B,T,5H) or null   GRU: r,z,n,hn,hp   LSTM: i,f,g,o,c
   int B, T, H;
 };
 
@@ -102,15 +103,17 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // U = hidden units per CTA = H / 16 (16 or 32);  NT = 8-row batch tiles per cluster (BG = 8·NT batch rows)
-template <int U, int NT>
-__global__ void __launch_bounds__(NWARPS * 32, 1)
-gru_fwd_persistent_kernel(const GruParams p) {
+template <int CELL, int U, int NT>
+__global__ void __launch_bounds__((CELL == CELL_GRU ? 12 : 16) * 32, 1)
+rnn_fwd_persistent_kernel(const GruParams p) {
+  constexpr int G = CELL == CELL_GRU ? 3 : 4;
+  constexpr int NWARPS = CELL == CELL_GRU ? 12 : 16;
   constexpr int H = U * CL;
   constexpr int BGR = 8 * NT;               // batch rows per cluster
   constexpr int LD = H + PAD;               // W smem row pitch in elements
   constexpr int UP = U + 8;                 // h-slice row pitch in elements (conflict-free ldmatrix)
   constexpr int SLICE = BGR * UP;           // elements of one CTA's (BGR x U) slice block
-  constexpr int ROWS = 3 * U;               // W_hh rows of this CTA (r, z, n blocks of U)
+  constexpr int ROWS = G * U;               // W_hh rows of this CTA (gate blocks of U)
   constexpr int MT = ROWS / 16;             // 16-row tiles
   constexpr int KSPLIT = NWARPS / MT;       // warps per tile along K
   constexpr int KSTEPS = H / 16 / KSPLIT;   // k-steps per warp
@@ -154,18 +157,23 @@ gru_fwd_persistent_kernel(const GruParams p) {
   const int gb = warp * ROWS_PER_WARP + lane / U;       // batch row within an 8-row tile
   const int gu = lane % U;                              // unit within the CTA slice
   const int j = c * U + gu;                             // hidden unit
-  float bh_r = 0.f, bh_z = 0.f, bh_n = 0.f;
-  float hp[NT];
-  unsigned short gi_r[NT], gi_z[NT], gi_n[NT];     // raw bf16 bits: converted at use, so the prefetch stays in flight
+  float bh[G];
+  float hp[NT];                                    // GRU: fp32 h_{t-1};  LSTM: fp32 cell state c_{t-1}
+  bf16 hprev_b[NT];                                // LSTM: bf16 h_{t-1} (what backward's wgrad consumes)
+  unsigned short gi_raw[NT][G];                    // raw bf16 bits: converted at use, so the prefetch stays in flight
   bool bvalid[NT];
-  if (gate_thread) { bh_r = p.b_hh[j]; bh_z = p.b_hh[H + j]; bh_n = p.b_hh[2 * H + j]; }
+#pragma unroll
+  for (int g = 0; g < G; g++) bh[g] = gate_thread ? p.b_hh[g * H + j] : 0.f;
 #pragma unroll
   for (int nt = 0; nt < NT; nt++) {
-    hp[nt] = 0.f; gi_r[nt] = gi_z[nt] = gi_n[nt] = 0;
+    hp[nt] = 0.f; hprev_b[nt] = __float2bfloat16_rn(0.f);
     bvalid[nt] = gate_thread && (b0 + nt * 8 + gb) < p.B;
+#pragma unroll
+    for (int g = 0; g < G; g++) gi_raw[nt][g] = 0;
     if (bvalid[nt]) {
-      const unsigned short* g = reinterpret_cast<const unsigned short*>(p.gi) + ((int64_t)(b0 + nt * 8 + gb) * T) * 3 * H;
-      gi_r[nt] = __ldg(g + j); gi_z[nt] = __ldg(g + H + j); gi_n[nt] = __ldg(g + 2 * H + j);
+      const unsigned short* gp = reinterpret_cast<const unsigned short*>(p.gi) + ((int64_t)(b0 + nt * 8 + gb) * T) * G * H;
+#pragma unroll
+      for (int g = 0; g < G; g++) gi_raw[nt][g] = __ldg(gp + g * H + j);
     }
   }
   const int mt = warp % MT, kq = warp / MT;
@@ -180,9 +188,11 @@ gru_fwd_persistent_kernel(const GruParams p) {
     // arm the barrier that will collect h_t from all 16 CTAs
     if (threadIdx.x == 0 && t + 1 < T) mbar_expect_tx(bars + cur, CL * SLICE * 2);
 
-    float gh_r[NT], gh_z[NT], gh_n[NT];
+    float gh[NT][G];
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) { gh_r[nt] = bh_r; gh_z[nt] = bh_z; gh_n[nt] = bh_n; }
+    for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+      for (int g = 0; g < G; g++) gh[nt][g] = bh[g];
     if (t > 0) {
       mbar_wait_cluster(bars + (cur ^ 1), ((t - 1) >> 1) & 1);
       // ---- partial product: tile mt (16 rows of W_slice) x K range kq, all batch tiles
@@ -220,36 +230,55 @@ gru_fwd_persistent_kernel(const GruParams p) {
 #pragma unroll
         for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-          for (int q = 0; q < KSPLIT; q++) {
-            gh_r[nt] += sG[(q * ROWS + gu) * BGR + nt * 8 + gb];
-            gh_z[nt] += sG[(q * ROWS + U + gu) * BGR + nt * 8 + gb];
-            gh_n[nt] += sG[(q * ROWS + 2 * U + gu) * BGR + nt * 8 + gb];
-          }
+          for (int q = 0; q < KSPLIT; q++)
+#pragma unroll
+            for (int g = 0; g < G; g++) gh[nt][g] += sG[(q * ROWS + g * U + gu) * BGR + nt * 8 + gb];
       }
     }
 
     if (gate_thread) {
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
-        const float r = sigmoidf_(__uint_as_float((uint32_t)gi_r[nt] << 16) + gh_r[nt]);
-        const float z = sigmoidf_(__uint_as_float((uint32_t)gi_z[nt] << 16) + gh_z[nt]);
-        const float n = tanhf(__uint_as_float((uint32_t)gi_n[nt] << 16) + r * gh_n[nt]);
-        const float h = (1.f - z) * n + z * hp[nt];
-        const bf16 hb = __float2bfloat16_rn(h);
-        if (bvalid[nt]) {
-          const int64_t row = (int64_t)(b0 + nt * 8 + gb) * T + t;
-          p.hseq[row * H + j] = hb;
-          if (p.saved != nullptr) {
-            float* s = p.saved + row * 5 * H;
-            s[j] = r; s[H + j] = z; s[2 * H + j] = n; s[3 * H + j] = gh_n[nt]; s[4 * H + j] = hp[nt];
+        float x[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) x[g] = __uint_as_float((uint32_t)gi_raw[nt][g] << 16);
+        const int64_t row = (int64_t)(b0 + nt * 8 + gb) * T + t;
+        bf16 hb;
+        if (CELL == CELL_GRU) {
+          const float r = sigmoidf_(x[0] + gh[nt][0]);
+          const float z = sigmoidf_(x[1] + gh[nt][1]);
+          const float n = tanhf(x[2] + r * gh[nt][2]);
+          const float h = (1.f - z) * n + z * hp[nt];
+          hb = __float2bfloat16_rn(h);
+          if (bvalid[nt] && p.saved != nullptr) {
+            float* sp = p.saved + row * 5 * H;
+            sp[j] = r; sp[H + j] = z; sp[2 * H + j] = n; sp[3 * H + j] = gh[nt][2]; sp[4 * H + j] = hp[nt];
             p.hprev[row * H + j] = __float2bfloat16_rn(hp[nt]);
           }
+          hp[nt] = h;
+        } else {
+          const float ig = sigmoidf_(x[0] + gh[nt][0]);
+          const float fg = sigmoidf_(x[1] + gh[nt][1]);
+          const float gg = tanhf(x[2] + gh[nt][2]);
+          const float og = sigmoidf_(x[G - 1] + gh[nt][G - 1]);
+          const float cc = fg * hp[nt] + ig * gg;
+          hb = __float2bfloat16_rn(og * tanhf(cc));
+          if (bvalid[nt] && p.saved != nullptr) {
+            float* sp = p.saved + row * 5 * H;
+            sp[j] = ig; sp[H + j] = fg; sp[2 * H + j] = gg; sp[3 * H + j] = og; sp[4 * H + j] = cc;
+            p.hprev[row * H + j] = hprev_b[nt];
+          }
+          hp[nt] = cc;
+          hprev_b[nt] = hb;
+        }
+        if (bvalid[nt]) {
+          p.hseq[row * H + j] = hb;
           if (t + 1 < T) {                 // prefetch the next step's input projection
-            const unsigned short* g = reinterpret_cast<const unsigned short*>(p.gi) + (row + 1) * 3 * H;
-            gi_r[nt] = __ldg(g + j); gi_z[nt] = __ldg(g + H + j); gi_n[nt] = __ldg(g + 2 * H + j);
+            const unsigned short* gp = reinterpret_cast<const unsigned short*>(p.gi) + (row + 1) * G * H;
+#pragma unroll
+            for (int g = 0; g < G; g++) gi_raw[nt][g] = __ldg(gp + g * H + j);
           }
         }
-        hp[nt] = h;
         sOut[cur * SLICE + (nt * 8 + gb) * UP + gu] = hb;
       }
       fence_async_smem();                  // the bulk copies below read sOut through the async proxy
@@ -268,15 +297,16 @@ gru_fwd_persistent_kernel(const GruParams p) {
   cluster_sync();                 // no CTA exits while a peer may still write into its shared memory
 }
 
-template <int U, int NT>
+template <int CELL, int U, int NT>
 int launch(const GruParams& prm, cudaStream_t st) {
-  constexpr int H = U * CL, LD = H + PAD, ROWS = 3 * U, MT = ROWS / 16, KSPLIT = NWARPS / MT, BGR = 8 * NT, SLICE = BGR * (U + 8);
+  constexpr int G = CELL == CELL_GRU ? 3 : 4, NWARPS = CELL == CELL_GRU ? 12 : 16;
+  constexpr int H = U * CL, LD = H + PAD, ROWS = G * U, MT = ROWS / 16, KSPLIT = NWARPS / MT, BGR = 8 * NT, SLICE = BGR * (U + 8);
   constexpr int SMEM = ROWS * LD * 2 + 2 * CL * SLICE * 2 + 2 * SLICE * 2 + KSPLIT * ROWS * BGR * 4 + 16;
   static_assert(SMEM <= 232448, "persistent GRU: shared memory budget");
   static bool cfg = false;
   if (!cfg) {
-    MAR_CUDA(cudaFuncSetAttribute(gru_fwd_persistent_kernel<U, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    MAR_CUDA(cudaFuncSetAttribute(gru_fwd_persistent_kernel<U, NT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    MAR_CUDA(cudaFuncSetAttribute(rnn_fwd_persistent_kernel<CELL, U, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(rnn_fwd_persistent_kernel<CELL, U, NT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cfg = true;
   }
   const int groups = (int)ceil_div(prm.B, BGR);
@@ -290,8 +320,8 @@ int launch(const GruParams& prm, cudaStream_t st) {
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfgl.attrs = attr;
   cfgl.numAttrs = 1;
-  MAR_CUDA(cudaLaunchKernelEx(&cfgl, gru_fwd_persistent_kernel<U, NT>, prm));
-  MAR_LAUNCH_CHECK("gru_fwd_persistent");
+  MAR_CUDA(cudaLaunchKernelEx(&cfgl, rnn_fwd_persistent_kernel<CELL, U, NT>, prm));
+  MAR_LAUNCH_CHECK(CELL == CELL_GRU ? "gru_fwd_persistent" : "lstm_fwd_persistent");
   return MAR_OK;
 }
 
@@ -313,20 +343,24 @@ __device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk
 
 struct GruBwdParams {
   const bf16* dhseq;   // (B,T,H)
-  const float* saved;  // (B,T,5H): r, z, n, hn, hp
-  const bf16* w_hh;    // (3H,H)
-  bf16* dgi;           // (B,T,3H)
-  bf16* dgh;           // (B,T,3H)
+  const float* saved;  // (B,T,5H)   GRU: r, z, n, hn, hp    LSTM: i, f, g, o, c
+  const bf16* w_hh;    // (G·H,H)
+  bf16* dgi;           // (B,T,G·H)  GRU: d(gi);  LSTM: d(gates)
+  bf16* dgh;           // (B,T,3H)   GRU only: d(gh) (differs from dgi in the n block)
   int B, T, H;
 };
 
-template <int U, int NT>
+// LSTM backward through time uses the same decomposition: per step  dc += dh·o·(1−tanh²c);  d_i = dc·g·i(1−i),
+// d_f = dc·c_{t-1}·f(1−f),  d_g = dc·i·(1−g²),  d_o = dh·tanh(c)·o(1−o);  the cell carry dc·f stays in a register of
+// the owning thread, dh_{t-1} = d(gates)·W_hh is reduce-scattered like the GRU's.
+template <int CELL, int U, int NT>
 __global__ void __launch_bounds__(NWARPS_B * 32, 1)
-gru_bwd_persistent_kernel(const GruBwdParams p) {
+rnn_bwd_persistent_kernel(const GruBwdParams p) {
+  constexpr int G = CELL == CELL_GRU ? 3 : 4;
   constexpr int H = U * CL;
   constexpr int BGR = 8 * NT;
   constexpr int LD = H + PAD;
-  constexpr int ROWS = 3 * U;               // local gate rows j (K of the transposed product)
+  constexpr int ROWS = G * U;               // local gate rows j (K of the transposed product)
   constexpr int DLD = ROWS + 8;             // dgh slice row pitch (bf16)
   constexpr int BLK = BGR * U;              // fp32 elements of one (batch x unit-slice) block
   constexpr int MTILES = H / 16;            // 16-column tiles of the output k'
@@ -365,7 +399,7 @@ gru_bwd_persistent_kernel(const GruBwdParams p) {
   const int gb = warp * ROWS_PER_WARP + lane / U;
   const int gu = lane % U;
   const int j = c * U + gu;
-  float dh_direct[NT];
+  float dh_direct[NT];      // GRU: dh·z carried to the previous step;  LSTM: the cell-state carry dc·f
   float sv[NT][5];
   bool bvalid[NT];
 #pragma unroll
@@ -395,7 +429,7 @@ gru_bwd_persistent_kernel(const GruBwdParams p) {
       if (it > 0) mbar_wait_cluster(bars + (cur ^ 1), ((it - 1) >> 1) & 1);
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
-        float dh = dh_direct[nt];
+        float dh = CELL == CELL_GRU ? dh_direct[nt] : 0.f;
         if (it > 0) {
           const float* rb = sR + (cur ^ 1) * CL * BLK + (nt * 8 + gb) * U + gu;
 #pragma unroll
@@ -403,26 +437,45 @@ gru_bwd_persistent_kernel(const GruBwdParams p) {
         }
         const int64_t row = (int64_t)(b0 + nt * 8 + gb) * T + t;
         if (bvalid[nt]) dh += __bfloat162float(p.dhseq[row * H + j]);
-        const float r = sv[nt][0], z = sv[nt][1], n = sv[nt][2], hn = sv[nt][3], hp = sv[nt][4];
-        const float dn_pre = dh * (1.f - z) * (1.f - n * n);
-        const float dz_pre = dh * (hp - n) * z * (1.f - z);
-        const float dr_pre = dn_pre * hn * r * (1.f - r);
-        const bf16 d_r = __float2bfloat16_rn(dr_pre), d_z = __float2bfloat16_rn(dz_pre);
-        const bf16 d_n = __float2bfloat16_rn(dn_pre), d_nr = __float2bfloat16_rn(dn_pre * r);
-        dh_direct[nt] = dh * z;
-        if (bvalid[nt]) {
-          bf16* a = p.dgi + row * 3 * H;
-          bf16* q = p.dgh + row * 3 * H;
-          a[j] = d_r; a[H + j] = d_z; a[2 * H + j] = d_n;
-          q[j] = d_r; q[H + j] = d_z; q[2 * H + j] = d_nr;
-          if (t > 0) {                     // prefetch the saved gates of the next (earlier) step
-            const float* s = p.saved + (row - 1) * 5 * H;
+        bf16 dq[G];                                  // what the recurrent product consumes (d gh / d gates)
+        if (CELL == CELL_GRU) {
+          const float r = sv[nt][0], z = sv[nt][1], n = sv[nt][2], hn = sv[nt][3], hp = sv[nt][4];
+          const float dn_pre = dh * (1.f - z) * (1.f - n * n);
+          const float dz_pre = dh * (hp - n) * z * (1.f - z);
+          const float dr_pre = dn_pre * hn * r * (1.f - r);
+          dq[0] = __float2bfloat16_rn(dr_pre); dq[1] = __float2bfloat16_rn(dz_pre); dq[2] = __float2bfloat16_rn(dn_pre * r);
+          dh_direct[nt] = dh * z;
+          if (bvalid[nt]) {
+            bf16* a = p.dgi + row * 3 * H;
+            bf16* q = p.dgh + row * 3 * H;
+            a[j] = dq[0]; a[H + j] = dq[1]; a[2 * H + j] = __float2bfloat16_rn(dn_pre);
+            q[j] = dq[0]; q[H + j] = dq[1]; q[2 * H + j] = dq[2];
+          }
+        } else {
+          const float ig = sv[nt][0], fg = sv[nt][1], gg = sv[nt][2], og = sv[nt][3], cc = sv[nt][4];
+          float cp = 0.f;
+          if (bvalid[nt] && t > 0) cp = __ldg(p.saved + (row - 1) * 5 * H + 4 * H + j);
+          const float tc = tanhf(cc);
+          const float dc = dh_direct[nt] + dh * og * (1.f - tc * tc);
+          dq[0] = __float2bfloat16_rn(dc * gg * ig * (1.f - ig));
+          dq[1] = __float2bfloat16_rn(dc * cp * fg * (1.f - fg));
+          dq[2] = __float2bfloat16_rn(dc * ig * (1.f - gg * gg));
+          dq[G - 1] = __float2bfloat16_rn(dh * tc * og * (1.f - og));
+          dh_direct[nt] = dc * fg;
+          if (bvalid[nt]) {
+            bf16* a = p.dgi + row * G * H;
 #pragma unroll
-            for (int e = 0; e < 5; e++) sv[nt][e] = __ldg(s + e * H + j);
+            for (int g = 0; g < G; g++) a[g * H + j] = dq[g];
           }
         }
+        if (bvalid[nt] && t > 0) {                   // prefetch the saved gates of the next (earlier) step
+          const float* sp = p.saved + (row - 1) * 5 * H;
+#pragma unroll
+          for (int e = 0; e < 5; e++) sv[nt][e] = __ldg(sp + e * H + j);
+        }
         bf16* d = sD + (nt * 8 + gb) * DLD;
-        d[gu] = d_r; d[U + gu] = d_z; d[2 * U + gu] = d_nr;
+#pragma unroll
+        for (int g = 0; g < G; g++) d[g * U + gu] = dq[g];
       }
     }
     if (t == 0) break;                     // no earlier step to carry into (uniform)
@@ -478,15 +531,16 @@ gru_bwd_persistent_kernel(const GruBwdParams p) {
   cluster_sync();
 }
 
-template <int U, int NT>
+template <int CELL, int U, int NT>
 int launch_bwd(const GruBwdParams& prm, cudaStream_t st) {
-  constexpr int H = U * CL, LD = H + PAD, ROWS = 3 * U, BGR = 8 * NT, BLK = BGR * U;
+  constexpr int G = CELL == CELL_GRU ? 3 : 4;
+  constexpr int H = U * CL, LD = H + PAD, ROWS = G * U, BGR = 8 * NT, BLK = BGR * U;
   constexpr int SMEM = ROWS * LD * 2 + BGR * (ROWS + 8) * 2 + 3 * CL * BLK * 4 + 16;
   static_assert(SMEM <= 232448, "persistent GRU backward: shared memory budget");
   static bool cfg = false;
   if (!cfg) {
-    MAR_CUDA(cudaFuncSetAttribute(gru_bwd_persistent_kernel<U, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    MAR_CUDA(cudaFuncSetAttribute(gru_bwd_persistent_kernel<U, NT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    MAR_CUDA(cudaFuncSetAttribute(rnn_bwd_persistent_kernel<CELL, U, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(rnn_bwd_persistent_kernel<CELL, U, NT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cfg = true;
   }
   const int groups = (int)ceil_div(prm.B, BGR);
@@ -500,8 +554,8 @@ int launch_bwd(const GruBwdParams& prm, cudaStream_t st) {
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfgl.attrs = attr;
   cfgl.numAttrs = 1;
-  MAR_CUDA(cudaLaunchKernelEx(&cfgl, gru_bwd_persistent_kernel<U, NT>, prm));
-  MAR_LAUNCH_CHECK("gru_bwd_persistent");
+  MAR_CUDA(cudaLaunchKernelEx(&cfgl, rnn_bwd_persistent_kernel<CELL, U, NT>, prm));
+  MAR_LAUNCH_CHECK(CELL == CELL_GRU ? "gru_bwd_persistent" : "lstm_bwd_persistent");
   return MAR_OK;
 }
 
@@ -522,8 +576,8 @@ int gru_fwd_persistent(const void* gi, const void* w_hh, const float* b_hh, void
   prm.saved = saved; prm.B = (int)B; prm.T = (int)T; prm.H = (int)H;
   // 16 batch rows per cluster once the batch would otherwise need more clusters than fit the chip at once
   const bool wide = B > 32;
-  if (H == 512) return wide ? launch<32, 2>(prm, st) : launch<32, 1>(prm, st);
-  if (H == 256) return wide ? launch<16, 2>(prm, st) : launch<16, 1>(prm, st);
+  if (H == 512) return wide ? launch<CELL_GRU, 32, 2>(prm, st) : launch<CELL_GRU, 32, 1>(prm, st);
+  if (H == 256) return wide ? launch<CELL_GRU, 16, 2>(prm, st) : launch<CELL_GRU, 16, 1>(prm, st);
   MAR_UNSUPPORTED("gru (persistent engine): hidden size %lld", (long long)H);
 }
 
@@ -534,7 +588,32 @@ int gru_bwd_persistent(const void* dhseq, const float* saved, const void* w_hh, 
   prm.dhseq = (const bf16*)dhseq; prm.saved = saved; prm.w_hh = (const bf16*)w_hh; prm.dgi = (bf16*)dgi; prm.dgh = (bf16*)dgh;
   prm.B = (int)B; prm.T = (int)T; prm.H = (int)H;
   const bool wide = B > 32;
-  if (H == 512) return wide ? launch_bwd<32, 2>(prm, st) : launch_bwd<32, 1>(prm, st);
-  if (H == 256) return wide ? launch_bwd<16, 2>(prm, st) : launch_bwd<16, 1>(prm, st);
+  if (H == 512) return wide ? launch_bwd<CELL_GRU, 32, 2>(prm, st) : launch_bwd<CELL_GRU, 32, 1>(prm, st);
+  if (H == 256) return wide ? launch_bwd<CELL_GRU, 16, 2>(prm, st) : launch_bwd<CELL_GRU, 16, 1>(prm, st);
   MAR_UNSUPPORTED("gru backward (persistent engine): hidden size %lld", (long long)H);
+}
+
+int lstm_fwd_persistent(const void* gi, const void* w_hh, const float* b_hh, void* hseq, void* hprev, float* saved, int64_t B,
+                        int64_t T, int64_t H, cudaStream_t st) {
+  MAR_CHECK_ARG(((uintptr_t)w_hh % 16 == 0), "lstm (persistent engine): w_hh must be 16 B aligned");
+  GruParams prm;
+  prm.gi = (const bf16*)gi; prm.w_hh = (const bf16*)w_hh; prm.b_hh = b_hh; prm.hseq = (bf16*)hseq; prm.hprev = (bf16*)hprev;
+  prm.saved = saved; prm.B = (int)B; prm.T = (int)T; prm.H = (int)H;
+  const bool wide = B > 32;
+  if (H == 512) return wide ? launch<CELL_LSTM, 32, 2>(prm, st) : launch<CELL_LSTM, 32, 1>(prm, st);
+  if (H == 256) return wide ? launch<CELL_LSTM, 16, 2>(prm, st) : launch<CELL_LSTM, 16, 1>(prm, st);
+  MAR_UNSUPPORTED("lstm (persistent engine): hidden size %lld", (long long)H);
+}
+
+int lstm_bwd_persistent(const void* dhseq, const float* saved, const void* w_hh, void* dgates, int64_t B, int64_t T, int64_t H,
+                        cudaStream_t st) {
+  MAR_CHECK_ARG(((uintptr_t)w_hh % 16 == 0), "lstm (persistent engine): w_hh must be 16 B aligned");
+  GruBwdParams prm;
+  prm.dhseq = (const bf16*)dhseq; prm.saved = saved; prm.w_hh = (const bf16*)w_hh; prm.dgi = (bf16*)dgates; prm.dgh = nullptr;
+  prm.B = (int)B; prm.T = (int)T; prm.H = (int)H;
+  const bool wide = B > 32;
+  (void)wide;
+  if (H == 512) return launch_bwd<CELL_LSTM, 32, 1>(prm, st);   // 4·32 rows of W_hh + the fp32 exchange buffers of 16 batch rows exceed 227 KB
+  if (H == 256) return wide ? launch_bwd<CELL_LSTM, 16, 2>(prm, st) : launch_bwd<CELL_LSTM, 16, 1>(prm, st);
+  MAR_UNSUPPORTED("lstm backward (persistent engine): hidden size %lld", (long long)H);
 }

@@ -420,6 +420,39 @@ def test_gru_persistent_backward_matches_step_engine(B, T, H, last_only):
         assert_close(a[0][:, t], b[0][:, t], 1.5e-2, f"persistent GRU dgi at t={t}")
 
 
+@pytest.mark.parametrize("B,T,H", [(64, 64, 512), (8, 16, 512), (13, 9, 512), (5, 33, 256), (1, 1, 512), (40, 3, 256)])
+def test_lstm_persistent_cluster_engine_matches_step_engine(B, T, H):
+    """nn.LSTM recurrence (gate order i,f,g,o; train_video_rnn.py:94-106) on the persistent cluster engine: forward
+    (hseq, saved i,f,g,o,c, bf16 h_{t-1}) and BPTT (d gates) against the step-per-launch engine."""
+    from multimodalaggressionrecognition_b200 import _lib
+    k = 1 / math.sqrt(H)
+    gi = torch.randn(B, T, 4 * H, device=DEV).to(torch.bfloat16)
+    w = ((torch.rand(4 * H, H, device=DEV) * 2 - 1) * k).to(torch.bfloat16)
+    bh = ((torch.rand(4 * H, device=DEV) * 2 - 1) * k).float()
+    st = torch.cuda.current_stream().cuda_stream
+    dh = torch.randn(B, T, H, device=DEV).to(torch.bfloat16)
+    outs = {}
+    for eng in (_lib.ENGINE_TCGEN05, _lib.ENGINE_SIMT):
+        hseq = torch.full((B, T, H), float("nan"), device=DEV, dtype=torch.bfloat16)
+        hprev = torch.full_like(hseq, float("nan"))
+        saved = torch.full((B, T, 5 * H), float("nan"), device=DEV)
+        work = torch.empty(B * 5 * H, device=DEV)
+        _lib.call("mar_lstm_fwd", gi.data_ptr(), w.data_ptr(), bh.data_ptr(), hseq.data_ptr(), hprev.data_ptr(),
+                  saved.data_ptr(), work.data_ptr(), B, T, H, _lib.MAR_BF16, eng, st)
+        dg = torch.full((B, T, 4 * H), float("nan"), device=DEV, dtype=torch.bfloat16)
+        _lib.call("mar_lstm_bwd", dh.data_ptr(), saved.data_ptr(), w.data_ptr(), dg.data_ptr(), work.data_ptr(),
+                  B, T, H, _lib.MAR_BF16, eng, st)
+        torch.cuda.synchronize()
+        outs[eng] = (hseq.float(), hprev.float(), saved, dg.float())
+    a, b = outs[_lib.ENGINE_TCGEN05], outs[_lib.ENGINE_SIMT]
+    for x in a:
+        assert torch.isfinite(x).all()
+    assert_close(a[0], b[0], 4e-3, "persistent LSTM hseq")
+    assert_close(a[1], b[1], 4e-3, "persistent LSTM hprev")
+    assert_close(a[2], b[2], 4e-3, "persistent LSTM saved gates / cell state")
+    assert_close(a[3], b[3], 1e-2, "persistent LSTM d(gates)")     # the two engines back-propagate their own saved gates
+
+
 def test_gru_auto_engine_is_persistent_in_bf16():
     x = torch.randn(4, 6, 512, device=DEV)
     ps = [torch.randn(3 * 512, 512, device=DEV) * 0.04, torch.randn(3 * 512, 512, device=DEV) * 0.04,

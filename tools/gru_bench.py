@@ -48,7 +48,9 @@ flops = T * 2.0 * B * 3 * H * H
 res["recurrence_gflops_persistent"] = round(flops / res["recurrence_fwd_ms_persistent"] / 1e6, 1)
 
 # ---- the C2 train step (fwd + CE + bwd) through the drop-in modules
-model = W.build_c2(M).to(dev)
+ap2 = os.environ.get("C2_HEADS", "GRU_1L").split(",")
+model = W.build_c2(M, heads=tuple(ap2)).to(dev)
+res["heads"] = ap2
 x, y = W.batch_c2(B, T, 512)
 x, y = x.to(dev), y.to(dev)
 crit = M.MultiCrossEntropyLoss() if hasattr(M, "MultiCrossEntropyLoss") else None
