@@ -453,9 +453,23 @@ int gemm_tcgen05(const TcGemmArgs& a, cudaStream_t st) {
   p.splits = 1; p.kb_per_split = kb_total;
   if (a.allow_split && a.out_fp32 && a.flags == 0 && a.residual == nullptr && a.aux == nullptr) {
     const int64_t tiles = ceil_div(m_blocks, cl) * ceil_div(a.N, BN);
-    int64_t want = ceil_div((int64_t)(mar_sm_count() / cl), tiles);
-    int64_t max_split = kb_total / 8 > 0 ? kb_total / 8 : 1;   // at least 8 k-blocks (512 rows) per split
-    int64_t splits = want < max_split ? want : max_split;
+    const int64_t clusters = mar_sm_count() / cl;
+    const int64_t max_split = kb_total / 8 > 0 ? kb_total / 8 : 1;   // at least 8 k-blocks (512 rows) per split
+    // Work items = tiles x splits are dealt round-robin to the persistent clusters: pick the split count whose last
+    // wave is fullest (tiles x splits just under a multiple of the cluster count), looking at up to 4 waves; the
+    // smallest such count wins ties (every split adds one fp32 red.add pass over the output).
+    int64_t splits = 1;
+    double best = 0.0;
+    for (int64_t waves = 1; waves <= 4; waves++) {
+      int64_t sp = waves * clusters / tiles;
+      if (sp < 1) sp = 1;
+      if (sp > max_split) sp = max_split;
+      const int64_t kbs = ceil_div(kb_total, sp);
+      sp = ceil_div(kb_total, kbs);                              // splits actually produced by this k-block count
+      const int64_t items = tiles * sp;
+      const double util = (double)items / (double)(ceil_div(items, clusters) * clusters);
+      if (util > best + 0.02) { best = util; splits = sp; }
+    }
     if (splits > 1) {
       p.kb_per_split = (int)ceil_div(kb_total, splits);
       p.splits = (int)ceil_div(kb_total, p.kb_per_split);

@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu --tb=short -x -k "gru or rnn or lstm" 2>&1 | tail -8
-timeout 300 python -m pytest tests/test_models_gpu.py -q -m gpu --tb=line -k "c2" 2>&1 | tail -3
-timeout 300 python tools/gru_bench.py --B 64 2>&1 | tail -1 | cut -c230-700
-C2_HEADS=LSTM_1L,GRU_1L,Avg_features timeout 300 python tools/gru_bench.py --B 64 2>&1 | tail -1 | cut -c230-700
+mkdir -p gpurun_out
+timeout 300 python tools/gemm_bench.py --mode wgrad --shapes qkv,ffn1,ffn2,out,qkv_a,emb 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu --tb=short -x -k "linear or gemm" 2>&1 | tail -3
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','model_frac_of_bf16_peak')}, d['roofline']['achieved'], d['roofline']['gemm_ms_per_step'], d['e2e']['value'])"
