@@ -174,10 +174,12 @@ class TrainStep:
     """One optimizer step of the hot path as a single call:  losses = step(data, labels).
 
     model(data) → criterion(pred, labels) → LossesDict.backward() → gradient all-reduce (if world > 1) → Adam.
-    Returns the dict of per-head losses as 0-d DEVICE tensors (no host sync).  With `graph=True` (single GPU)
-    the whole step is captured into a CUDA graph on first use and replayed afterwards: inputs are copied into
-    static buffers (H2D directly from pinned host memory when given CPU tensors), dropout masks advance on the
-    device, ~250 kernel launches collapse into one graph launch."""
+    Returns the dict of per-head losses as 0-d DEVICE tensors (no host sync).  With `graph=True` the whole step —
+    including the bucketed NCCL all-reduces on the side stream when world > 1 — is captured into a CUDA graph on
+    first use and replayed afterwards: dropout masks advance on the device, ~150 kernel launches collapse into one
+    graph launch.  Inputs go through TWO sets of static buffers (and two captured graphs) used alternately: when
+    the batch is given as pinned HOST tensors, the H2D copy of step i+1 runs on a copy stream while the graph of
+    step i is still executing, so the transfer is hidden behind compute without any change to the call."""
 
     def __init__(self, model: nn.Module, criterion: Callable, lr: float = 1e-3, graph: bool = False,
                  group=None, num_buckets: int = 4, precision: Optional[str] = None):
@@ -185,11 +187,11 @@ class TrainStep:
         self.flat = FlatParams(list(model.parameters()))
         self.opt = FlatAdam(self.flat, lr=lr)
         self.sync = GradSync(self.flat, group=group, num_buckets=num_buckets)
-        self.use_graph = graph and self.sync.world == 1
+        self.use_graph = graph
         self.precision = precision
-        self._graph = None
-        self._static_in = None
-        self._static_out = None
+        self._sets = [dict(static_in=None, graph=None, static_out=None, done=None) for _ in range(2)]
+        self._calls = 0
+        self._copy_stream = None
         self._warm = 0
         self.captured_launches = 0
         self.last_pred = None
@@ -258,29 +260,64 @@ class TrainStep:
     def _graphed(self, data, labels):
         dev = self.flat.flat.device
         src = self._tensors([data, labels])
-        if self._static_in is None:
-            self._static_in = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in src]
-        for s, t in zip(self._static_in, src):
-            s.copy_(t, non_blocking=True)
-        sdata, slabels = self._like([data, labels], self._static_in)
-        if self._graph is None:
+        cur = self._sets[self._calls & 1]
+        self._calls += 1
+        if cur["static_in"] is None:
+            cur["static_in"] = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in src]
+        main = torch.cuda.current_stream()
+        from_host = all(not t.is_cuda for t in src)
+        if from_host and self._graph_ready():
+            # H2D on the copy stream: it only has to wait for the last replay that READ this buffer set, not for
+            # the step that is executing right now on the main stream (that one reads the other set)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+            cs = self._copy_stream
+            if cur["done"] is not None:
+                cs.wait_event(cur["done"])
+            with torch.cuda.stream(cs):
+                for s_, t in zip(cur["static_in"], src):
+                    s_.copy_(t, non_blocking=True)
+            main.wait_stream(cs)
+        else:
+            for s_, t in zip(cur["static_in"], src):
+                s_.copy_(t, non_blocking=True)
+        sdata, slabels = self._like([data, labels], cur["static_in"])
+        if cur["graph"] is None:
             if self._warm < 3:                      # eager warm-up steps on a side stream before capture
                 self._warm += 1
                 side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
+                side.wait_stream(main)
                 with torch.cuda.stream(side):
                     out = self._eager(sdata, slabels)
-                torch.cuda.current_stream().wait_stream(side)
+                main.wait_stream(side)
                 return out
             ops.clear_weight_cache()
             g = torch.cuda.CUDAGraph()
             before = ops.launch_count()
             with torch.cuda.graph(g):
-                self._static_out = self._eager(sdata, slabels)
+                cur["static_out"] = self._eager(sdata, slabels)
             self.captured_launches = ops.launch_count() - before   # libmar kernels per replay
-            self._graph = g                         # capture records but does not execute: fall through to replay
-        self._graph.replay()
-        return self._static_out
+            cur["graph"] = g                        # capture records but does not execute: fall through to replay
+        cur["graph"].replay()
+        if cur["done"] is None:
+            cur["done"] = torch.cuda.Event()
+        cur["done"].record(main)
+        return cur["static_out"]
+
+    def _graph_ready(self) -> bool:
+        return self._warm >= 3
+
+    def release_graphs(self) -> None:
+        """Drop the captured graphs (and their memory pools).  Call before torch.distributed.destroy_process_group():
+        a communicator must not be torn down while graphs that captured its collectives are still alive."""
+        if self.flat.flat.is_cuda:
+            torch.cuda.synchronize()
+        for s in self._sets:
+            s["graph"] = None
+            s["static_out"] = None
+            s["done"] = None
+        if self.flat.flat.is_cuda:
+            torch.cuda.synchronize()
 
 
 class _null:

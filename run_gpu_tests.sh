@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python tools/gemm_bench.py --mode wgrad --shapes qkv,ffn1,ffn2,out,qkv_a,emb 2>&1 | tail -1
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu --tb=short -x -k "linear or gemm" 2>&1 | tail -3
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','model_frac_of_bf16_peak')}, d['roofline']['achieved'], d['roofline']['gemm_ms_per_step'], d['e2e']['value'])"
+date +%s > /tmp/t0
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "n2 rc=$? elapsed $(( $(date +%s) - $(cat /tmp/t0) ))s"
+python -c "import sys,json; d=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1]); print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, 'e2e', d['e2e']['value'], d['config']['cuda_graph'])"
+tail -3 gpurun_out/bench_n2.err
