@@ -157,6 +157,13 @@ int mar_concat_rows(const void* src, void* dst, int64_t B, int64_t T, int64_t T_
 int mar_cross_entropy_fwd(const float* logits, const int64_t* labels, const float* class_weight,
                           float* loss, float* dlogits, int64_t* preds, int64_t B, int64_t C, void* stream);
 
+/* Multi-class focal loss, the criterion train_multimodal.py:494-510 loads from torch.hub
+ * (adeelh/pytorch-multi-class-focal-loss, unpinned and absent offline: restated from its published algorithm,
+ * parity unpinned): per row  -alpha[y]·(1-p_y)^gamma·log p_y, 'mean' = plain mean over rows with label >= 0
+ * (train_multimodal.py passes the class weights as alpha and gamma = 1.5..2).  alpha (C) fp32 or NULL. */
+int mar_focal_loss_fwd(const float* logits, const int64_t* labels, const float* alpha, float gamma,
+                       float* loss, float* dlogits, int64_t B, int64_t C, void* stream);
+
 /* ---- GRU / LSTM recurrence ------------------------------------------------------------------ */
 /* One-layer batch_first GRU, h0 = 0 (nn.GRU at models.py:110,122; gate order r,z,n).
  * gi (B,T,3H) = x·W_ihᵀ + b_ih is produced by mar_linear_fwd.  w_hh (3H,H) in `dtype`, b_hh fp32.

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "mar_rowzero_mask": (c_int, [P, P, c_int64, c_int64, c_int, P]),
     "mar_concat_rows": (c_int, [P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P]),
     "mar_cross_entropy_fwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, P]),
+    "mar_focal_loss_fwd": (c_int, [P, P, P, c_float, P, P, c_int64, c_int64, P]),
     "mar_gru_fwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P]),
     "mar_gru_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P]),
     "mar_gru_work_floats": (c_int64, [c_int64, c_int64, c_int64]),

@@ -238,6 +238,67 @@ __global__ void concat_rows_kernel(const uint4* __restrict__ src, uint4* __restr
 }
 
 // ------------------------------------------------------------------------------------------
+// focal loss (adeelh/pytorch-multi-class-focal-loss, the criterion train_multimodal.py:494-510 fetches from
+// torch.hub): per row  L = -alpha[y] · (1 - p_y)^gamma · log p_y ;  'mean' = plain mean over the rows whose
+// label is not ignored (NOT the alpha-weighted mean of nn.CrossEntropyLoss).  Single block, fp32.
+// dL/dz_k = alpha[y] · [ gamma (1-p_y)^(gamma-1) p_y log p_y - (1-p_y)^gamma ] · (delta_ky - p_k) / n
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+focal_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const float* __restrict__ alpha,
+                  float gamma, float* __restrict__ loss, float* __restrict__ dlogits, int64_t B, int64_t C) {
+  __shared__ float s_num[256], s_cnt[256];
+  float num = 0.f, cnt = 0.f;
+  for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+    const int64_t y = labels[b];
+    if (y < 0 || y >= C) continue;
+    const float* l = logits + b * C;
+    float m = l[0];
+    for (int64_t c = 1; c < C; c++) m = fmaxf(m, l[c]);
+    float se = 0.f;
+    for (int64_t c = 0; c < C; c++) se += expf(l[c] - m);
+    const float log_pt = l[y] - m - logf(se);
+    const float pt = expf(log_pt);
+    const float a = alpha ? alpha[y] : 1.f;
+    num += -a * powf(fmaxf(1.f - pt, 0.f), gamma) * log_pt;
+    cnt += 1.f;
+  }
+  s_num[threadIdx.x] = num;
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_num[threadIdx.x] += s_num[threadIdx.x + o];
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const float n = s_cnt[0];
+  if (threadIdx.x == 0) loss[0] = n > 0.f ? s_num[0] / n : 0.f;
+  if (dlogits == nullptr) return;
+  const float invn = n > 0.f ? 1.f / n : 0.f;
+  for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* l = logits + b * C;
+    float* g = dlogits + b * C;
+    const int64_t y = labels[b];
+    if (y < 0 || y >= C) {
+      for (int64_t c = 0; c < C; c++) g[c] = 0.f;
+      continue;
+    }
+    float m = l[0];
+    for (int64_t c = 1; c < C; c++) m = fmaxf(m, l[c]);
+    float se = 0.f;
+    for (int64_t c = 0; c < C; c++) se += expf(l[c] - m);
+    const float log_pt = l[y] - m - logf(se);
+    const float pt = expf(log_pt);
+    const float om = fmaxf(1.f - pt, 0.f);
+    const float a = (alpha ? alpha[y] : 1.f) * invn;
+    // d/dp_y of -(1-p)^g log p, times p_y (the softmax Jacobian's common factor)
+    const float base = gamma > 0.f ? gamma * powf(om, gamma - 1.f) * pt * log_pt - powf(om, gamma) : -1.f;
+    for (int64_t c = 0; c < C; c++) g[c] = a * base * ((c == y ? 1.f : 0.f) - expf(l[c] - m) / se);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // cross entropy: single block (B is a few hundred), fp32
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -450,6 +511,15 @@ int mar_cross_entropy_fwd(const float* logits, const int64_t* labels, const floa
   MAR_CHECK_ARG(logits && labels && loss && B > 0 && C > 0, "mar_cross_entropy_fwd: bad arguments");
   cross_entropy_kernel<<<1, 256, 0, S(stream)>>>(logits, labels, class_weight, loss, dlogits, preds, B, C);
   MAR_LAUNCH_CHECK("cross_entropy");
+  return MAR_OK;
+}
+
+int mar_focal_loss_fwd(const float* logits, const int64_t* labels, const float* alpha, float gamma, float* loss,
+                       float* dlogits, int64_t B, int64_t C, void* stream) {
+  MAR_CHECK_ARG(logits && labels && loss && B > 0 && C > 0, "mar_focal_loss_fwd: bad arguments");
+  MAR_CHECK_ARG(gamma >= 0.f, "mar_focal_loss_fwd: gamma must be >= 0");
+  focal_loss_kernel<<<1, 256, 0, S(stream)>>>(logits, labels, alpha, gamma, loss, dlogits, B, C);
+  MAR_LAUNCH_CHECK("focal_loss");
   return MAR_OK;
 }
 

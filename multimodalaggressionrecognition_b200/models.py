@@ -273,9 +273,42 @@ class LossesDict(dict):
         return sum(vals[1:], vals[0]) if vals else None
 
 
+class FocalLoss(nn.Module):
+    """Drop-in for `torch.hub.load('adeelh/pytorch-multi-class-focal-loss', 'FocalLoss', alpha=..., gamma=...,
+    reduction='mean')` (train_multimodal.py:494-510): same constructor arguments, fused forward + gradient
+    kernel (mar_focal_loss_fwd).  loss_i = -alpha[y_i]·(1 - p_{y_i})^gamma·log p_{y_i}; 'mean' / 'sum' / over the
+    rows whose label is not `ignore_index`; an all-ignored batch gives 0."""
+
+    def __init__(self, alpha: Optional[torch.Tensor] = None, gamma: float = 0.0, reduction: str = "mean",
+                 ignore_index: int = -100):
+        super().__init__()
+        if reduction not in ("mean", "sum"):
+            raise ValueError('Reduction must be one of: "mean", "sum" (per-row "none" is not on the hot path)')
+        self.alpha = None if alpha is None else torch.as_tensor(alpha, dtype=torch.float32)
+        self.gamma, self.reduction, self.ignore_index = float(gamma), reduction, int(ignore_index)
+
+    def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if x.dim() > 2:                      # (N, C, d1, ..) -> (N·d1·.., C), as the hub module does
+            c = x.shape[1]
+            x = x.permute(0, *range(2, x.dim()), 1).reshape(-1, c)
+            y = y.reshape(-1)
+        y = y.to(x.device)
+        y = y.masked_fill(y == self.ignore_index, -1)
+        loss = ops.focal_loss(x, y, self.alpha, self.gamma)
+        if self.reduction == "sum":
+            loss = loss * (y >= 0).sum().to(loss.dtype)
+        return loss
+
+
 def _apply_criterion(criterion, preds, labels, keep=None):
-    """Plain / class-weighted nn.CrossEntropyLoss runs on the fused kernel (ignored rows carry label -1);
-    anything else (e.g. the hub focal loss, train_multimodal.py:494-510) is called as given."""
+    """Plain / class-weighted nn.CrossEntropyLoss and this module's FocalLoss run on the fused kernels (ignored
+    rows carry label -1); any other criterion object is called as given."""
+    if isinstance(criterion, FocalLoss) and preds.is_cuda:
+        labels = labels.masked_fill(labels == criterion.ignore_index, -1)
+        if keep is not None:
+            labels = labels.masked_fill(~keep, -1)
+        loss = ops.focal_loss(preds, labels, criterion.alpha, criterion.gamma)
+        return loss if criterion.reduction == "mean" else loss * (labels >= 0).sum().to(loss.dtype)
     plain_ce = isinstance(criterion, nn.CrossEntropyLoss) and criterion.reduction == "mean" \
         and criterion.label_smoothing == 0.0
     if plain_ce and preds.is_cuda:

@@ -535,6 +535,35 @@ def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, weight: Optional[t
     return _CrossEntropy.apply(logits, labels, weight)
 
 
+class _FocalLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, alpha, gamma):
+        B, C = logits.shape
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        call("mar_focal_loss_fwd", logits.data_ptr(), labels.data_ptr(), _p(alpha), float(gamma), loss.data_ptr(),
+             dlogits.data_ptr(), B, C, _stream())
+        ctx.save_for_backward(dlogits)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None, None, None
+
+
+def focal_loss(logits: torch.Tensor, labels: torch.Tensor, alpha: Optional[torch.Tensor] = None, gamma: float = 0.0) -> torch.Tensor:
+    """Multi-class focal loss with 'mean' reduction (train_multimodal.py:494-510).  Rows with label < 0 are ignored."""
+    _require_cuda(logits, "focal_loss")
+    if logits.dtype != torch.float32:
+        logits = to_compute(logits, torch.float32)
+    logits = logits.contiguous()
+    labels = labels.to(device=logits.device, dtype=torch.int64).contiguous()
+    if alpha is not None:
+        alpha = alpha.to(device=logits.device, dtype=torch.float32).contiguous()
+    return _FocalLoss.apply(logits, labels, alpha, float(gamma))
+
+
 def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
     """argmax over classes on the device (trainer.py:170, :726)."""
     logits = to_compute(logits, torch.float32).contiguous()

@@ -200,6 +200,25 @@ def cross_entropy(logits: Tensor, labels: Tensor, weight: Optional[Tensor] = Non
     return (nll * w).sum() / w.sum()
 
 
+def focal_loss(logits: Tensor, labels: Tensor, alpha: Optional[Tensor] = None, gamma: float = 0.0,
+               ignore_index: int = -100) -> Tensor:
+    """The criterion train_multimodal.py:494-510 loads with torch.hub.load('adeelh/pytorch-multi-class-focal-loss',
+    'FocalLoss', alpha=class_weights, gamma=..., reduction='mean').  The hub repo is a third-party dependency that is
+    unpinned (default branch) and absent offline, so this restates its published algorithm — PARITY UNPINNED:
+        log_p = log_softmax(x);  ce = NLLLoss(weight=alpha, reduction='none')(log_p, y) = -alpha[y]·log_p[y]
+        pt = exp(log_p[y]);  loss = (1 - pt)^gamma · ce;  'mean' → loss.mean() over the rows with y != ignore_index
+    (a plain mean, unlike the alpha-weighted mean of nn.CrossEntropyLoss); no such rows → 0."""
+    keep = labels != ignore_index
+    labels, logits = labels[keep], logits[keep]
+    if labels.numel() == 0:
+        return logits.sum() * 0.0
+    m = logits.max(dim=1, keepdim=True).values
+    log_p = logits - m - torch.log(torch.exp(logits - m).sum(dim=1, keepdim=True))
+    log_pt = log_p.gather(1, labels[:, None]).squeeze(1)
+    a = torch.ones_like(log_pt) if alpha is None else alpha[labels]
+    return ((1.0 - torch.exp(log_pt)) ** gamma * (-a * log_pt)).mean()
+
+
 def adam_step(params: List[Tensor], grads: List[Optional[Tensor]], exp_avg: List[Tensor],
               exp_avg_sq: List[Tensor], step: int, lr: float = 1e-3, beta1: float = 0.9,
               beta2: float = 0.999, eps: float = 1e-8) -> None:

@@ -326,6 +326,39 @@ def test_cross_entropy_weighted_and_ignored():
     assert torch.equal(ops.argmax_rows(logits.to(DEV)).cpu(), logits.argmax(dim=1))
 
 
+@pytest.mark.parametrize("gamma", [0.0, 1.5, 2.0])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_focal_loss_kernel_and_module(gamma, weighted):
+    """mar_focal_loss_fwd + the FocalLoss drop-in (train_multimodal.py:494-510) against the oracle restatement of the
+    hub module: value and gradient, ignored rows, the all-ignored batch, and gamma = 0 == alpha-weighted NLL mean."""
+    from multimodalaggressionrecognition_b200 import models as M
+    B, C = 37, 3
+    logits = torch.randn(B, C) * 2
+    labels = torch.randint(0, C, (B,))
+    labels[::5] = -100
+    alpha = torch.tensor([0.2, 1.0, 2.5]) if weighted else None
+    lr = logits.clone().requires_grad_(True)
+    ref = O.focal_loss(lr, labels, alpha, gamma)
+    ref.backward()
+    crit = M.FocalLoss(alpha=alpha, gamma=gamma, reduction="mean")
+    lg = logits.to(DEV).requires_grad_(True)
+    got = crit(lg, labels.to(DEV))
+    got.backward()
+    assert abs(float(got) - float(ref)) < 2e-6 * max(1.0, abs(float(ref)))
+    assert_close(lg.grad.cpu(), lr.grad, 2e-5, "focal grad")
+    assert float(lg.grad[::5].abs().max()) == 0.0
+    # through the multimodal criterion wrapper (EMPTY rows are masked the same way)
+    mm = M.MultiModalCrossEntropyLoss({"phys": crit})
+    names = tuple("phys" if i % 7 else "phys_EMPTY" for i in range(B))
+    lab2 = labels.clone(); lab2[labels == -100] = 0
+    out = mm({"phys": logits.to(DEV)}, [[names, lab2.to(DEV)]])
+    keep = torch.tensor([i % 7 != 0 for i in range(B)])
+    assert abs(float(out["phys"]) - float(O.focal_loss(logits[keep], lab2[keep], alpha, gamma))) < 2e-6 * max(1.0, abs(float(ref)))
+    # all rows ignored -> 0, finite gradient
+    z = M.FocalLoss(gamma=gamma)(lg, torch.full((B,), -100, device=DEV))
+    assert float(z) == 0.0
+
+
 # ------------------------------------------------------------------------------------------
 # recurrences
 # ------------------------------------------------------------------------------------------

@@ -86,3 +86,24 @@ def test_safe_softmax_all_masked_row():
     s[1, 2] = 0.5
     p = O.softmax_lastdim_safe(s)
     assert torch.equal(p[0], torch.zeros(4)) and float(p[1, 2]) == 1.0
+
+
+def test_oracle_focal_loss_restates_the_hub_module():
+    """The focal loss the reference fetches from torch.hub is absent offline: check the restatement against the
+    module's published forward written with torch's own log_softmax / nll_loss (parity unpinned, see oracle.py)."""
+    import torch.nn.functional as F
+    from oracle import oracle as O
+    torch.manual_seed(0)
+    x = torch.randn(50, 4) * 3
+    y = torch.randint(0, 4, (50,))
+    y[::6] = -100
+    alpha = torch.tensor([0.3, 1.0, 2.0, 0.7])
+    for gamma in (0.0, 1.5, 2.0):
+        keep = y != -100
+        log_p = F.log_softmax(x[keep], dim=-1)
+        ce = F.nll_loss(log_p, y[keep], weight=alpha, reduction="none")
+        pt = log_p[torch.arange(int(keep.sum())), y[keep]].exp()
+        ref = ((1 - pt) ** gamma * ce).mean()
+        got = O.focal_loss(x, y, alpha, gamma)
+        assert abs(float(got) - float(ref)) < 1e-6
+    assert float(O.focal_loss(x, torch.full((50,), -100), alpha, 2.0)) == 0.0
