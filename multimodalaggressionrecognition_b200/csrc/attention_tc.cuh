@@ -109,4 +109,24 @@ inline int make_map_btc(CUtensorMap* map, const void* base, int64_t B, int64_t T
 }
 
 
+// 3-D fp32 map over a (B, T, cols) tensor, no swizzle: box = box_cols columns x box_rows tokens x 1 batch element.
+// Used for TMA reduce-add stores (cp.reduce.async.bulk.tensor): rows t >= T are clipped by the hardware.
+inline int make_map_f32_btc(CUtensorMap* map, const void* base, int64_t B, int64_t T, int64_t cols, int box_cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) { mar_set_error("cuTensorMapEncodeTiled not available from the driver"); return MAR_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstride[2] = {(cuuint64_t)cols * 4, (cuuint64_t)T * (cuuint64_t)cols * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mar_set_error("cuTensorMapEncodeTiled (attention dQ accumulator) failed (%d): B=%lld T=%lld cols=%lld", (int)r, (long long)B,
+                  (long long)T, (long long)cols);
+    return MAR_ERR_CUDA;
+  }
+  return MAR_OK;
+}
+
 }  // namespace attn_tc

@@ -28,6 +28,7 @@
 // Dropout: the shared counter hash with element index ((b·H+h)·T + q)·Tp + k (common.cuh), i.e. the mask the
 // forward of ANY engine drew.  Fully masked rows (LSE = -inf) contribute nothing.
 #include <algorithm>
+#include <type_traits>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "attention.cuh"
@@ -43,7 +44,8 @@ constexpr int BQ = 64;                  // queries per step
 constexpr int NCOMPUTE = 16;            // compute warps
 constexpr int NREAD = 4;                // dQᵀ read-out warps
 constexpr int NTHREADS = (2 + NCOMPUTE + NREAD) * 32;
-constexpr int QSTAGES = 3;              // Q / dO smem ring
+constexpr int QSTAGES = 4;              // Q / dO smem ring: tile i+4 is requested when tile i retires, two tile periods ahead of its use
+                                        // (with 3 stages the TMA round trip was exposed: compute warps waited 60 % of the time for Sᵀ)
 constexpr int LSTAGES = 4;              // LSE / delta smem ring
 constexpr int QBOX_BYTES = BQ * 128;    // one 64-row x 64-column box
 
@@ -60,8 +62,10 @@ struct BwdParams {
   int smem_bytes;
 };
 
-__device__ __forceinline__ void red_add_f32(float* p, float a) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+// smem tile -> global tensor with element-wise fp32 add, performed by the TMA unit (no LSU atomics)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -72,10 +76,20 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                : "memory");
 }
 
-template <int DH>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// IDX32: every dropout pair index of the launch fits 32 bits (true for all the reference's shapes)
+template <int DH, bool IDX32>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
-                   const __grid_constant__ CUtensorMap tm_do, const BwdParams p) {
+                   const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dq, const BwdParams p) {
   constexpr int NBOX = (DH + 63) / 64;
   constexpr int KV_BYTES = NBOX * BOX_BYTES;        // 128-row operand tile
   constexpr int Q_BYTES = NBOX * QBOX_BYTES;        // 64-row operand tile
@@ -92,20 +106,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
   uint8_t* sV = sK + KV_BYTES;
   uint8_t* sQ = sV + KV_BYTES;                  // [QSTAGES][Q_BYTES]
   uint8_t* sDO = sQ + QSTAGES * Q_BYTES;        // [QSTAGES][Q_BYTES]
-  uint8_t* sDS = sDO + QSTAGES * Q_BYTES;       // [2][DS_BYTES]
-  float* sL = reinterpret_cast<float*>(sDS + 2 * DS_BYTES);   // [LSTAGES][64] LSE in log2 units (+inf = no contribution)
+  uint8_t* sDS = sDO + QSTAGES * Q_BYTES;       // [DS_BYTES] (single: rewritten only after the dQᵀ MMA that read it)
+  constexpr int DQ_ROWS = DH <= 96 ? 32 : 16;        // query rows per TMA reduce (staging size is what is left of 227 KB)
+  float* sDQ = reinterpret_cast<float*>(sDS + DS_BYTES);   // [DQ_ROWS][DH] fp32 staging of a dQ block
+  float* sL = sDQ + DQ_ROWS * DH;   // [LSTAGES][64] LSE in log2 units (+inf = no contribution)
   float* sD = sL + LSTAGES * BQ;                              // [LSTAGES][64] delta
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + LSTAGES * BQ);
   uint64_t* bar_kv = bars + 0;
   uint64_t* bar_qdo = bars + 1;                 // [QSTAGES] Q_i / dO_i tiles landed
-  uint64_t* bar_ld = bars + 4;                  // [LSTAGES] LSE / delta of tile i staged
-  uint64_t* bar_ldfree = bars + 8;              // [LSTAGES] compute warps are done with that stage
-  uint64_t* bar_s = bars + 12;                  // [2] Sᵀ, dPᵀ of a TMEM stage complete
-  uint64_t* bar_pds = bars + 14;                // [2] P̃ᵀ, dSᵀ written (TMEM + smem) by the compute warps
-  uint64_t* bar_mma2 = bars + 16;               // dV, dK, dQᵀ MMAs of tile i complete
-  uint64_t* bar_dqr = bars + 17;                // dQᵀ tile read out of TMEM
-  uint64_t* bar_done = bars + 18;               // every MMA of this CTA complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* bar_ld = bars + 5;                  // [LSTAGES] LSE / delta of tile i staged
+  uint64_t* bar_ldfree = bars + 9;              // [LSTAGES] compute warps are done with that stage
+  uint64_t* bar_s = bars + 13;                  // [2] Sᵀ, dPᵀ of a TMEM stage complete
+  uint64_t* bar_pds = bars + 15;                // [2] P̃ᵀ, dSᵀ written (TMEM + smem) by the compute warps
+  uint64_t* bar_mma2 = bars + 17;               // dV, dK, dQᵀ MMAs of tile i complete
+  uint64_t* bar_dqr = bars + 18;                // dQᵀ tile read out of TMEM
+  uint64_t* bar_done = bars + 19;               // every MMA of this CTA complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   if (reinterpret_cast<uint8_t*>(tmem_slot + 2) > smem_raw + p.smem_bytes) __trap();   // dynamic smem base less aligned than assumed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -116,6 +132,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
   const int b = bh / H, h = bh % H;
   const int d = H * DH;
   const int nk = min(BT, T - kt * BT);    // keys of this tile inside the sequence
+  // The key tiles of one (b,h) run on neighbouring SMs at the same time and all reduce into the same dQ rows:
+  // each starts its walk over the query tiles at a different place, so concurrent red.adds hit different rows.
+  const int q_rot = (kt * n_q) / n_kt;
+  auto q_tile = [&](int i) { const int t = i + q_rot; return t >= n_q ? t - n_q : t; };
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_kv);
@@ -148,8 +168,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
       mbar_expect_tx(bar_qdo + s, 2 * Q_BYTES);
 #pragma unroll
       for (int bx = 0; bx < NBOX; bx++) {
-        tma_load_3d(sQ + s * Q_BYTES + bx * QBOX_BYTES, &tm_q, bar_qdo + s, h * DH + bx * 64, i * BQ, b);
-        tma_load_3d(sDO + s * Q_BYTES + bx * QBOX_BYTES, &tm_do, bar_qdo + s, h * DH + bx * 64, i * BQ, b);
+        tma_load_3d(sQ + s * Q_BYTES + bx * QBOX_BYTES, &tm_q, bar_qdo + s, h * DH + bx * 64, q_tile(i) * BQ, b);
+        tma_load_3d(sDO + s * Q_BYTES + bx * QBOX_BYTES, &tm_do, bar_qdo + s, h * DH + bx * 64, q_tile(i) * BQ, b);
       }
     };
     if (elect_one()) {
@@ -172,7 +192,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
     int issued = 0;
     auto issue_s = [&](int i) {           // Sᵀ_i and dPᵀ_i into TMEM stage i % NST
       const int s = i % QSTAGES;
-      const int nq = min(BQ, T - i * BQ);
+      const int nq = min(BQ, T - q_tile(i) * BQ);
       const uint32_t col = tmem_base + COL_ST + (uint32_t)(i % NST) * 128;
       const uint32_t idesc_s = make_idesc_bf16(BT, (nq + 15) & ~15, 0, 0);
       mbar_wait(bar_qdo + s, (i / QSTAGES) & 1);
@@ -196,7 +216,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
     ensure_s(LOOK);
     for (int i = 0; i < n_q; i++) {
       const int s = i % QSTAGES;
-      const int nq = min(BQ, T - i * BQ);
+      const int nq = min(BQ, T - q_tile(i) * BQ);
       const int qsteps = (nq + 15) / 16;
       const uint32_t col = tmem_base + COL_ST + (uint32_t)(i % NST) * 128;
       mbar_wait(bar_pds + (i % NST), (i / NST) & 1);
@@ -220,7 +240,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
 #pragma unroll 1
         for (int ks = 0; ks < ksteps_keys; ks++)
           umma_f16(tmem_base + COL_DQ, make_desc_mnmajor(sK_a, ks, BOX_BYTES),
-                   make_desc_mnmajor(sDS_a + (i & 1) * DS_BYTES, ks, DS_BYTES), idesc_dq, ks > 0 ? 1u : 0u);
+                   make_desc_mnmajor(sDS_a, ks, DS_BYTES), idesc_dq, ks > 0 ? 1u : 0u);
         umma_commit(bar_mma2);
         if (i == n_q - 1) umma_commit(bar_done);
       }
@@ -238,7 +258,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
       const int s = i % LSTAGES;
       if (i >= LSTAGES) mbar_wait(bar_ldfree + s, ((i / LSTAGES) - 1) & 1);
       for (int k = lane; k < BQ; k += 32) {
-        const int q = i * BQ + k;
+        const int q = q_tile(i) * BQ + k;
         float l = INFINITY, dl = 0.f;
         if (q < T) {
           l = p.lse[(int64_t)bh * T + q] * LOG2E;
@@ -266,7 +286,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
     if (drop) dk = make_drop_key(p.rng, p.site, p.p_drop);
     const uint64_t Tp = (uint64_t)((T + 1) & ~1);
     const uint64_t half_tp = Tp >> 1;
-    const bool hi_half = (key & 1) != 0;
+    const uint32_t keep_shift = (key & 1) ? 0u : 16u;    // which 16-bit half of the pair hash belongs to this key
+    const uint32_t thr_hi = dk.thr16 << 16;
+    const uint32_t half_tp32 = (uint32_t)half_tp;
     // dSᵀ smem row of this key: [row][64 queries], 16 B chunks XOR-swizzled by (row % 8)
     const int ds_off0 = row * 128 + (((chunk * 2) ^ (row & 7)) << 4);
     const int ds_off1 = row * 128 + (((chunk * 2 + 1) ^ (row & 7)) << 4);
@@ -274,7 +296,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
 
     for (int i = 0; i < n_q; i++) {
       const int ls = i % LSTAGES, st = i % NST;
-      const int nq = min(BQ, T - i * BQ);
+      const int nq = min(BQ, T - q_tile(i) * BQ);
       const bool active = chunk * 16 < nq;
       const float* l_s = sL + ls * BQ + chunk * 16;
       const float* d_s = sD + ls * BQ + chunk * 16;
@@ -288,40 +310,56 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
         tmem_ld_32x32b_x16(col + chunk * 16, rs);
         tmem_ld_32x32b_x16(col + 64 + chunk * 16, rp);
         // pair index of element (q, key): (((bh*T + q) * Tp) >> 1) + (key >> 1)
-        uint64_t pair = (((uint64_t)bh * (uint64_t)T + (uint64_t)(i * BQ + chunk * 16)) * Tp >> 1) + (uint64_t)(key >> 1);
+        uint64_t pair = (((uint64_t)bh * (uint64_t)T + (uint64_t)(q_tile(i) * BQ + chunk * 16)) * Tp >> 1) + (uint64_t)(key >> 1);
+        uint32_t pair32 = (uint32_t)pair;
+        const uint32_t l_addr = smem_u32(l_s), d_addr = smem_u32(d_s);
+        // the whole 16-column chunk inside the sequence and every key of the warp valid: no per-element selects
+        const bool fast = (chunk * 16 + 16 <= nq) && __all_sync(0xffffffffu, kvalid);
         tmem_ld_wait();
+        auto body = [&](auto fast_tag) {
+          constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          float pd[2], ds[2];
+          for (int e4 = 0; e4 < 16; e4 += 4) {
+            const float4 l4 = lds128(l_addr + e4 * 4), d4 = lds128(d_addr + e4 * 4);
+            const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            float pd[4], ds[4];
 #pragma unroll
-          for (int u = 0; u < 2; u++) {
-            const int ql = e + u;
-            const bool ok = kvalid && (chunk * 16 + ql < nq);
-            const float pr = ok ? ex2f(fmaf(__uint_as_float(rs[ql]), scale2, -l_s[ql])) : 0.f;
-            float dp = __uint_as_float(rp[ql]);
-            float pdv = pr;
-            if (drop) {
-              const uint32_t r = drop_rand_pair(dk, pair);
-              const bool keep = (hi_half ? (r >> 16) : (r & 0xffffu)) >= dk.thr16;
-              pdv = keep ? pr * dk.scale : 0.f;
-              dp = keep ? dp * dk.scale : 0.f;
-              pair += half_tp;
+            for (int u = 0; u < 4; u++) {
+              const int ql = e4 + u;
+              const bool ok = FAST || (kvalid && (chunk * 16 + ql < nq));
+              float pr = ex2f(fmaf(__uint_as_float(rs[ql]), scale2, -lv[u]));
+              if (!FAST) pr = ok ? pr : 0.f;
+              float dp = __uint_as_float(rp[ql]);
+              float pdv = pr;
+              if (drop) {
+                uint32_t r;
+                if (IDX32) { r = drop_rand_pair32(dk, pair32); pair32 += half_tp32; }
+                else { r = drop_rand_pair(dk, pair); pair += half_tp; }
+                const bool keep = (r << keep_shift) >= thr_hi;     // == (16-bit half of r) >= thr16
+                pdv = keep ? pr * dk.scale : 0.f;
+                dp = keep ? dp * dk.scale : 0.f;
+              }
+              pd[u] = pdv;
+              ds[u] = pr * (dp - dv[u]);
+              if (!FAST) ds[u] = ok ? ds[u] : 0.f;
             }
-            pd[u] = pdv;
-            ds[u] = ok ? pr * (dp - d_s[ql]) : 0.f;
+            pk[e4 / 2] = pack_bf16x2(pd[0], pd[1]);
+            pk[e4 / 2 + 1] = pack_bf16x2(pd[2], pd[3]);
+            dsk[e4 / 2] = pack_bf16x2(ds[0], ds[1]);
+            dsk[e4 / 2 + 1] = pack_bf16x2(ds[2], ds[3]);
           }
-          pk[e / 2] = pack_bf16x2(pd[0], pd[1]);
-          dsk[e / 2] = pack_bf16x2(ds[0], ds[1]);
-        }
+        };
+        if (fast) body(std::true_type{}); else body(std::false_type{});
       }
       // every warp of this lane quarter has read its Sᵀ / dPᵀ columns: the packed results may overwrite them
       named_bar_sync(1 + quarter, 128);
       if (active) {
         tmem_st_32x32b_x8(col + chunk * 8, pk);
         tmem_st_32x32b_x8(col + 64 + chunk * 8, dsk);
-        uint8_t* dsb = sDS + (i & 1) * DS_BYTES;
-        *reinterpret_cast<uint4*>(dsb + ds_off0) = make_uint4(dsk[0], dsk[1], dsk[2], dsk[3]);
-        *reinterpret_cast<uint4*>(dsb + ds_off1) = make_uint4(dsk[4], dsk[5], dsk[6], dsk[7]);
+        if (i > 0) mbar_wait(bar_mma2, (i - 1) & 1);     // the dQᵀ MMA of the previous tile has finished reading dSᵀ
+        const uint32_t dsb = smem_u32(sDS);
+        sts128(dsb + ds_off0, dsk[0], dsk[1], dsk[2], dsk[3]);
+        sts128(dsb + ds_off1, dsk[4], dsk[5], dsk[6], dsk[7]);
         tmem_st_wait();
         fence_proxy_async();
       }
@@ -363,7 +401,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
     const float scale = rsqrtf((float)DH);
     const bool live = quarter * 32 < DH;                // warp-uniform
     for (int i = 0; i < n_q; i++) {
-      const int nq = min(BQ, T - i * BQ);
+      const int nq = min(BQ, T - q_tile(i) * BQ);
       uint32_t r0[32], r1[32];
       mbar_wait(bar_mma2, i & 1);
       tc_fence_after();
@@ -375,26 +413,40 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dqr);      // the MMA issuer may overwrite dQᵀ while we drain the registers
-      if (live && c < DH) {
-        if (p.dq_acc != nullptr) {
-          float* dst = p.dq_acc + ((int64_t)b * T + (int64_t)i * BQ) * d + h * DH + c;
+      if (p.dq_acc != nullptr) {
+        // dQ block -> fp32 staging [q][dh] in shared memory -> ONE TMA reduce-add per DQ_ROWS query rows (the L2 does the
+        // adds; scalar red.global.add ran at about one element per clock per SM and paced the whole kernel)
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (j < nq) red_add_f32(dst + (int64_t)j * d, __uint_as_float(r0[j]) * scale);
+        for (int g0 = 0; g0 < BQ; g0 += DQ_ROWS) {
+          if (g0 < nq) {                                  // warp-uniform
+            if (warp == 2 + NCOMPUTE && lane == 0) tma_store_wait_read();      // the previous reduce has read the staging
+            named_bar_sync(5, NREAD * 32);
+            if (live && c < DH) {
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (32 + j < nq) red_add_f32(dst + (int64_t)(32 + j) * d, __uint_as_float(r1[j]) * scale);
-        } else {
-          bf16* dst = p.dqkv + ((int64_t)b * T + (int64_t)i * BQ) * (3 * d) + h * DH + c;
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (j < nq) dst[(int64_t)j * 3 * d] = __float2bfloat16_rn(__uint_as_float(r0[j]) * scale);
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (32 + j < nq) dst[(int64_t)(32 + j) * 3 * d] = __float2bfloat16_rn(__uint_as_float(r1[j]) * scale);
+              for (int j = 0; j < DQ_ROWS; j++) {
+                const int jj = g0 + j;
+                sDQ[j * DH + c] = __uint_as_float(jj < 32 ? r0[jj & 31] : r1[jj & 31]) * scale;
+              }
+            }
+            fence_proxy_async();
+            named_bar_sync(5, NREAD * 32);
+            if (warp == 2 + NCOMPUTE && lane == 0) {
+              tma_reduce_add_3d(&tm_dq, sDQ, h * DH, q_tile(i) * BQ + g0, b);
+              tma_store_commit();
+            }
+          }
         }
+      } else if (live && c < DH) {
+        bf16* dst = p.dqkv + ((int64_t)b * T + (int64_t)q_tile(i) * BQ) * (3 * d) + h * DH + c;
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (j < nq) dst[(int64_t)j * 3 * d] = __float2bfloat16_rn(__uint_as_float(r0[j]) * scale);
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (32 + j < nq) dst[(int64_t)(32 + j) * 3 * d] = __float2bfloat16_rn(__uint_as_float(r1[j]) * scale);
       }
     }
+    if (warp == 2 + NCOMPUTE && lane == 0) tma_store_wait_all();      // every reduce has landed before the CTA retires
   }
 
   tc_fence_before();
@@ -452,16 +504,18 @@ attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, i
   }
 }
 
-template <int DH>
-int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
+template <int DH, bool IDX32>
+int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
                void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
   constexpr int NBOX = (DH + 63) / 64;
-  constexpr int USED = 2 * NBOX * BOX_BYTES + 2 * QSTAGES * NBOX * QBOX_BYTES + 2 * BT * 128 + 2 * LSTAGES * BQ * 4 + 19 * 8 + 16;
+  constexpr int USED = 2 * NBOX * BOX_BYTES + 2 * QSTAGES * NBOX * QBOX_BYTES + BT * 128 + (DH <= 96 ? 32 : 16) * DH * 4 +
+                       2 * LSTAGES * BQ * 4 + 20 * 8 + 16;
+  static_assert(USED + 1024 <= 232448, "attention backward: shared memory budget");
   constexpr int SMEM = USED + 1024;
   static_assert(SMEM <= 232448, "attention backward: shared memory budget");
   static bool cfg = false;
   if (!cfg) {
-    MAR_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, IDX32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     cfg = true;
   }
   const int64_t d = H * DH;
@@ -474,18 +528,24 @@ int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const 
     MAR_LAUNCH_CHECK("attn_delta_tc");
   }
   if (dq_acc != nullptr) MAR_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)(B * T * d) * sizeof(float), st));
-  CUtensorMap tm_kv, tm_q, tm_do;
+  CUtensorMap tm_kv, tm_q, tm_do, tm_dq;
   int rc = make_map_btc(&tm_kv, qkv, B, T, 3 * d, BT);
   if (rc) return rc;
   rc = make_map_btc(&tm_q, qkv, B, T, 3 * d, BQ);
   if (rc) return rc;
   rc = make_map_btc(&tm_do, dout, B, T, d, BQ);
   if (rc) return rc;
+  if (dq_acc != nullptr) {
+    rc = make_map_f32_btc(&tm_dq, dq_acc, B, T, d, DH, DH <= 96 ? 32 : 16);
+    if (rc) return rc;
+  } else {
+    tm_dq = tm_do;            // unused by the kernel when T <= 128
+  }
   BwdParams prm;
   prm.key_mask = key_mask; prm.lse = lse; prm.delta = delta; prm.dq_acc = dq_acc; prm.dqkv = (bf16*)dqkv;
   prm.B = (int)B; prm.T = (int)T; prm.H = (int)H; prm.p_drop = p; prm.rng = rng; prm.site = site; prm.smem_bytes = SMEM;
   const int64_t n_t = ceil_div(T, BT);
-  attn_bwd_tc_kernel<DH><<<(unsigned)(B * H * n_t), NTHREADS, SMEM, st>>>(tm_kv, tm_q, tm_do, prm);
+  attn_bwd_tc_kernel<DH, IDX32><<<(unsigned)(B * H * n_t), NTHREADS, SMEM, st>>>(tm_kv, tm_q, tm_do, tm_dq, prm);
   MAR_LAUNCH_CHECK("attn_bwd_tc");
   if (dq_acc != nullptr) {
     const int64_t n = B * T * (d / 8);
@@ -494,6 +554,15 @@ int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const 
     MAR_LAUNCH_CHECK("attn_dq_convert");
   }
   return MAR_OK;
+}
+
+template <int DH>
+int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
+               void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
+  const int64_t Tp = (T + 1) & ~(int64_t)1;
+  const bool idx32 = (B * H * T + 64) * Tp / 2 + T < (int64_t)0xffffffffll;      // largest pair index any thread forms
+  return idx32 ? bwd_launch_t<DH, true>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st)
+               : bwd_launch_t<DH, false>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st);
 }
 
 }  // namespace

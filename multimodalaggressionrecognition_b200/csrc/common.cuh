@@ -163,6 +163,10 @@ __device__ __forceinline__ uint32_t drop_rand_pair(const DropKey& k, uint64_t pa
   uint32_t lo = (uint32_t)pair_index, hi = (uint32_t)(pair_index >> 32);
   return lowbias32(lo ^ k.key ^ (hi * 0x85ebca6bu));
 }
+// the same 32 random bits when the pair index is known to fit 32 bits (hi == 0 folds away)
+__device__ __forceinline__ uint32_t drop_rand_pair32(const DropKey& k, uint32_t pair_index) {
+  return lowbias32(pair_index ^ k.key);
+}
 // keep flag of one element with linear index e
 __device__ __forceinline__ bool drop_keep(const DropKey& k, uint64_t e) {
   uint32_t r = drop_rand_pair(k, e >> 1);
