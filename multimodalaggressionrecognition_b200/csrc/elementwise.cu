@@ -36,44 +36,77 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
   for (int j = 0; j < VEC; j++) csum[j] = 0.f;
 
   if (c0 < N) {
-    for (int64_t r = r_begin + ry; r < r_end; r += 8) {
-      float g[VEC], o[VEC];
-      const int64_t e0 = r * N + c0;
-      if (VEC == 8) {
-        float g8[8];
-        Vec8<T>::load(dout + e0, g8);
+    if (VEC == 8) {
+      // 4 rows per trip: all loads of the trip are issued before the first use (memory-level parallelism), the
+      // dropout mask comes from ONE hash per PAIR of elements (drop_keep2), as in the forward epilogue
+      constexpr int U = 4;
+      for (int64_t r = r_begin + ry; r < r_end; r += 8 * U) {
+        uint4 gq[U], oq[U];
 #pragma unroll
-        for (int j = 0; j < VEC; j++) g[j] = g8[j];
-        if (relu) {
-          float o8[8];
-          Vec8<TO>::load(out + e0, o8);
-#pragma unroll
-          for (int j = 0; j < VEC; j++) o[j] = o8[j];
+        for (int u = 0; u < U; u++) {
+          const int64_t rr = r + 8 * u;
+          if (rr < r_end) {
+            gq[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(dout) + (rr * N + c0) * sizeof(T));
+            if (relu) oq[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(out) + (rr * N + c0) * sizeof(TO));
+          }
         }
-      } else {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int64_t rr = r + 8 * u;
+          if (rr >= r_end) break;
+          const int64_t e0 = rr * N + c0;
+          float g[8], o[8];
+          if (sizeof(T) == 2) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&gq[u]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const float2 f2 = __bfloat1622float2(h2[j]); g[2 * j] = f2.x; g[2 * j + 1] = f2.y; }
+          } else {
+            Vec8<T>::load(dout + e0, g);
+          }
+          if (relu) {
+            if (sizeof(TO) == 2) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&oq[u]);
+#pragma unroll
+              for (int j = 0; j < 4; j++) { const float2 f2 = __bfloat1622float2(h2[j]); o[2 * j] = f2.x; o[2 * j + 1] = f2.y; }
+            } else {
+              Vec8<TO>::load(out + e0, o);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) g[j] = o[j] > 0.f ? g[j] * scale : 0.f;
+          } else if (drop) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              bool k0, k1;
+              drop_keep2(dk, (uint64_t)(e0 >> 1) + j, k0, k1);      // N % 8 == 0 and c0 % 8 == 0: e0 is even
+              g[2 * j] = k0 ? g[2 * j] * scale : 0.f;
+              g[2 * j + 1] = k1 ? g[2 * j + 1] * scale : 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) csum[j % VEC] += g[j];
+          if (dz != nullptr) Vec8<T>::store(dz + e0, g);
+        }
+      }
+    } else {
+      for (int64_t r = r_begin + ry; r < r_end; r += 8) {
+        float g[VEC], o[VEC];
+        const int64_t e0 = r * N + c0;
 #pragma unroll
         for (int j = 0; j < VEC; j++) {
           bool ok = c0 + j < N;
           g[j] = ok ? to_f32<T>(dout[e0 + j]) : 0.f;
           o[j] = (ok && relu) ? to_f32<TO>(out[e0 + j]) : 0.f;
         }
-      }
 #pragma unroll
-      for (int j = 0; j < VEC; j++) {
-        float f;
-        if (relu) f = o[j] > 0.f ? scale : 0.f;
-        else if (drop) f = drop_keep(dk, (uint64_t)(e0 + j)) ? scale : 0.f;
-        else f = 1.f;
-        g[j] *= f;
-        csum[j] += g[j];
-      }
-      if (dz != nullptr) {
-        if (VEC == 8) {
-          float g8[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) g8[j] = g[j % VEC];
-          Vec8<T>::store(dz + e0, g8);
-        } else {
+        for (int j = 0; j < VEC; j++) {
+          float f;
+          if (relu) f = o[j] > 0.f ? scale : 0.f;
+          else if (drop) f = drop_keep(dk, (uint64_t)(e0 + j)) ? scale : 0.f;
+          else f = 1.f;
+          g[j] *= f;
+          csum[j] += g[j];
+        }
+        if (dz != nullptr) {
 #pragma unroll
           for (int j = 0; j < VEC; j++)
             if (c0 + j < N) dz[e0 + j] = from_f32<T>(g[j]);
