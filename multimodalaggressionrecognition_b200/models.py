@@ -73,14 +73,16 @@ def encoder_layer_forward(layer: nn.TransformerEncoderLayer, h: torch.Tensor, B:
     sa = layer.self_attn
     train = layer.training
     d = h.shape[-1]
-    qkv = ops.linear(h, sa.in_proj_weight, sa.in_proj_bias)
+    # fork=True: the residual branch takes h / x1 from the projection op, so in backward the residual gradient is
+    # added inside that projection's dgrad GEMM epilogue instead of by a separate elementwise pass
+    qkv, h_res = ops.linear(h, sa.in_proj_weight, sa.in_proj_bias, fork=True)
     o = ops.attention(qkv.view(B, T, 3 * d), key_mask, sa.num_heads, sa.dropout if train else 0.0)
-    pre1 = ops.linear(o.view(B * T, d), sa.out_proj.weight, sa.out_proj.bias, residual=h,
+    pre1 = ops.linear(o.view(B * T, d), sa.out_proj.weight, sa.out_proj.bias, residual=h_res,
                       dropout_p=layer.dropout1.p if train else 0.0)
     x1 = ops.layer_norm(pre1, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
-    hid = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu_pre=True,
-                     dropout_p=layer.dropout.p if train else 0.0)
-    pre2 = ops.linear(hid, layer.linear2.weight, layer.linear2.bias, residual=x1,
+    hid, x1_res = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu_pre=True,
+                             dropout_p=layer.dropout.p if train else 0.0, fork=True)
+    pre2 = ops.linear(hid, layer.linear2.weight, layer.linear2.bias, residual=x1_res,
                       dropout_p=layer.dropout2.p if train else 0.0)
     return ops.layer_norm(pre2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
 

@@ -242,8 +242,11 @@ def to_compute(x: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Te
 # --------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, flags, p, out_dtype, need_dx):
+    def forward(ctx, x, weight, bias, residual, flags, p, out_dtype, need_dx, fork=False):
         # x (M,K) compute dtype; weight (N,K) fp32 master; bias (N) fp32; residual (M,N) compute dtype
+        # fork: also return x itself as a second output.  A consumer that uses x twice (the projection and the
+        # residual branch of an encoder sub-layer) takes the residual from that output, so its gradient arrives
+        # HERE and is added inside the dgrad GEMM's epilogue (dx = dz·W + d_fork) instead of in a separate pass.
         M, K = x.shape
         N = weight.shape[0]
         cd = x.dtype
@@ -272,10 +275,13 @@ class _Linear(torch.autograd.Function):
         ctx.eng = _eng()
         need_out = bool(flags & (EPI_RELU_PRE | EPI_RELU_POST))
         ctx.save_for_backward(x, out if need_out else None)
+        ctx.fork = bool(fork)
+        if fork:
+            return out, x.view_as(x)
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dfork=None):
         x, out = ctx.saved_tensors
         M, K = x.shape
         N = ctx.w_shape[0]
@@ -296,22 +302,28 @@ class _Linear(torch.autograd.Function):
                 call("mar_linear_bwd_epilogue", dout.data_ptr(), None, None, dbias.data_ptr(), M, N, _dt(dout),
                      _dt(dout), 0, 0.0, None, 0, st)
         dx = dw = None
+        add = None
+        if ctx.fork and dfork is not None:
+            add = dfork if dfork.dtype == cd else _Cast.apply(dfork, cd)
+            add = add.contiguous()
         if needs_x:
             dx = torch.empty((M, K), dtype=cd, device=x.device)
-            call("mar_linear_dgrad", dz.data_ptr(), ctx.wc.data_ptr(), _p(ctx.wt), None, dx.data_ptr(), K, M, N, K,
+            call("mar_linear_dgrad", dz.data_ptr(), ctx.wc.data_ptr(), _p(ctx.wt), _p(add), dx.data_ptr(), K, M, N, K,
                  _dt(dz), ctx.eng, st)
         if needs_w:
             dw = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
             call("mar_linear_wgrad", dz.data_ptr(), x.data_ptr(), x.stride(0), dw.data_ptr(), M, N, K, _dt(dz), 0,
                  ctx.eng, st)
         dres = dout if (ctx.has_res and needs_r) else None
-        return dx, dw, dbias, dres, None, None, None, None
+        return dx, dw, dbias, dres, None, None, None, None, None
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, relu_pre: bool = False, dropout_p: float = 0.0,
-           relu_post: bool = False, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """out = residual + relu_post(dropout(relu_pre(x·Wᵀ + b))) on the last dim of x."""
+           relu_post: bool = False, out_dtype: Optional[torch.dtype] = None, fork: bool = False):
+    """out = residual + relu_post(dropout(relu_pre(x·Wᵀ + b))) on the last dim of x.
+    fork=True returns (out, x_fork): use x_fork wherever x is needed again (a residual branch) and its gradient is
+    folded into this linear's dgrad GEMM instead of a separate elementwise add."""
     shape = x.shape
     x2 = _rows(to_compute(x))
     r2 = None
@@ -319,8 +331,12 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         r2 = _rows(to_compute(residual, x2.dtype))
     flags = (EPI_RELU_PRE if relu_pre else 0) | (EPI_DROPOUT if dropout_p > 0 else 0) | (EPI_RELU_POST if relu_post else 0)
     need_dx = torch.is_grad_enabled() and x2.requires_grad
+    if fork and need_dx:
+        out, xf = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype, need_dx, True)
+        return out.view(*shape[:-1], weight.shape[0]), xf.view(shape)
     out = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype, need_dx)
-    return out.view(*shape[:-1], weight.shape[0])
+    out = out.view(*shape[:-1], weight.shape[0])
+    return (out, x2.view(shape)) if fork else out
 
 
 # --------------------------------------------------------------------------------------
