@@ -238,6 +238,47 @@ def to_compute(x: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Te
 
 
 # --------------------------------------------------------------------------------------
+# gradient sink: inside a TrainStep every parameter owns a persistent fp32 .grad view into one flat, pre-zeroed
+# buffer.  The weight-gradient GEMM / bias / LayerNorm reductions then accumulate STRAIGHT into that view and the
+# autograd Function returns None for the parameter, so no temporary, no zero-fill and no AccumulateGrad add kernel
+# is launched per parameter.  `notify` tells the step driver that the parameter's gradient is complete (the
+# post-accumulate hook autograd would have fired).
+# --------------------------------------------------------------------------------------
+_sink_cfg = {"on": False, "notify": None}
+
+
+@contextlib.contextmanager
+def grad_sink(notify=None):
+    old = dict(_sink_cfg)
+    _sink_cfg["on"], _sink_cfg["notify"] = True, notify
+    try:
+        yield
+    finally:
+        _sink_cfg.update(old)
+
+
+import os as _os
+# Which gradients are sunk: weights, biases (and "ln" = LayerNorm gains/offsets).  With ALL parameters sunk no
+# AccumulateGrad node runs at all and CUDA-graph capture of the step fails with cudaErrorStreamCaptureIsolation
+# (measured on torch 2.11), so the 18 small LayerNorm vectors keep going through autograd by default.
+_SINK_KINDS = set(_os.environ.get("MAR_SINK", "w,b").split(","))
+
+
+def _sink_target(param, kind: str = "w") -> Optional[torch.Tensor]:
+    if not _sink_cfg["on"] or not isinstance(param, torch.nn.Parameter) or kind not in _SINK_KINDS:
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous():
+        return None
+    return g
+
+
+def _sunk(param) -> None:
+    if _sink_cfg["notify"] is not None:
+        _sink_cfg["notify"](param)
+
+
+# --------------------------------------------------------------------------------------
 # linear (+ fused epilogue)
 # --------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
@@ -276,6 +317,7 @@ class _Linear(torch.autograd.Function):
         need_out = bool(flags & (EPI_RELU_PRE | EPI_RELU_POST))
         ctx.save_for_backward(x, out if need_out else None)
         ctx.fork = bool(fork)
+        ctx.weight_ref, ctx.bias_ref = weight, bias
         if fork:
             return out, x.view_as(x)
         return out
@@ -291,7 +333,10 @@ class _Linear(torch.autograd.Function):
             dout = _Cast.apply(dout, cd)
         dout = dout.contiguous()
         needs_x, needs_w, needs_b, needs_r = ctx.needs_input_grad[0:4]
-        dbias = torch.zeros(N, dtype=torch.float32, device=x.device) if (ctx.has_bias and needs_b) else None
+        dbias = sunk_b = None
+        if ctx.has_bias and needs_b:
+            sunk_b = _sink_target(ctx.bias_ref, "b")
+            dbias = sunk_b if sunk_b is not None else torch.zeros(N, dtype=torch.float32, device=x.device)
         if ctx.flags != 0:
             dz = torch.empty_like(dout)
             call("mar_linear_bwd_epilogue", dout.data_ptr(), _p(out), dz.data_ptr(), _p(dbias), M, N, _dt(dout),
@@ -311,9 +356,18 @@ class _Linear(torch.autograd.Function):
             call("mar_linear_dgrad", dz.data_ptr(), ctx.wc.data_ptr(), _p(ctx.wt), _p(add), dx.data_ptr(), K, M, N, K,
                  _dt(dz), ctx.eng, st)
         if needs_w:
-            dw = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
-            call("mar_linear_wgrad", dz.data_ptr(), x.data_ptr(), x.stride(0), dw.data_ptr(), M, N, K, _dt(dz), 0,
-                 ctx.eng, st)
+            sunk_w = _sink_target(ctx.weight_ref)
+            if sunk_w is not None and tuple(sunk_w.shape) == ctx.w_shape:
+                call("mar_linear_wgrad", dz.data_ptr(), x.data_ptr(), x.stride(0), sunk_w.data_ptr(), M, N, K, _dt(dz), 1,
+                     ctx.eng, st)
+                _sunk(ctx.weight_ref)
+            else:
+                dw = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
+                call("mar_linear_wgrad", dz.data_ptr(), x.data_ptr(), x.stride(0), dw.data_ptr(), M, N, K, _dt(dz), 0,
+                     ctx.eng, st)
+        if sunk_b is not None:
+            dbias = None
+            _sunk(ctx.bias_ref)
         dres = dout if (ctx.has_res and needs_r) else None
         return dx, dw, dbias, dres, None, None, None, None, None
 
@@ -391,8 +445,9 @@ def attention(qkv: torch.Tensor, key_mask: Optional[torch.Tensor], num_heads: in
 # --------------------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, zero_rows, need_grad):
+    def forward(ctx, x, gamma, beta, eps, zero_rows, need_grad, gamma_ref=None, beta_ref=None):
         rows, D = x.shape
+        ctx.gamma_ref, ctx.beta_ref = gamma_ref, beta_ref
         y = torch.empty_like(x)
         if zero_rows is not None and need_grad:
             raise RuntimeError("layer_norm(zero_rows=...) is the eval-only nested-tensor zero fill; no backward")
@@ -411,11 +466,16 @@ class _LayerNorm(torch.autograd.Function):
             dy = _Cast.apply(dy, x.dtype)
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        dgamma = torch.zeros(D, dtype=torch.float32, device=x.device)
-        dbeta = torch.zeros(D, dtype=torch.float32, device=x.device)
+        sg, sb = _sink_target(ctx.gamma_ref, "ln"), _sink_target(ctx.beta_ref, "ln")
+        sunk = sg is not None and sb is not None
+        dgamma = sg if sunk else torch.zeros(D, dtype=torch.float32, device=x.device)
+        dbeta = sb if sunk else torch.zeros(D, dtype=torch.float32, device=x.device)
         call("mar_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
              dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D, _dt(x), _stream())
-        return dx, dgamma, dbeta, None, None, None
+        if sunk:
+            _sunk(ctx.gamma_ref); _sunk(ctx.beta_ref)
+            return dx, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None
 
 
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
@@ -425,7 +485,8 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     g = gamma if gamma.dtype == torch.float32 else gamma.float()
     b = beta if beta.dtype == torch.float32 else beta.float()
     need_grad = torch.is_grad_enabled() and (x2.requires_grad or g.requires_grad or b.requires_grad)
-    return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad).view(shape)
+    return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad, gamma if g is gamma else None,
+                            beta if b is beta else None).view(shape)
 
 
 # --------------------------------------------------------------------------------------

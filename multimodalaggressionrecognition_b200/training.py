@@ -125,10 +125,20 @@ class GradSync:
         self.handles = []
         self.order: List[int] = []
         self.enabled = True          # False: hooks do nothing (backward passes outside a TrainStep, e.g. profiling)
+        self.index_of = {id(p): i for i, p in enumerate(flat.params)}
+        self._hooks = [self._make_hook(i) for i in range(n)]
         if self.world > 1:
             for i, p in enumerate(flat.params):
-                p.register_post_accumulate_grad_hook(self._make_hook(i))
+                p.register_post_accumulate_grad_hook(self._hooks[i])
         self.reset()
+
+    def notify(self, param) -> None:
+        """A kernel accumulated this parameter's gradient straight into the flat buffer (ops.grad_sink), so autograd
+        will not run its post-accumulate hook: count it here."""
+        if self.world > 1:
+            i = self.index_of.get(id(param))
+            if i is not None:
+                self._hooks[i](param)
 
     def reset(self) -> None:
         for b, (lo, hi, _, _) in enumerate(self.buckets):
@@ -226,11 +236,12 @@ class TrainStep:
             ops.rng_advance(self.flat.flat.device)
         pred = self.model(data)
         losses = self.criterion(pred, labels)
-        if hasattr(losses, "backward") and not isinstance(losses, torch.Tensor):
-            losses.backward()
-        else:
-            losses.backward()
-            losses = {"loss": losses}
+        with ops.grad_sink(self.sync.notify):       # weight / bias / LayerNorm gradients accumulate straight into the flat buffer
+            if hasattr(losses, "backward") and not isinstance(losses, torch.Tensor):
+                losses.backward()
+            else:
+                losses.backward()
+                losses = {"loss": losses}
         self.sync.finish()
         self.opt.step()
         self.last_pred = pred
