@@ -300,7 +300,7 @@ def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
             e0.record()
             orig(name, *a)
             e1.record()
-            recs.append((name, 2.0 * a[i] * a[j] * a[k], e0, e1, _lib.load().mar_last_engine()))
+            recs.append((name, 2.0 * a[i] * a[j] * a[k], e0, e1, _lib.load().mar_last_engine(), (a[i], a[j], a[k])))
         else:
             orig(name, *a)
 
@@ -309,16 +309,27 @@ def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
     try:
         for p in model.parameters():
             p.grad = None
-        for it in range(2):                    # first pass warms, second is recorded
-            recs.clear()
+        passes = []
+        for it in range(4):                    # first pass warms; three recorded passes, per-launch MEDIAN (an eager
+            recs.clear()                       # launch can sit behind a host hiccup that a graph replay never sees)
             ops.rng_advance()
             losses = crit(model(gdata), glabels)
             losses.backward()
             torch.cuda.synchronize()
+            if it > 0:
+                passes.append([(nm, f, e0.elapsed_time(e1), eng, mnk) for (nm, f, e0, e1, eng, mnk) in recs])
     finally:
         ops.call = orig
         training.call = orig
-    tc = [(f, e0.elapsed_time(e1)) for (_, f, e0, e1, eng) in recs if eng == 2]
+    n = min(len(p_) for p_ in passes)
+    med = []
+    for i in range(n):
+        nm, f, _, eng, mnk = passes[0][i]
+        med.append((nm, f, statistics.median(p_[i][2] for p_ in passes), eng, mnk))
+    if os.environ.get("MAR_GEMM_TABLE"):          # per-launch table on stderr (M, N, K as the C ABI names them)
+        for (nm, f, ms_, eng, mnk) in med:
+            log(f"{nm:18s} M={mnk[0]:6d} N={mnk[1]:5d} K={mnk[2]:5d} engine={eng} {ms_ * 1e3:8.1f} us {f / ms_ / 1e9:8.1f} TFLOP/s")
+    tc = [(f, ms_) for (_, f, ms_, eng, _mnk) in med if eng == 2]
     if not tc:
         return None
     flops = sum(f for f, _ in tc)
@@ -335,7 +346,8 @@ def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
             "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, mean over the step's 49 launches)",
             "launches": len(tc), "gemm_ms_per_step": ms,
             "gemm_flops_per_step": flops,
-            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernels timed inside a full step"}
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernels timed inside a full step "
+                           f"(CUDA events around every GEMM launch of an eager step, per-launch median of 3 steps)"}
 
 
 def main():
