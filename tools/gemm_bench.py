@@ -6,7 +6,7 @@ import torch
 from multimodalaggressionrecognition_b200 import _lib
 
 SHAPES = {"qkv": (80384, 2304, 768), "ffn1": (80384, 2048, 768), "ffn2": (80384, 768, 2048), "out": (80384, 768, 768),
-          "qkv_a": (64000, 2304, 768), "emb": (16384, 768, 512), "sq8k": (8192, 8192, 8192)}
+          "qkv_a": (64000, 2304, 768), "emb": (16384, 768, 512), "sq8k": (8192, 8192, 8192), "vid_out": (16384, 768, 768), "vid_qkv": (16384, 2304, 768)}
 
 def main():
     ap = argparse.ArgumentParser()
