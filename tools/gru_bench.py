@@ -67,4 +67,13 @@ for name, engine in (("auto", "auto"), ("steps", "simt")):
         res[f"c2_clips_per_s_{name}"] = round(B / ms * 1e3, 1)
     except Exception as e:  # the simt engine in bf16 mode may refuse some ops; report instead of hiding
         res[f"c2_train_step_{name}_error"] = str(e)[:200]
+# ---- the same step through the sync-free step driver (flat Adam, CUDA graph): what train_video_rnn.py would run
+from multimodalaggressionrecognition_b200 import training
+mar.set_precision("bf16")
+step = training.TrainStep(model, M.MultiCrossEntropyLoss(), graph=True)
+for _ in range(8):          # 3 eager warm-ups + one capture per input-buffer set happen before the timed region
+    step(x, y)
+ms = timeit(lambda: step(x, y), args.reps)
+res["c2_trainstep_graph_ms"] = round(ms, 3)
+res["c2_trainstep_graph_clips_per_s"] = round(B / ms * 1e3, 1)
 print(json.dumps(res))
