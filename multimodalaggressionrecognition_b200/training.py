@@ -199,7 +199,12 @@ class TrainStep:
         self.sync = GradSync(self.flat, group=group, num_buckets=num_buckets)
         self.use_graph = graph
         self.precision = precision
-        self._sets = [dict(static_in=None, graph=None, static_out=None, done=None) for _ in range(2)]
+        # captured graphs are keyed by the batch SIGNATURE: tensor shapes/dtypes AND the non-tensor leaves (the
+        # per-sample modality / label names whose `_EMPTY` markers steer the model's control flow, datasets.py:564-608)
+        # — a batch with another signature (last batch of an epoch, a verb-only batch) never replays a foreign graph
+        self._graphs = {}
+        self.max_signatures = 3          # further signatures run eagerly (each capture owns its activation pool)
+        self._sets = None                # the two buffer sets of the most recent signature (kept for introspection)
         self._calls = 0
         self._copy_stream = None
         self._warm = 0
@@ -268,10 +273,36 @@ class TrainStep:
             return x
         return walk(batch)
 
+    @staticmethod
+    def _signature(batch):
+        sig = []
+        def walk(x):
+            if isinstance(x, torch.Tensor):
+                sig.append((tuple(x.shape), str(x.dtype)))
+            elif isinstance(x, (list, tuple)) and not (x and isinstance(x[0], str)):
+                sig.append(("[", len(x)))
+                for y in x:
+                    walk(y)
+            elif isinstance(x, (list, tuple)):
+                sig.append(tuple(x))
+            else:
+                sig.append(repr(x))
+        walk(batch)
+        return tuple(sig)
+
     def _graphed(self, data, labels):
         dev = self.flat.flat.device
         src = self._tensors([data, labels])
-        cur = self._sets[self._calls & 1]
+        sig = self._signature([data, labels])
+        state = self._graphs.get(sig)
+        if state is None:
+            if len(self._graphs) >= self.max_signatures:        # too many distinct batch layouts: stay eager for this one
+                return self._eager(self._to_dev(data, dev), self._to_dev(labels, dev))
+            state = {"sets": [dict(static_in=None, graph=None, static_out=None, done=None) for _ in range(2)], "calls": 0}
+            self._graphs[sig] = state
+        self._sets = state["sets"]
+        cur = state["sets"][state["calls"] & 1]
+        state["calls"] += 1
         self._calls += 1
         if cur["static_in"] is None:
             cur["static_in"] = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in src]
@@ -323,10 +354,12 @@ class TrainStep:
         a communicator must not be torn down while graphs that captured its collectives are still alive."""
         if self.flat.flat.is_cuda:
             torch.cuda.synchronize()
-        for s in self._sets:
-            s["graph"] = None
-            s["static_out"] = None
-            s["done"] = None
+        for state in self._graphs.values():
+            for s in state["sets"]:
+                s["graph"] = None
+                s["static_out"] = None
+                s["done"] = None
+        self._graphs = {}
         if self.flat.flat.is_cuda:
             torch.cuda.synchronize()
 

@@ -298,3 +298,37 @@ def test_reference_state_dict_round_trip():
     with torch.no_grad(), mar.precision("fp32"):
         pa, pb = a(batch[0]), b(batch[0])
     assert all(torch.equal(pa[k], pb[k]) for k in pa)
+
+
+def test_train_step_graphs_are_keyed_by_batch_signature():
+    """A graph-captured TrainStep fed a stream of batches whose layout changes (full batch, verb-only batch with the
+    video modality EMPTY, a smaller last batch) must follow the eager TrainStep step for step: a batch never
+    replays a graph captured for another signature (the `_EMPTY` names steer the model's control flow)."""
+    from multimodalaggressionrecognition_b200 import training
+    kw = dict(t_audio=24, t_video=8)
+    batches = {
+        "full": W.batch_c3(B=8, seed=1, **kw),
+        "full2": W.batch_c3(B=8, seed=2, **kw),
+        "verb_only": W.batch_c3(B=8, seed=3, empty="video", **kw),
+        "last": W.batch_c3(B=5, seed=4, **kw),
+    }
+    order = ["full", "full2", "full", "full2", "verb_only", "full", "last", "verb_only", "full2", "last", "verb_only", "full"]
+    curves = {}
+    for graph in (False, True):
+        torch.manual_seed(0)
+        model = W.perturb_norms(W.disable_dropout(W.build_c3(M, **kw))).to(DEV).train()
+        crit = M.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(), "verb": torch.nn.CrossEntropyLoss()})
+        step = training.TrainStep(model, crit, lr=1e-3, graph=graph, precision="fp32")
+        out = []
+        for name in order:
+            data, labels = batches[name]
+            losses = step(W.to_device(data, DEV), W.to_device(labels, DEV))
+            out.append({k: float(v) for k, v in losses.items()})
+        curves[graph] = out
+        if graph:
+            assert len(step._graphs) == 3            # full/full2 share one signature; verb_only and last have their own
+            step.release_graphs()
+    for i, (a, b) in enumerate(zip(curves[False], curves[True])):
+        assert set(a) == set(b), f"step {i} ({order[i]}): heads {set(a)} vs {set(b)}"
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-4 * max(1.0, abs(a[k])), f"step {i} ({order[i]}) loss[{k}]: eager {a[k]} vs graph {b[k]}"
