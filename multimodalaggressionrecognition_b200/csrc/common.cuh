@@ -173,6 +173,14 @@ __device__ __forceinline__ bool drop_keep(const DropKey& k, uint64_t e) {
   uint32_t r16 = (e & 1) ? (r >> 16) : (r & 0xffffu);
   return r16 >= k.thr16;
 }
+// the same two keep flags when the pair index fits 32 bits: (r & 0xffff) >= t  <=>  (r << 16) >= (t << 16) and
+// (r >> 16) >= t  <=>  r >= (t << 16), so the mask is bit-identical to drop_keep2 with 6 instructions less per pair
+__device__ __forceinline__ void drop_keep2_32(const DropKey& k, uint32_t pair_index, bool& k0, bool& k1) {
+  const uint32_t r = lowbias32(pair_index ^ k.key);
+  const uint32_t thr_hi = k.thr16 << 16;
+  k0 = (r << 16) >= thr_hi;
+  k1 = r >= thr_hi;
+}
 // keep flags of the pair (2*pair, 2*pair+1)
 __device__ __forceinline__ void drop_keep2(const DropKey& k, uint64_t pair_index, bool& k0, bool& k1) {
   uint32_t r = drop_rand_pair(k, pair_index);

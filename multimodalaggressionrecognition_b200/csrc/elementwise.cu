@@ -31,6 +31,7 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
   DropKey dk;
   if (drop) dk = make_drop_key(rng, site, p);
   const float scale = drop ? dk.scale : 1.f;
+  const bool idx32 = ((uint64_t)M * (uint64_t)N >> 1) < 0xffffffffull;     // every pair index fits 32 bits
   float csum[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; j++) csum[j] = 0.f;
@@ -76,8 +77,9 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
           } else if (drop) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-              bool k0, k1;
-              drop_keep2(dk, (uint64_t)(e0 >> 1) + j, k0, k1);      // N % 8 == 0 and c0 % 8 == 0: e0 is even
+              bool k0, k1;                                           // N % 8 == 0 and c0 % 8 == 0: e0 is even
+              if (idx32) drop_keep2_32(dk, (uint32_t)(e0 >> 1) + (uint32_t)j, k0, k1);
+              else drop_keep2(dk, (uint64_t)(e0 >> 1) + j, k0, k1);
               g[2 * j] = k0 ? g[2 * j] * scale : 0.f;
               g[2 * j + 1] = k1 ? g[2 * j + 1] * scale : 0.f;
             }

@@ -195,6 +195,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int ew = warp - 4;                // epilogue warp index
     const int half = ew >> 2;               // column half of the tile
     const bool do_drop = (p.flags & MAR_EPI_DROPOUT) && p.p_drop > 0.f;
+    const bool idx32 = ((uint64_t)(p.M + BLOCK_M) * (uint64_t)p.N >> 1) < 0xffffffffull;   // incl. the rows of a ragged last tile
     DropKey dk;
     if (do_drop) dk = make_drop_key(p.rng, p.site, p.p_drop);
     uint8_t* box = smem_e + ew * EPI_BOX_BYTES;
@@ -257,12 +258,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         if (do_drop) {
           const uint64_t e0 = (uint64_t)row * (uint64_t)p.N + (uint64_t)col0;
+          if (idx32) {                       // every pair index of this launch fits 32 bits (warp-uniform)
+            const uint32_t p0 = (uint32_t)(e0 >> 1);
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            bool k0, k1;
-            drop_keep2(dk, (e0 >> 1) + j, k0, k1);
-            v[2 * j] = k0 ? v[2 * j] * dk.scale : 0.f;
-            v[2 * j + 1] = k1 ? v[2 * j + 1] * dk.scale : 0.f;
+            for (int j = 0; j < 16; j++) {
+              bool k0, k1;
+              drop_keep2_32(dk, p0 + (uint32_t)j, k0, k1);
+              v[2 * j] = k0 ? v[2 * j] * dk.scale : 0.f;
+              v[2 * j + 1] = k1 ? v[2 * j + 1] * dk.scale : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              bool k0, k1;
+              drop_keep2(dk, (e0 >> 1) + j, k0, k1);
+              v[2 * j] = k0 ? v[2 * j] * dk.scale : 0.f;
+              v[2 * j + 1] = k1 ? v[2 * j + 1] * dk.scale : 0.f;
+            }
           }
         }
         if (p.flags & MAR_EPI_RELU_POST) {
