@@ -46,7 +46,8 @@ struct FwdParams {
   uint32_t site;
 };
 
-template <int DH>
+// DROP: 0 = no dropout, 1 = dropout with 64-bit pair indices, 2 = dropout, every pair index of the launch fits 32 bits
+template <int DH, int DROP>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
   constexpr int NBOX = (DH + 63) / 64;
@@ -158,7 +159,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
     const int q = qt * BQ + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float scale2 = rsqrtf((float)DH) * LOG2E;
-    const bool drop = p.p_drop > 0.f;
+    constexpr bool drop = DROP != 0;                        // compile-time: the hash is not even compiled into the p = 0 kernel
     DropKey dk;
     dk.key = 0; dk.thr16 = 0; dk.scale = 1.f;
     if (drop) dk = make_drop_key(p.rng, p.site, p.p_drop);
@@ -235,7 +236,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
 #pragma unroll
           for (int i = 0; i < 16; i++) {
             bool k0, k1;
-            drop_keep2(dk, pair0 + (uint64_t)i, k0, k1);
+            if (DROP == 2) drop_keep2_32(dk, (uint32_t)pair0 + (uint32_t)i, k0, k1);
+            else drop_keep2(dk, pair0 + (uint64_t)i, k0, k1);
             pk[i] = pack_bf16x2(k0 ? pv[2 * i] * dk.scale : 0.f, k1 ? pv[2 * i + 1] * dk.scale : 0.f);
           }
         } else {
@@ -290,7 +292,9 @@ int fwd_launch(const void* qkv, const uint8_t* key_mask, void* out, float* lse, 
   constexpr int SMEM = 3 * NBOX * BOX_BYTES + MAX_KV_TILES * 16 + 64 + 1024;
   static bool cfg = false;
   if (!cfg) {
-    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     cfg = true;
   }
   CUtensorMap tm;
@@ -300,7 +304,12 @@ int fwd_launch(const void* qkv, const uint8_t* key_mask, void* out, float* lse, 
   prm.key_mask = key_mask; prm.out = (bf16*)out; prm.lse = lse; prm.B = (int)B; prm.T = (int)T; prm.H = (int)H;
   prm.p_drop = p; prm.rng = rng; prm.site = site;
   const int64_t q_tiles = ceil_div(T, BQ);
-  attn_fwd_tc_kernel<DH><<<(unsigned)(B * H * q_tiles), 192, SMEM, st>>>(tm, prm);
+  const int64_t Tp = (T + 1) & ~(int64_t)1;
+  const bool idx32 = (B * H * T + 128) * Tp / 2 + T < (int64_t)0xffffffffll;      // largest pair index any thread forms
+  const unsigned grid = (unsigned)(B * H * q_tiles);
+  if (p > 0.f && idx32) attn_fwd_tc_kernel<DH, 2><<<grid, 192, SMEM, st>>>(tm, prm);
+  else if (p > 0.f) attn_fwd_tc_kernel<DH, 1><<<grid, 192, SMEM, st>>>(tm, prm);
+  else attn_fwd_tc_kernel<DH, 0><<<grid, 192, SMEM, st>>>(tm, prm);
   MAR_LAUNCH_CHECK("attn_fwd_tc");
   return MAR_OK;
 }
