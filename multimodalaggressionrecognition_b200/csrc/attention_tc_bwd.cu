@@ -85,8 +85,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// IDX32: every dropout pair index of the launch fits 32 bits (true for all the reference's shapes)
-template <int DH, bool IDX32>
+// DROP: 0 = no dropout (the mask hash is not compiled in), 1 = dropout with 64-bit pair indices, 2 = dropout and
+// every pair index of the launch fits 32 bits (true for all the reference's shapes)
+template <int DH, int DROP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dq, const BwdParams p) {
@@ -280,7 +281,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
     const bool kvalid = key < T && !(p.key_mask != nullptr && p.key_mask[(int64_t)b * T + key] != 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float scale = rsqrtf((float)DH), scale2 = scale * LOG2E;
-    const bool drop = p.p_drop > 0.f;
+    constexpr bool drop = DROP != 0;
+    constexpr bool IDX32 = DROP == 2;
     DropKey dk;
     dk.key = 0; dk.thr16 = 0; dk.scale = 1.f;
     if (drop) dk = make_drop_key(p.rng, p.site, p.p_drop);
@@ -504,7 +506,7 @@ attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, i
   }
 }
 
-template <int DH, bool IDX32>
+template <int DH, int DROP>
 int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
                void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
   constexpr int NBOX = (DH + 63) / 64;
@@ -515,7 +517,7 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
   static_assert(SMEM <= 232448, "attention backward: shared memory budget");
   static bool cfg = false;
   if (!cfg) {
-    MAR_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, IDX32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     cfg = true;
   }
   const int64_t d = H * DH;
@@ -545,7 +547,7 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
   prm.key_mask = key_mask; prm.lse = lse; prm.delta = delta; prm.dq_acc = dq_acc; prm.dqkv = (bf16*)dqkv;
   prm.B = (int)B; prm.T = (int)T; prm.H = (int)H; prm.p_drop = p; prm.rng = rng; prm.site = site; prm.smem_bytes = SMEM;
   const int64_t n_t = ceil_div(T, BT);
-  attn_bwd_tc_kernel<DH, IDX32><<<(unsigned)(B * H * n_t), NTHREADS, SMEM, st>>>(tm_kv, tm_q, tm_do, tm_dq, prm);
+  attn_bwd_tc_kernel<DH, DROP><<<(unsigned)(B * H * n_t), NTHREADS, SMEM, st>>>(tm_kv, tm_q, tm_do, tm_dq, prm);
   MAR_LAUNCH_CHECK("attn_bwd_tc");
   if (dq_acc != nullptr) {
     const int64_t n = B * T * (d / 8);
@@ -561,8 +563,9 @@ int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const 
                void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
   const int64_t Tp = (T + 1) & ~(int64_t)1;
   const bool idx32 = (B * H * T + 64) * Tp / 2 + T < (int64_t)0xffffffffll;      // largest pair index any thread forms
-  return idx32 ? bwd_launch_t<DH, true>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st)
-               : bwd_launch_t<DH, false>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st);
+  if (p <= 0.f) return bwd_launch_t<DH, 0>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st);
+  return idx32 ? bwd_launch_t<DH, 2>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st)
+               : bwd_launch_t<DH, 1>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st);
 }
 
 }  // namespace
