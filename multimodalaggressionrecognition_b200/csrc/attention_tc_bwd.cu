@@ -44,8 +44,7 @@ constexpr int BQ = 64;                  // queries per step
 constexpr int NCOMPUTE = 16;            // compute warps
 constexpr int NREAD = 4;                // dQᵀ read-out warps
 constexpr int NTHREADS = (2 + NCOMPUTE + NREAD) * 32;
-constexpr int QSTAGES = 4;              // Q / dO smem ring: tile i+4 is requested when tile i retires, two tile periods ahead of its use
-                                        // (with 3 stages the TMA round trip was exposed: compute warps waited 60 % of the time for Sᵀ)
+constexpr int QSTAGES = 3;              // Q / dO smem ring (a 4th stage bought nothing: the TMA round trip is not what the walk waits for)
 constexpr int LSTAGES = 4;              // LSE / delta smem ring
 constexpr int QBOX_BYTES = BQ * 128;    // one 64-row x 64-column box
 
@@ -107,9 +106,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
   uint8_t* sV = sK + KV_BYTES;
   uint8_t* sQ = sV + KV_BYTES;                  // [QSTAGES][Q_BYTES]
   uint8_t* sDO = sQ + QSTAGES * Q_BYTES;        // [QSTAGES][Q_BYTES]
-  uint8_t* sDS = sDO + QSTAGES * Q_BYTES;       // [DS_BYTES] (single: rewritten only after the dQᵀ MMA that read it)
+  uint8_t* sDS = sDO + QSTAGES * Q_BYTES;       // [2][DS_BYTES]: tile i+1 is written while the dQᵀ MMA of tile i still reads
   constexpr int DQ_ROWS = DH <= 96 ? 32 : 16;        // query rows per TMA reduce (staging size is what is left of 227 KB)
-  float* sDQ = reinterpret_cast<float*>(sDS + DS_BYTES);   // [DQ_ROWS][DH] fp32 staging of a dQ block
+  float* sDQ = reinterpret_cast<float*>(sDS + 2 * DS_BYTES);   // [DQ_ROWS][DH] fp32 staging of a dQ block
   float* sL = sDQ + DQ_ROWS * DH;   // [LSTAGES][64] LSE in log2 units (+inf = no contribution)
   float* sD = sL + LSTAGES * BQ;                              // [LSTAGES][64] delta
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + LSTAGES * BQ);
@@ -241,7 +240,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
 #pragma unroll 1
         for (int ks = 0; ks < ksteps_keys; ks++)
           umma_f16(tmem_base + COL_DQ, make_desc_mnmajor(sK_a, ks, BOX_BYTES),
-                   make_desc_mnmajor(sDS_a, ks, DS_BYTES), idesc_dq, ks > 0 ? 1u : 0u);
+                   make_desc_mnmajor(sDS_a + (i & 1) * DS_BYTES, ks, DS_BYTES), idesc_dq, ks > 0 ? 1u : 0u);
         umma_commit(bar_mma2);
         if (i == n_q - 1) umma_commit(bar_done);
       }
@@ -358,8 +357,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
       if (active) {
         tmem_st_32x32b_x8(col + chunk * 8, pk);
         tmem_st_32x32b_x8(col + 64 + chunk * 8, dsk);
-        if (i > 0) mbar_wait(bar_mma2, (i - 1) & 1);     // the dQᵀ MMA of the previous tile has finished reading dSᵀ
-        const uint32_t dsb = smem_u32(sDS);
+        const uint32_t dsb = smem_u32(sDS + (i & 1) * DS_BYTES);
         sts128(dsb + ds_off0, dsk[0], dsk[1], dsk[2], dsk[3]);
         sts128(dsb + ds_off1, dsk[4], dsk[5], dsk[6], dsk[7]);
         tmem_st_wait();
@@ -510,7 +508,7 @@ template <int DH, int DROP>
 int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
                void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
   constexpr int NBOX = (DH + 63) / 64;
-  constexpr int USED = 2 * NBOX * BOX_BYTES + 2 * QSTAGES * NBOX * QBOX_BYTES + BT * 128 + (DH <= 96 ? 32 : 16) * DH * 4 +
+  constexpr int USED = 2 * NBOX * BOX_BYTES + 2 * QSTAGES * NBOX * QBOX_BYTES + 2 * BT * 128 + (DH <= 96 ? 32 : 16) * DH * 4 +
                        2 * LSTAGES * BQ * 4 + 20 * 8 + 16;
   static_assert(USED + 1024 <= 232448, "attention backward: shared memory budget");
   constexpr int SMEM = USED + 1024;
