@@ -14,6 +14,9 @@ Parity pinning: the reference ships no golden vectors.  The ora
 against the LIVE reference classes imported from /root/reference in the build container by
 `oracle/make_golden.py`, which also writes the fixtures under `tests/golden/`; `tests/
 test_oracle_golden.py` re-checks the oracle against those fixtures on any machine.
+Exception — PARITY UNPINNED: `focal_loss` restates the torch.hub criterion of train_multimodal.py:494-510
+(adeelh/pytorch-multi-class-focal-loss, default branch, not vendored, no network here) from its published
+algorithm; it is checked against the same formula written with torch's log_softmax / nll_loss only.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py` (its `cpu_baseline` leg and
 `--impl reference`) may import this module.  The product package never does.
