@@ -102,54 +102,64 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer + MMA issuer
-      auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col0, int row0) {
+    // ---------------------------------------------------------------- TMA producer + MMA issuer
+    // The whole warp walks this code converged and waits on the mbarriers together; one elected lane issues the TMA
+    // and tcgen05 instructions, so every operand is warp-uniform (a one-lane branch makes ptxas wrap each MMA in a
+    // per-lane operand-marshalling loop: ~20 instructions per issue, as long as a 128x128x16 MMA runs).
+    auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col0, int row0) {
+      if (elect_one()) {
         mbar_expect_tx(bar, OP_BYTES);
 #pragma unroll
         for (int bx = 0; bx < NBOX; bx++) tma_load_3d(dst + bx * BOX_BYTES, &tm_qkv, bar, col0 + bx * 64, row0, b);
-      };
-      auto issue_s = [&](int j) {
-        const int nk = min(BKV, T - j * BKV);
-        const uint32_t idesc = make_idesc_bf16(BQ, (nk + 15) & ~15, 0, 0);
+      }
+      __syncwarp();
+    };
+    const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+    auto issue_s = [&](int j) {
+      const int nk = min(BKV, T - j * BKV);
+      const uint32_t idesc = make_idesc_bf16(BQ, (nk + 15) & ~15, 0, 0);
+      if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < KSTEPS; ks++) {
-          const uint32_t qa = smem_u32(sQ + (ks / 4) * BOX_BYTES), ka = smem_u32(sK + (ks / 4) * BOX_BYTES);
-          umma_f16(tmem_base + COL_S, make_desc_kmajor(qa, ks % 4), make_desc_kmajor(ka, ks % 4), idesc, ks > 0 ? 1u : 0u);
-        }
+        for (int ks = 0; ks < KSTEPS; ks++)
+          umma_f16(tmem_base + COL_S, make_desc_kmajor(sQ_a + (ks / 4) * BOX_BYTES, ks % 4),
+                   make_desc_kmajor(sK_a + (ks / 4) * BOX_BYTES, ks % 4), idesc, ks > 0 ? 1u : 0u);
         umma_commit(bar_s);
-      };
-      load_tile(sQ, bar_q, h * DH, qt * BQ);
-      load_tile(sK, bar_k, d + h * DH, 0);
-      load_tile(sV, bar_v, 2 * d + h * DH, 0);
-      mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, 0);
+      }
+      __syncwarp();
+    };
+    load_tile(sQ, bar_q, h * DH, qt * BQ);
+    load_tile(sK, bar_k, d + h * DH, 0);
+    load_tile(sV, bar_v, 2 * d + h * DH, 0);
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_k, 0);
+    tc_fence_after();
+    issue_s(0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 0, 1);
+    for (int j = 0; j < n_kv; j++) {
+      const uint32_t ph = j & 1;
+      if (j + 1 < n_kv) {                 // K tile is free once S_j is complete
+        mbar_wait(bar_s, ph);
+        load_tile(sK, bar_k, d + h * DH, (j + 1) * BKV);
+      }
+      mbar_wait(bar_p, ph);
+      mbar_wait(bar_v, ph);
       tc_fence_after();
-      issue_s(0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 0, 1);
-      for (int j = 0; j < n_kv; j++) {
-        const uint32_t ph = j & 1;
-        if (j + 1 < n_kv) {                 // K tile is free once S_j is complete
-          mbar_wait(bar_s, ph);
-          load_tile(sK, bar_k, d + h * DH, (j + 1) * BKV);
-        }
-        mbar_wait(bar_p, ph);
-        mbar_wait(bar_v, ph);
-        tc_fence_after();
-        const int nk = min(BKV, T - j * BKV);
-        const int pv_steps = (nk + 15) / 16;
-        const uint32_t va = smem_u32(sV);
+      const int nk = min(BKV, T - j * BKV);
+      const int pv_steps = (nk + 15) / 16;
+      if (elect_one()) {
+#pragma unroll 1
         for (int ks = 0; ks < pv_steps; ks++)
-          umma_f16_ts(tmem_base + COL_O, tmem_base + COL_P + ks * 8, make_desc_mnmajor(va, ks, BOX_BYTES), idesc_pv,
+          umma_f16_ts(tmem_base + COL_O, tmem_base + COL_P + ks * 8, make_desc_mnmajor(sV_a, ks, BOX_BYTES), idesc_pv,
                       (j > 0 || ks > 0) ? 1u : 0u);
         umma_commit(bar_pv);
-        if (j + 1 < n_kv) {
-          mbar_wait(bar_k, ph ^ 1);
-          tc_fence_after();
-          issue_s(j + 1);                   // executes after P̃·V_j (in-order tensor pipe): S may overwrite P̃_j
-          mbar_wait(bar_pv, ph);            // V tile free
-          load_tile(sV, bar_v, 2 * d + h * DH, (j + 1) * BKV);
-        }
+      }
+      __syncwarp();
+      if (j + 1 < n_kv) {
+        mbar_wait(bar_k, ph ^ 1);
+        tc_fence_after();
+        issue_s(j + 1);                   // executes after P̃·V_j (in-order tensor pipe): S may overwrite P̃_j
+        mbar_wait(bar_pv, ph);            // V tile free
+        load_tile(sV, bar_v, 2 * d + h * DH, (j + 1) * BKV);
       }
     }
   } else if (warp >= 2) {
