@@ -298,7 +298,7 @@ class TrainStep:
         if state is None:
             if len(self._graphs) >= self.max_signatures:        # too many distinct batch layouts: stay eager for this one
                 return self._eager(self._to_dev(data, dev), self._to_dev(labels, dev))
-            state = {"sets": [dict(static_in=None, graph=None, static_out=None, done=None) for _ in range(2)], "calls": 0}
+            state = {"sets": [dict(static_in=None, graph=None, static_out=None, static_pred=None, done=None) for _ in range(2)], "calls": 0}
             self._graphs[sig] = state
         self._sets = state["sets"]
         cur = state["sets"][state["calls"] & 1]
@@ -339,8 +339,10 @@ class TrainStep:
             with torch.cuda.graph(g):
                 cur["static_out"] = self._eager(sdata, slabels)
             self.captured_launches = ops.launch_count() - before   # libmar kernels per replay
+            cur["static_pred"] = self.last_pred     # this graph's own logits buffers
             cur["graph"] = g                        # capture records but does not execute: fall through to replay
         cur["graph"].replay()
+        self.last_pred = cur["static_pred"]         # valid until this buffer set's next replay (two steps later)
         if cur["done"] is None:
             cur["done"] = torch.cuda.Event()
         cur["done"].record(main)
@@ -358,10 +360,126 @@ class TrainStep:
             for s in state["sets"]:
                 s["graph"] = None
                 s["static_out"] = None
+                s["static_pred"] = None
                 s["done"] = None
         self._graphs = {}
         if self.flat.flat.is_cuda:
             torch.cuda.synchronize()
+
+
+class EpochAccumulator:
+    """The reference trainers' per-epoch bookkeeping without their per-step host reads.
+
+    `TorchSupervisedTrainer.train_step` / `.test_step` end every step with `loss.item()` per head
+    (`compute_batch_loss`, trainer.py:175-177, :731-737) and `torch.max(pred, 1)[1].cpu().numpy()` per head
+    (`nn_output_processing`, trainer.py:165-171, :718-729) plus the labels' `.cpu()` (`create_batch_results_dict`,
+    trainer.py:179, :888-914): 2 x heads + 1 blocking device->host reads per step.  Here `add()` only enqueues
+    device work (a multiply-add into a running loss sum per head, an argmax kernel, references to the label
+    tensors); `results()` does ONE device->host transfer per epoch and then builds exactly the dictionary
+    `compute_epoch_results` returns (trainer.py:237-283 single model, :739-812 multi-head `RNN_trainer`,
+    :916-1007 `MultimodalTrainer`):  {head: {'loss': sum_steps(loss x size) / dataset_size, metric: value, ...}}.
+
+    Kept verbatim from the reference: `size` is `len(data[0])` for list inputs and `len(data)` otherwise
+    (trainer.py:155-158) - for the multimodal layout `data[0]` is the `[names, tensor]` pair, so size is 2, not the
+    batch size; label groups / heads whose samples are all `_EMPTY` are dropped from that step's losses and
+    predictions, partially-EMPTY groups keep only their present rows (trainer.py:893-912); metrics are called as
+    `metric(true, pred, **kwargs)` with `metrics_dict` entries being either a callable or
+    `{'metric': f, 'kwargs': {...}}`, and any entry named 'loss' (case-insensitive) is skipped."""
+
+    def __init__(self, metrics_dict: Optional[Dict] = None):
+        self.metrics_dict = dict(metrics_dict or {})
+        self.reset()
+
+    def reset(self) -> None:
+        self._loss: Dict[str, torch.Tensor] = {}     # head -> running sum on the device
+        self._pred: Dict[str, List[torch.Tensor]] = {}
+        self._true: Dict[str, List[torch.Tensor]] = {}
+        self._keep: Dict[str, List] = {}             # head -> per step: None (all rows) or a host bool array
+        self._flat = False                           # single-output trainer: results() returns {'loss':…, metric:…}
+        self.steps = 0
+
+    @staticmethod
+    def batch_size_as_reference(data) -> int:
+        """trainer.py:155-158."""
+        return len(data[0]) if isinstance(data, list) else len(data)
+
+    @staticmethod
+    def _argmax(logits: torch.Tensor) -> torch.Tensor:
+        if logits.is_cuda:
+            return ops.argmax_rows(logits.detach())
+        return logits.detach().argmax(dim=1)          # host-side logic tests (no GPU)
+
+    def add(self, losses, pred, labels, data=None, size: Optional[int] = None) -> None:
+        """One step's results; nothing here waits for the device.  `losses`: {head: 0-d tensor} (or a tensor),
+        `pred`: {head: (B,C) logits} (or a tensor), `labels`: (B,) tensor or the multimodal `[[names, y], ...]`."""
+        if size is None:
+            size = self.batch_size_as_reference(data) if data is not None else 1
+        self._flat = isinstance(pred, torch.Tensor)
+        losses = {"loss": losses} if isinstance(losses, torch.Tensor) else losses
+        pred = {"loss": pred} if isinstance(pred, torch.Tensor) else pred
+        heads, true, keep = list(pred.keys()), {}, {}
+        if isinstance(labels, torch.Tensor):
+            for h in heads:                            # every head is scored against the same labels (trainer.py:739-812)
+                true[h], keep[h] = labels, None
+        else:
+            present_heads = []
+            for names, y in labels:
+                head = names[0].split('_')[0]
+                present = [n.split('_')[-1] != 'EMPTY' for n in names]
+                if head in pred and any(present):
+                    present_heads.append(head)
+                    true[head] = y
+                    keep[head] = None if all(present) else present
+            heads = [h for h in heads if h in present_heads]
+        for h in heads:
+            if h in losses:
+                term = losses[h].detach().float() * float(size)
+                self._loss[h] = term if h not in self._loss else self._loss[h] + term
+            self._pred.setdefault(h, []).append(self._argmax(pred[h]))
+            self._true.setdefault(h, []).append(true[h].detach().clone())     # the caller may reuse its label buffers
+            self._keep.setdefault(h, []).append(keep[h])
+        self.steps += 1
+
+    def results(self, dataset_size: int) -> Dict[str, Dict]:
+        """ONE device->host transfer, then the reference's epoch dictionary."""
+        import numpy as np
+        heads = list(self._pred.keys())
+        if not heads:
+            return {}
+        dev = self._pred[heads[0]][0].device
+        parts, layout = [], []
+        for h in heads:
+            p = torch.cat(self._pred[h]).to(torch.int64)
+            t = torch.cat([x.to(dev) for x in self._true[h]]).to(torch.int64)
+            parts += [p, t]
+            layout.append((h, p.numel()))
+        loss_heads = [h for h in heads if h in self._loss]
+        packed = torch.cat(parts).double()
+        if loss_heads:
+            packed = torch.cat([packed, torch.stack([self._loss[h].double() for h in loss_heads])])
+        host = packed.cpu().numpy()                    # the epoch's only synchronisation
+        out, off = {}, 0
+        for h, n in layout:
+            p = host[off:off + n].astype(np.int64)
+            t = host[off + n:off + 2 * n].astype(np.int64)
+            off += 2 * n
+            if any(k is not None for k in self._keep[h]):
+                rows = np.concatenate([np.ones(x.numel(), dtype=bool) if k is None else np.asarray(k, dtype=bool)
+                                       for x, k in zip(self._pred[h], self._keep[h])])
+                p, t = p[rows], t[rows]
+            out[h] = {"pred": p, "true": t}
+        log = {}
+        for i, h in enumerate(loss_heads):
+            log[h] = {"loss": float(host[off + i]) / dataset_size}
+        for h in heads:
+            entry = log.setdefault(h, {})
+            for name, metric in self.metrics_dict.items():
+                if name.lower() == "loss":
+                    continue
+                fn, kw = (metric["metric"], metric["kwargs"]) if type(metric) is dict else (metric, {})
+                entry[name] = fn(out[h]["true"], out[h]["pred"], **kw)
+        self.last_arrays = out
+        return log["loss"] if self._flat else log
 
 
 class _null:

@@ -52,6 +52,54 @@ def c3_oracle_cfg(t_audio: int = 250, t_video: int = 64, d: int = 768, heads: in
     }
 
 
+def build_c3x(ns, modalities: Tuple[str, ...] = ("audio", "video"), fusion: str = "equal", classifier: str = "concat",
+              top: str = "physverb", t_audio: int = 250, t_video: int = 64, t_text: int = 48, d: int = 768,
+              d_video_in: int = 512, heads: int = 8, classes: int = 2) -> nn.Module:
+    """The other assemblies train_multimodal.py can build: any subset of
+    audio / text / video (text enters through `nn.Sequential()`, zero-padded RuBERT tokens, train_multimodal.py:365),
+    `EqualSizedTransformerModalitiesFusion` or `AveragedFeaturesTransformerFusion` (:374-375),
+    `PhysVerbClassifierConcatFeatures` or the base `PhysVerbClassifier` (:406-411), under `PhysVerbModel` or
+    the older `MultimodalModel` with one `OutputClassifier` per modality (:425-443)."""
+    makers = {
+        'audio': lambda: ns.TransformerSequenceProcessor(nn.Sequential(), d, 1, heads, classes),
+        'text': lambda: nn.Sequential(),
+        'video': lambda: ns.TransformerSequenceProcessor(ns.EmbeddingLayer(d_video_in, d), d, 1, heads, classes),
+    }
+    shapes = {'audio': [t_audio, d], 'text': [t_text, d], 'video': [t_video, d]}
+    extractors = nn.ModuleDict({m: makers[m]() for m in ('audio', 'text', 'video') if m in modalities})
+    fusion_cls = {"equal": ns.EqualSizedTransformerModalitiesFusion, "avg": ns.AveragedFeaturesTransformerFusion}[fusion]
+    fusion_module = fusion_cls(1, d, heads)
+    shapes = {m: s for m, s in shapes.items() if m in modalities}
+    if top == "old":
+        heads_dict = nn.ModuleDict({m: ns.OutputClassifier(d, classes) for m in ('audio', 'text', 'video') if m in modalities})
+        return ns.MultimodalModel(extractors, fusion_module, heads_dict, shapes, d, classes)
+    clf_cls = {"concat": ns.PhysVerbClassifierConcatFeatures, "base": ns.PhysVerbClassifier}[classifier]
+    classifiers = clf_cls(list(modalities), classes, {'video': [d, d], 'audio': [d, d], 'text': [d, d]}, dict(MODALITY2AGGR))
+    return ns.PhysVerbModel(extractors, fusion_module, classifiers, shapes, dict(MODALITY2AGGR), d, classes)
+
+
+def c3x_oracle_cfg(modalities=("audio", "video"), fusion: str = "equal", classifier: str = "concat", top: str = "physverb",
+                   t_audio: int = 250, t_video: int = 64, t_text: int = 48, d: int = 768, heads: int = 8, **_) -> dict:
+    ex = {'audio': {"layers": 1, "heads": heads, "extractor": "identity"},
+          'text': {"layers": 0, "heads": heads, "extractor": "identity"},      # nn.Sequential(): tokens pass through
+          'video': {"layers": 1, "heads": heads, "extractor": "embedding"}}
+    shapes = {'audio': [t_audio, d], 'text': [t_text, d], 'video': [t_video, d]}
+    aggr = ['phys', 'verb']        # ConcatFeatures builds a head per value of modality2aggr, whatever the modalities
+    return {
+        "feature_shapes": {m: shapes[m] for m in modalities}, "extractors": {m: ex[m] for m in modalities},
+        "fusion_layers": 1, "fusion_heads": heads, "aggr_types": aggr, "fusion": fusion, "classifier": classifier,
+        "top": top, "modality2aggr": dict(MODALITY2AGGR),
+    }
+
+
+def build_audio_text(ns, d: int = 768, heads: int = 8, classes: int = 2, text_layers: int = 2) -> nn.Module:
+    """AudioTextualModel (models.py:889-928) as train_audio_text.py:158-178 assembles it, with the audio branch's
+    out-of-scope CNN front end replaced by pre-computed d-wide features."""
+    audio = ns.TransformerSequenceProcessor(nn.Sequential(), d, 1, heads, classes)
+    text = ns.TransformerSequenceProcessor(nn.Sequential(), d, text_layers, heads, classes)
+    return ns.AudioTextualModel(audio, text, d, classes)
+
+
 def disable_dropout(model: nn.Module) -> nn.Module:
     """Exact-parity recipe: every nn.Dropout.p = 0 and every self_attn.dropout = 0."""
     for m in model.modules():
@@ -89,6 +137,15 @@ def batch_c1(B: int = 32, T: int = 250, d: int = 768, seed: int = 1000):
     return torch.randn(B, T, d, generator=g), torch.randint(0, 2, (B,), generator=g)
 
 
+def batch_c1_learnable(B: int = 32, T: int = 250, d: int = 768, seed: int = 1000, shift: float = 0.06):
+    """`batch_c1` with a label the model can learn (the first 32 feature columns are shifted by ±shift according to
+    the label), so that a loss curve over an epoch goes somewhere and the trained model's predictions differ
+    between clips."""
+    x, y = batch_c1(B, T, d, seed)
+    x[:, :, :32] += shift * (2.0 * y.float() - 1.0)[:, None, None]
+    return x, y
+
+
 def batch_c2(B: int = 64, T: int = 64, d: int = 512, seed: int = 1000):
     g = _gen(seed)
     return torch.randn(B, T, d, generator=g), torch.randint(0, 2, (B,), generator=g)
@@ -116,6 +173,52 @@ def batch_c3(B: int = 256, t_audio: int = 250, t_video: int = 64, d_audio: int =
     data = [[(a_name,) * B, audio], [(v_name,) * B, video]]
     labels = [[(verb_name,) * B, y_verb], [(phys_name,) * B, y_phys]]
     return data, labels
+
+
+def _ragged_zero_pad(x: torch.Tensor, g: torch.Generator, min_len: int = 1) -> torch.Tensor:
+    """AppendZeroValues (datasets.py:212-231): every sample keeps a random number of leading tokens, the rest is 0."""
+    B, T, _ = x.shape
+    lens = torch.randint(min_len, T + 1, (B,), generator=g)
+    lens[0] = T                                   # at least one full-length sample
+    x = x.clone()
+    for i in range(B):
+        x[i, int(lens[i]):] = 0.0
+    return x
+
+
+def batch_c3x(B: int = 8, modalities=("audio", "video"), t_audio: int = 250, t_video: int = 64, t_text: int = 48,
+              d_audio: int = 768, d_video: int = 512, d_text: int = 768, seed: int = 1000, empty: Optional[str] = None,
+              ragged_text: bool = True, flat_labels: bool = False, **_):
+    """`batch_c3` for any modality subset; text tokens are zero-padded to `t_text` with per-sample lengths (the
+    real key-padding masks of the fusion encoder).  flat_labels → `(B,)` labels for the
+    older MultimodalModel + MultiCrossEntropyLoss."""
+    g = _gen(seed)
+    shapes = {'audio': (t_audio, d_audio), 'text': (t_text, d_text), 'video': (t_video, d_video)}
+    data = []
+    for m in modalities:
+        x = torch.randn(B, *shapes[m], generator=g)
+        if m == 'text' and ragged_text:
+            x = _ragged_zero_pad(x, g)
+        name = m
+        if empty == m:
+            x = torch.full_like(x, -1.0); name = m + '_EMPTY'
+        data.append([(name,) * B, x])
+    y_verb = torch.randint(0, 2, (B,), generator=g)
+    y_phys = torch.randint(0, 2, (B,), generator=g)
+    if flat_labels:
+        return data, y_verb
+    verb_name, phys_name = 'verb', 'phys'
+    if empty == 'video':
+        y_phys = torch.full_like(y_phys, -1); phys_name = 'phys_EMPTY'
+    return data, [[(verb_name,) * B, y_verb], [(phys_name,) * B, y_phys]]
+
+
+def batch_audio_text(B: int = 4, t_audio: int = 50, t_text: int = 48, d: int = 768, seed: int = 1000):
+    """train_audio_text.py batches: [[('audio',)*B, (B,T_a,d)], [('text',)*B, (B,T_t,d) zero-padded]], labels (B,)."""
+    g = _gen(seed)
+    audio = torch.randn(B, t_audio, d, generator=g)
+    text = _ragged_zero_pad(torch.randn(B, t_text, d, generator=g), g)
+    return [[('audio',) * B, audio], [('text',) * B, text]], torch.randint(0, 2, (B,), generator=g)
 
 
 def to_device(batch, device):

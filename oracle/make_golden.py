@@ -2,6 +2,11 @@
 build container only) and pin the CPU oracle against them.
 
     python oracle/make_golden.py            # writes tests/golden/golden_v1.pt, asserts oracle == reference
+    python oracle/make_golden.py v2         # writes tests/golden/golden_v2.pt: the script's other assemblies (text
+                                            # branch with ragged zero padding, averaged fusion, base classifier heads,
+                                            # the older MultimodalModel, AudioTextualModel, class-weighted CE)
+    python oracle/make_golden.py c1_epoch   # writes tests/golden/golden_c1_epoch.pt: BASELINE config 1 at full size,
+                                            # "1 epoch" = 48 Adam steps over 48 different batches (loss curve, predictions)
 
 Each case stores: the builder name + kwargs, the init seed (weights are re-created from the seed: the
 drop-in and the reference construct identical torch.nn containers in identical order), a checksum of
@@ -25,6 +30,7 @@ import models as ref  # noqa: E402  the reference
 
 from multimodalaggressionrecognition_b200 import workloads as W  # noqa: E402
 from oracle import oracle as O  # noqa: E402
+from tests import helpers as H  # noqa: E402  (spec -> oracle call / reference-facing loss call, shared with the tests)
 
 torch.set_num_threads(8)
 O.DROPOUT_ENABLED = False   # the reference side runs with every dropout p = 0
@@ -43,6 +49,28 @@ CASES = {
     "c3_audio_padded": dict(builder="build_c3", bkw=dict(t_audio=50, t_video=16), batch="batch_c3",
                             dkw=dict(B=4, t_audio=50, t_video=16, zero_pad_audio=13)),
 }
+_S = dict(t_audio=40, t_video=12, t_text=10)
+CASES_V2 = {
+    # audio + text: the text tokens are zero-padded per sample -> ragged, left-aligned key-padding mask (nested eval path)
+    "c3x_audio_text_ragged": dict(builder="build_c3x", bkw=dict(modalities=("audio", "text"), **_S),
+                                  batch="batch_c3x", dkw=dict(B=5, modalities=("audio", "text"), **_S)),
+    # audio + text + video: padded text tokens sit in the MIDDLE of the fused sequence (mask not left-aligned)
+    "c3x_three_modalities": dict(builder="build_c3x", bkw=dict(modalities=("audio", "text", "video"), **_S),
+                                 batch="batch_c3x", dkw=dict(B=4, modalities=("audio", "text", "video"), **_S)),
+    "c3x_three_video_empty": dict(builder="build_c3x", bkw=dict(modalities=("audio", "text", "video"), **_S),
+                                  batch="batch_c3x", dkw=dict(B=4, modalities=("audio", "text", "video"), empty="video", **_S)),
+    "c3x_avg_fusion": dict(builder="build_c3x", bkw=dict(modalities=("audio", "video"), fusion="avg", **_S),
+                           batch="batch_c3x", dkw=dict(B=6, modalities=("audio", "video"), **_S)),
+    "c3x_avg_fusion_video_empty": dict(builder="build_c3x", bkw=dict(modalities=("audio", "video"), fusion="avg", **_S),
+                                       batch="batch_c3x", dkw=dict(B=6, modalities=("audio", "video"), empty="video", **_S)),
+    "c3x_base_classifier": dict(builder="build_c3x", bkw=dict(modalities=("audio", "text", "video"), classifier="base", **_S),
+                                batch="batch_c3x", dkw=dict(B=4, modalities=("audio", "text", "video"), **_S)),
+    "c3x_old_multimodal_model": dict(builder="build_c3x", bkw=dict(modalities=("audio", "video"), top="old", **_S),
+                                     batch="batch_c3x", dkw=dict(B=4, modalities=("audio", "video"), flat_labels=True, **_S)),
+    "c3_weighted_ce": dict(builder="build_c3", bkw=dict(t_audio=50, t_video=16), batch="batch_c3",
+                           dkw=dict(B=6, t_audio=50, t_video=16), ce_weights={"phys": [0.3, 1.7], "verb": [1.25, 0.6]}),
+    "audio_text_model": dict(builder="build_audio_text", bkw={}, batch="batch_audio_text", dkw=dict(B=4, t_audio=30, t_text=12)),
+}
 FULL_GRADS = {
     "build_c1": ["1.classifier.4.weight", "0.transformer_squence_processing.norm.weight",
                  "0.transformer_squence_processing.layers.0.self_attn.in_proj_bias"],
@@ -50,6 +78,12 @@ FULL_GRADS = {
                  "models_dict.LSTM_1L.sequence_nn.bias_hh_l0"],
     "build_c3": ["classifiers.classifiers_dict.verb.3.weight", "modality_fusion_module.modality_fusion_transformer.norm.weight",
                  "modality_extractors_dict.video.feature_extractor.embedding.0.bias"],
+    "build_c3x": ["classifiers.classifiers_dict.verb.3.weight", "classifiers.audio.classifier.4.weight",
+                  "modality_fusion_module.modality_fusion_transformer.norm.weight",
+                  "modality_fusion_module.modality_fusion_transformer.layers.0.self_attn.in_proj_bias",
+                  "classifiers.adaptors_dict.audio.0.bias"],
+    "build_audio_text": ["output_classifier.3.weight", "modality_fusion_module.0.bias",
+                         "text_extractor.transformer_squence_processing.layers.1.self_attn.in_proj_bias"],
 }
 INIT_SEED = 1234
 
@@ -58,34 +92,17 @@ def weights_checksum(sd):
     return float(sum(v.double().abs().sum() for v in sd.values()))
 
 
-def ref_loss(builder, model, batch):
-    data, labels = batch
-    pred = model(data)
-    if builder == "build_c1":
-        return pred, {"loss": torch.nn.CrossEntropyLoss()(pred, labels)}
-    if builder == "build_c2":
-        return pred, ref.MultiCrossEntropyLoss()(pred, labels)
-    crit = ref.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(), "verb": torch.nn.CrossEntropyLoss()})
-    return pred, crit(pred, labels)
+def ref_loss(spec, model, batch):
+    """(pred dict, LossesDict) of the LIVE reference through the calls trainer.py makes."""
+    return H.model_losses(spec, ref, model, batch)
 
 
-def oracle_forward(builder, bkw, sd, data, training, grad_enabled):
-    if builder == "build_c1":
-        h = O.transformer_sequence_processor(data, sd, "0.", 2, 8, "identity", training)
-        return O.output_classifier(h, sd, "1.", training)
-    if builder == "build_c2":
-        kinds = {"GRU_1L": "gru", "LSTM_1L": "lstm", "Avg_features": "avg"}
-        return O.video_multi_nn(data, sd, {h: kinds[h] for h in bkw["heads"]}, training)
-    cfg = W.c3_oracle_cfg(bkw["t_audio"], bkw["t_video"])
-    return O.physverb_model(data, sd, cfg, training, grad_enabled)
+def oracle_forward(spec, sd, data, training, grad_enabled):
+    return H.oracle_forward(spec, sd, data, training, grad_enabled)
 
 
-def oracle_loss(builder, pred, labels):
-    if builder == "build_c1":
-        return {"loss": O.cross_entropy(pred, labels)}
-    if builder == "build_c2":
-        return O.multi_ce(pred, labels)
-    return O.multimodal_ce(pred, labels, heads=["phys", "verb"])
+def oracle_loss(spec, pred, labels):
+    return H.oracle_losses(spec, pred, labels)
 
 
 def as_dict(pred):
@@ -99,9 +116,9 @@ def check(name, a, b, tol=2e-5):
     return err
 
 
-def _ref_train_pass(builder, bkw, sd0, batch, dtype):
+def _ref_train_pass(spec, sd0, batch, dtype):
     """train-mode forward + per-head backward of the LIVE reference in `dtype` (dropout off)."""
-    model = W.disable_dropout(getattr(W, builder)(ref, **bkw)).to(dtype)
+    model = W.disable_dropout(getattr(W, spec["builder"])(ref, **spec["bkw"])).to(dtype)
     model.load_state_dict({k: v.to(dtype) for k, v in sd0.items()})
     model.train()
     data, labels = batch
@@ -110,7 +127,7 @@ def _ref_train_pass(builder, bkw, sd0, batch, dtype):
     old = torch.get_default_dtype()
     torch.set_default_dtype(dtype)     # the reference's zero stubs use the default dtype (models.py:851)
     try:
-        pred, losses = ref_loss(builder, model, (data, labels))
+        pred, losses = ref_loss(spec, model, (data, labels))
         if hasattr(losses, "backward"):
             losses.backward()
         else:
@@ -133,10 +150,10 @@ def run_case(name, spec):
     for seed in range(1000, 1040):
         dkw = dict(spec["dkw"], seed=seed)
         batch = getattr(W, spec["batch"])(**dkw)
-        _, l32, g32 = _ref_train_pass(builder, bkw, sd0, batch, torch.float32)
-        pred64, l64, g64 = _ref_train_pass(builder, bkw, sd0, batch, torch.float64)
+        _, l32, g32 = _ref_train_pass(spec, sd0, batch, torch.float32)
+        pred64, l64, g64 = _ref_train_pass(spec, sd0, batch, torch.float64)
         sdo = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
-        lo = oracle_loss(builder, oracle_forward(builder, bkw, sdo, batch[0], True, True), batch[1])
+        lo = oracle_loss(spec, oracle_forward(spec, sdo, batch[0], True, True), batch[1])
         if lo:
             sum(lo.values()).backward()
         worst = 0.0
@@ -166,7 +183,7 @@ def run_case(name, spec):
             out["eval_error"] = str(e)
         try:
             with torch.no_grad():
-                po = as_dict(oracle_forward(builder, bkw, sd0, data, False, False))
+                po = as_dict(oracle_forward(spec, sd0, data, False, False))
             for k in out.get("eval", {}):
                 check(f"{name}/eval/{k}", po[k], out["eval"][k])
             assert "eval_error" not in out
@@ -180,8 +197,8 @@ def run_case(name, spec):
     out["grads"] = {k: grads[k].clone() for k in FULL_GRADS[builder] if grads.get(k) is not None}
 
     sdo = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
-    po = oracle_forward(builder, bkw, sdo, data, True, True)
-    lo = oracle_loss(builder, po, labels)
+    po = oracle_forward(spec, sdo, data, True, True)
+    lo = oracle_loss(spec, po, labels)
     for k in out["train"]:
         check(f"{name}/train/{k}", as_dict(po)[k].detach(), out["train"][k])
     assert set(lo) == set(out["losses"]), (set(lo), set(out["losses"]))
@@ -203,7 +220,7 @@ def run_case(name, spec):
     curve = []
     for _ in range(3):
         opt.zero_grad()
-        _, losses = ref_loss(builder, model, batch)
+        _, losses = ref_loss(spec, model, batch)
         if hasattr(losses, "backward"):
             losses.backward()
         else:
@@ -213,8 +230,8 @@ def run_case(name, spec):
     out["adam_curve"] = curve
 
     def fwd(sd, d, training):
-        return oracle_forward(builder, bkw, sd, d, training, True)
-    tr = O.OracleTrainer(sd0, fwd, lambda p, t: oracle_loss(builder, p, t))
+        return oracle_forward(spec, sd, d, training, True)
+    tr = O.OracleTrainer(sd0, fwd, lambda p, t: oracle_loss(spec, p, t))
     for i in range(3):
         got = tr.step(data, labels, training=True)
         for k, v in curve[i].items():
@@ -223,7 +240,7 @@ def run_case(name, spec):
     return out
 
 
-def main():
+def main_v1():
     golden = {"torch": torch.__version__, "cases": {}}
     for name, spec in CASES.items():
         golden["cases"][name] = run_case(name, spec)
@@ -241,5 +258,59 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main_v2():
+    golden = {"torch": torch.__version__, "cases": {}}
+    for name, spec in CASES_V2.items():
+        golden["cases"][name] = run_case(name, spec)
+    torch.manual_seed(0)
+    golden["module_trees"] = {name: str(getattr(W, spec["builder"])(ref, **spec["bkw"])) for name, spec in CASES_V2.items()}
+    path = os.path.join(ROOT, "tests", "golden", "golden_v2.pt")
+    torch.save(golden, path)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+C1_EPOCH_STEPS = 48     # "1 epoch" := 48 steps of 32 clips (1 536 clips, train_names.txt holds 1 539)
+
+
+def main_c1_epoch():
+    """BASELINE config 1 at full size (B=32, T=250, d=768, 2 layers, fp32, Adam lr 1e-3) over one epoch of 48
+    DIFFERENT batches with a learnable label (batch i = W.batch_c1_learnable(seed=2000+i)), dropout off, through the LIVE reference; then the
+    logits / label predictions of the trained model on a held-out batch (seed 2999).  The oracle trainer is run
+    beside it and must reproduce the curve (its pin)."""
+    spec = dict(builder="build_c1", bkw={}, batch="batch_c1", dkw={})
+    torch.manual_seed(INIT_SEED)
+    model = W.perturb_norms(W.disable_dropout(W.build_c1(ref))).train()
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam(model.parameters())
+    crit = torch.nn.CrossEntropyLoss()
+    tr = O.OracleTrainer(sd0, lambda sd, d, t: oracle_forward(spec, sd, d, t, True), lambda p, t: oracle_loss(spec, p, t))
+    curve, curve_oracle = [], []
+    for i in range(C1_EPOCH_STEPS):
+        x, y = W.batch_c1_learnable(seed=2000 + i)
+        opt.zero_grad()
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step()
+        curve.append(float(loss.detach()))
+        curve_oracle.append(tr.step(x, y, training=True)["loss"])
+        print(f"  step {i}: reference {curve[-1]:.6f}  oracle {curve_oracle[-1]:.6f}", flush=True)
+    x, y = W.batch_c1_learnable(seed=2999)
+    model.eval()
+    with torch.no_grad():
+        logits = model(x)
+        lo = oracle_forward(spec, {k: v.detach() for k, v in tr.sd.items()}, x, False, False)["logits"]
+    dev = max(abs(a - b) for a, b in zip(curve, curve_oracle))
+    agree = float((logits.argmax(1) == lo.argmax(1)).float().mean())
+    print(f"  oracle vs reference: max |loss diff| over the epoch {dev:.3e}, held-out prediction agreement {agree:.3f}")
+    assert dev < 5e-3 and agree >= 0.9
+    out = {"torch": torch.__version__, "init_seed": INIT_SEED, "steps": C1_EPOCH_STEPS, "batch_seed0": 2000, "eval_seed": 2999,
+           "weights_checksum": weights_checksum(sd0), "loss_curve": curve, "loss_curve_oracle": curve_oracle,
+           "eval_logits": logits.clone(), "eval_pred": logits.argmax(1).clone(), "eval_labels": y.clone()}
+    path = os.path.join(ROOT, "tests", "golden", "golden_c1_epoch.pt")
+    torch.save(out, path)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1] if len(sys.argv) > 1 else "v1"
+    {"v1": main_v1, "v2": main_v2, "c1_epoch": main_c1_epoch}[which]()

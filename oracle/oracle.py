@@ -363,8 +363,11 @@ def physverb_extract_features(data, sd: SD, cfg: dict, training: bool = False) -
         if not_empty.any() and name in cfg["extractors"]:
             e = cfg["extractors"][name]
             idx = torch.from_numpy(not_empty)
-            got = transformer_sequence_processor(batch[idx], sd, f"modality_extractors_dict.{name}.",
-                                                 e["layers"], e["heads"], e["extractor"], training)
+            if e["layers"] == 0:      # nn.Sequential() as the extractor (text, train_multimodal.py:365): pass-through
+                got = batch[idx]
+            else:
+                got = transformer_sequence_processor(batch[idx], sd, f"modality_extractors_dict.{name}.",
+                                                     e["layers"], e["heads"], e["extractor"], training)
             feat = feat.index_put((idx,), got)
         out[name] = feat
     return dict(sorted(out.items()))
@@ -372,10 +375,17 @@ def physverb_extract_features(data, sd: SD, cfg: dict, training: bool = False) -
 
 def physverb_model(data, sd: SD, cfg: dict, training: bool = False, grad_enabled: bool = False) -> Dict[str, Tensor]:
     """PhysVerbModel.forward (models.py:865-879) with EqualSizedTransformerModalitiesFusion and
-    PhysVerbClassifierConcatFeatures, the C3 assembly of train_multimodal.py:298-420."""
+    PhysVerbClassifierConcatFeatures, the C3 assembly of train_multimodal.py:298-420; `cfg` also selects the
+    script's alternatives: "fusion": "avg" (AveragedFeaturesTransformerFusion, :375), "classifier": "base"
+    (PhysVerbClassifier, models.py:667-735), "top": "old" (MultimodalModel, models.py:505-558)."""
     feats = physverb_extract_features(data, sd, cfg, training)
-    fused = equal_sized_fusion(feats, sd, "modality_fusion_module.", cfg["fusion_layers"], cfg["fusion_heads"],
-                               training, grad_enabled)
+    fuse = averaged_features_fusion if cfg.get("fusion", "equal") == "avg" else equal_sized_fusion
+    fused = fuse(feats, sd, "modality_fusion_module.", cfg["fusion_layers"], cfg["fusion_heads"], training, grad_enabled)
+    if cfg.get("top", "physverb") == "old":
+        # MultimodalModel.forward (models.py:543-555): one OutputClassifier per modality on its own fused slice
+        return {m: output_classifier(fused[m], sd, f"classifiers.{m}.", training) for m in fused}
+    if cfg.get("classifier", "concat") == "base":
+        return physverb_classifier(fused, sd, "classifiers.", cfg["modality2aggr"], training)
     return physverb_classifier_concat(fused, sd, "classifiers.", cfg["aggr_types"], training)
 
 

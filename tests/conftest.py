@@ -15,8 +15,20 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     import torch
-    path = os.path.join(ROOT, "tests", "golden", "golden_v1.pt")
-    return torch.load(path, weights_only=False)
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "golden_v1.pt"), weights_only=False)
+    # golden_v2: the script's other assemblies (text branch, averaged fusion, base heads, MultimodalModel,
+    # AudioTextualModel, class-weighted CE) — `python oracle/make_golden.py v2`
+    g2 = torch.load(os.path.join(ROOT, "tests", "golden", "golden_v2.pt"), weights_only=False)
+    assert not set(g["cases"]) & set(g2["cases"])
+    g["cases"].update(g2["cases"])
+    g["module_trees"] = g2["module_trees"]
+    return g
+
+
+@pytest.fixture(scope="session")
+def golden_c1_epoch():
+    import torch
+    return torch.load(os.path.join(ROOT, "tests", "golden", "golden_c1_epoch.pt"), weights_only=False)
 
 
 @pytest.fixture(scope="session", autouse=True)

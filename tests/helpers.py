@@ -118,6 +118,13 @@ def build_case(spec, ns, device=None, init_seed=1234):
     return model, batch
 
 
+def _c3_cfg(spec):
+    bkw = spec["bkw"]
+    if spec["builder"] == "build_c3x":
+        return W.c3x_oracle_cfg(**bkw)
+    return W.c3_oracle_cfg(bkw.get("t_audio", 250), bkw.get("t_video", 64), bkw.get("d", 768), bkw.get("heads", 8))
+
+
 def oracle_forward(spec, sd, data, training, grad_enabled):
     b, bkw = spec["builder"], spec["bkw"]
     if b == "build_c1":
@@ -125,28 +132,98 @@ def oracle_forward(spec, sd, data, training, grad_enabled):
         return {"logits": O.output_classifier(h, sd, "1.", training)}
     if b == "build_c2":
         return O.video_multi_nn(data, sd, {h: KINDS[h] for h in bkw.get("heads", ("GRU_1L",))}, training)
-    cfg = W.c3_oracle_cfg(bkw.get("t_audio", 250), bkw.get("t_video", 64), bkw.get("d", 768), bkw.get("heads", 8))
-    return O.physverb_model(data, sd, cfg, training, grad_enabled)
+    if b == "build_audio_text":
+        heads = bkw.get("heads", 8)
+        cfg = {"audio": {"layers": 1, "heads": heads, "extractor": "identity"},
+               "text": {"layers": bkw.get("text_layers", 2), "heads": heads, "extractor": "identity"}}
+        return {"logits": O.audio_text_model(data, sd, cfg, training)}
+    return O.physverb_model(data, sd, _c3_cfg(spec), training, grad_enabled)
+
+
+def _ce_weights(spec, like: torch.Tensor):
+    w = spec.get("ce_weights")
+    return None if w is None else {k: torch.tensor(v, dtype=like.dtype, device=like.device) for k, v in w.items()}
 
 
 def oracle_losses(spec, pred, labels):
     b = spec["builder"]
-    if b == "build_c1":
+    if b in ("build_c1", "build_audio_text"):
         return {"loss": O.cross_entropy(pred["logits"], labels)}
-    if b == "build_c2":
+    if b == "build_c2" or spec["bkw"].get("top") == "old":
         return O.multi_ce(pred, labels)
-    return O.multimodal_ce(pred, labels, heads=["phys", "verb"])
+    return O.multimodal_ce(pred, labels, weights=_ce_weights(spec, next(iter(pred.values()))), heads=["phys", "verb"])
 
 
 def model_losses(spec, ns, model, batch):
-    """Drop-in forward + losses through the reference-facing API (same calls trainer.py makes)."""
+    """Drop-in forward + losses through the reference-facing API (same calls trainer.py makes).  `ns` is the
+    namespace the classes come from: this package's `models`, or the reference's (oracle/make_golden.py)."""
     data, labels = batch
     pred = model(data)
     b = spec["builder"]
-    if b == "build_c1":
+    if b in ("build_c1", "build_audio_text"):
         crit = ns.MultiCrossEntropyLoss()
         return {"logits": pred}, crit({"loss": pred}, labels)
-    if b == "build_c2":
+    if b == "build_c2" or spec["bkw"].get("top") == "old":
         return pred, ns.MultiCrossEntropyLoss()(pred, labels)
-    crit = ns.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(), "verb": torch.nn.CrossEntropyLoss()})
+    w = _ce_weights(spec, next(iter(pred.values()))) or {}
+    crit = ns.MultiModalCrossEntropyLoss({k: torch.nn.CrossEntropyLoss(weight=w.get(k)) for k in ("phys", "verb")})
     return pred, crit(pred, labels)
+
+
+# ---- epoch bookkeeping of the reference's trainers (oracle/make_golden_trainer.py, tests/test_host_logic_cpu.py) ----
+TRAINER_STREAMS = {
+    # TorchSupervisedTrainer: one tensor of logits, one loss, labels (B,)
+    "single": dict(kind="single", steps=7, B=16, seed=11, dataset_size=7 * 16 - 5),
+    # RNN_trainer: {head: logits}, {head: loss}, the same labels for every head (train_video_rnn.py)
+    "multi_head": dict(kind="multi_head", steps=5, B=12, seed=12, heads=("LSTM_1L", "GRU_1L", "Avg_features"), dataset_size=60),
+    # MultimodalTrainer: label groups with whole-group and per-row `_EMPTY` markers (datasets.py:592-608)
+    "multimodal": dict(kind="multimodal", steps=9, B=10, seed=13, heads=("phys", "verb"), dataset_size=90),
+}
+
+
+def trainer_metrics():
+    """metrics_dict as the train_*.py scripts build it (train_multimodal.py:515-524)."""
+    from sklearn import metrics
+    return {
+        'loss': None,
+        'accuracy': metrics.accuracy_score,
+        'recall': {'metric': metrics.recall_score, 'kwargs': {'average': None, 'zero_division': 0}},
+        'UAR': {'metric': metrics.recall_score, 'kwargs': {'average': 'macro', 'zero_division': 0}},
+    }
+
+
+def trainer_stream(kind, steps, B, seed, heads=("loss",), dataset_size=None, device=None):
+    """A seeded stream of (data, losses, pred, labels) as a trainer's step sees them.  For 'multimodal', step i's
+    label groups cycle through: all present / phys group all-EMPTY / verb group all-EMPTY / a few EMPTY rows in one
+    group (the non-homogeneous case `create_batch_results_dict` filters row-wise, trainer.py:893-905)."""
+    g = torch.Generator().manual_seed(seed)
+    dev = device or torch.device("cpu")
+    out = []
+    for i in range(steps):
+        b = B if i < steps - 1 else max(1, B - 3)              # a shorter last batch
+        if kind == "single":
+            logits = torch.randn(b, 2, generator=g)
+            out.append((torch.zeros(b, 4, 8), torch.rand((), generator=g).to(dev), logits.to(dev), torch.randint(0, 2, (b,), generator=g).to(dev)))
+            continue
+        pred = {h: torch.randn(b, 2, generator=g).to(dev) for h in heads}
+        losses = {h: torch.rand((), generator=g).to(dev) for h in heads}
+        if kind == "multi_head":
+            out.append((torch.zeros(b, 4, 8), losses, pred, torch.randint(0, 2, (b,), generator=g).to(dev)))
+            continue
+        data = [[("audio",) * b, torch.zeros(b, 4, 8)], [("video",) * b, torch.zeros(b, 2, 8)]]
+        labels = []
+        for h in ("verb", "phys"):
+            y = torch.randint(0, 2, (b,), generator=g)
+            names = [h] * b
+            mode = i % 4
+            if (mode == 1 and h == "phys") or (mode == 2 and h == "verb"):
+                names = [h + "_EMPTY"] * b
+                y = torch.full_like(y, -1)
+                losses.pop(h)                               # MultiModalCrossEntropyLoss emits no loss for an all-EMPTY group
+            elif mode == 3 and h == "phys":
+                for r in range(0, b, 3):
+                    names[r] = h + "_EMPTY"
+                    y[r] = -1
+            labels.append([tuple(names), y.to(dev)])
+        out.append((data, losses, pred, labels))
+    return out

@@ -50,3 +50,38 @@ def test_focal_loss_module_arguments():
     assert f.alpha.dtype == torch.float32 and f.gamma == 2.0 and f.ignore_index == -1
     with pytest.raises(RuntimeError):                           # no CPU path: CPU logits fail loudly
         f(torch.zeros(2, 2), torch.zeros(2, dtype=torch.long))
+
+
+@pytest.mark.parametrize("name", ["single", "multi_head", "multimodal"])
+def test_epoch_accumulator_reproduces_the_reference_trainers(name):
+    """training.EpochAccumulator (one device->host read per epoch) against what the LIVE reference's
+    TorchSupervisedTrainer / RNN_trainer / MultimodalTrainer methods returned for the same seeded step stream
+    (tests/golden/golden_trainer_epoch.pt, oracle/make_golden_trainer.py) — including the reference's
+    `size = len(data[0])` rule, all-EMPTY groups dropped per step and row-wise EMPTY filtering."""
+    import os
+    import numpy as np
+    from multimodalaggressionrecognition_b200 import training
+    from tests import helpers as H
+    golden = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_trainer_epoch.pt"), weights_only=False)
+    case = golden["cases"][name]
+    spec = case["spec"]
+    assert spec == H.TRAINER_STREAMS[name]
+    acc = training.EpochAccumulator(H.trainer_metrics())
+    for data, losses, pred, labels in H.trainer_stream(**spec):
+        acc.add(losses, pred, labels, data=data)
+    got = acc.results(spec["dataset_size"])
+    ref = case["results"]
+
+    def same(a, b, where):
+        assert set(a) == set(b), where
+        for k in a:
+            assert np.allclose(np.asarray(a[k], dtype=np.float64), np.asarray(b[k], dtype=np.float64), rtol=1e-6, atol=1e-9), f"{where}/{k}: {a[k]} vs {b[k]}"
+
+    if name == "single":
+        same(got, ref, name)
+    else:
+        assert list(got) == list(ref)                       # same heads, in the reference's order
+        for h in ref:
+            same(got[h], ref[h], f"{name}/{h}")
+    acc.reset()
+    assert acc.results(1) == {}

@@ -151,7 +151,9 @@ def _attn_ref(qkv, mask, H):
     return torch.matmul(p, sp(v)).permute(0, 2, 1, 3).reshape(B, T, d)
 
 
-@pytest.mark.parametrize("B,T,H,dh", [(2, 50, 8, 96), (3, 37, 4, 64), (2, 130, 2, 32), (1, 314, 8, 96), (2, 64, 8, 96), (2, 33, 1, 128)])
+@pytest.mark.parametrize("B,T,H,dh", [(2, 50, 8, 96), (3, 37, 4, 64), (2, 130, 2, 32), (1, 314, 8, 96), (2, 64, 8, 96), (2, 33, 1, 128),
+                                      # the 1-token-per-modality sequences of AveragedFeaturesTransformerFusion (models.py:482-503)
+                                      (3, 2, 8, 96), (2, 1, 4, 64), (4, 5, 8, 96)])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("masked", [False, True])
 def test_attention_fwd_bwd(B, T, H, dh, mode, masked):

@@ -14,6 +14,9 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
 CASES = ["c1_small", "c1_odd", "c2_small", "c3_small", "c3_video_empty", "c3_audio_empty", "c3_audio_padded"]
+CASES_V2 = ["c3x_audio_text_ragged", "c3x_three_modalities", "c3x_three_video_empty", "c3x_avg_fusion",
+            "c3x_avg_fusion_video_empty", "c3x_base_classifier", "c3x_old_multimodal_model", "c3_weighted_ce",
+            "audio_text_model"]
 
 
 @pytest.fixture(autouse=True)
@@ -24,7 +27,7 @@ def _no_dropout():
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + CASES_V2)
 def test_golden_parity(golden, name, mode):
     """eval outputs (incl. the nested-tensor zero-fill path), train logits, per-head losses, every parameter
     gradient — against what the reference itself produced."""
@@ -32,6 +35,13 @@ def test_golden_parity(golden, name, mode):
     spec = case["spec"]
     tol = H.FP32_TOL if mode == "fp32" else H.BF16_TOL
     model, batch = H.build_case(spec, M, DEV)
+    floor, eval_bar = None, {}
+    if mode == "bf16":
+        # what torch's own bf16 arithmetic does on this case (logits of a near-initialisation model are small
+        # differences of large terms: on some of the tiny golden batches plain torch bf16 is itself 2e-2 off);
+        # the bf16 bars are max(the absolute bar, 1.5 x that floor), as for the gradients (tests/helpers.py)
+        floor = H.bf16_floor(spec, model, getattr(W, spec["batch"])(**spec["dkw"]))
+        eval_bar = {k: max(tol, H.BF16_VS_TORCH * e) for k, e in floor["logits"].items()}
     with mar.precision(mode):
         model.eval()
         if "eval" in case:
@@ -40,7 +50,7 @@ def test_golden_parity(golden, name, mode):
             pred = pred if isinstance(pred, dict) else {"logits": pred}
             for k, v in case["eval"].items():
                 assert pred[k].dtype == torch.float32
-                H.assert_close(pred[k].cpu(), v, tol, f"{name}/{mode}/eval/{k}")
+                H.assert_close(pred[k].cpu(), v, tol if mode == "fp32" else eval_bar.get(k, tol), f"{name}/{mode}/eval/{k}")
         else:
             with torch.no_grad(), pytest.raises(RuntimeError):
                 model(batch[0])
@@ -50,7 +60,8 @@ def test_golden_parity(golden, name, mode):
         assert set(losses) == set(case["losses"])
         losses.backward()
     for k, v in case["train"].items():
-        H.assert_close(pred[k].cpu(), v, tol, f"{name}/{mode}/train/{k}")
+        bar = eval_bar.get(k, tol)
+        H.assert_close(pred[k].cpu(), v, bar, f"{name}/{mode}/train/{k}")
     for k, v in case["losses"].items():
         assert abs(float(losses[k]) - v) <= (2e-5 if mode == "fp32" else 5e-3), f"{name}/{mode}/loss/{k}"
     grads = {k: p.grad for k, p in model.named_parameters()}
@@ -70,7 +81,6 @@ def test_golden_parity(golden, name, mode):
         for k, v in case["grads"].items():
             H.assert_grad_close(grads[k].cpu(), v, tol, f"{name}/{mode}/grad/{k}")
     else:
-        floor = H.bf16_floor(spec, model, getattr(W, spec["batch"])(**spec["dkw"]))
         H.assert_bf16_grads({k: grads[k] for k in case["grads"]}, case["grads"], floor, f"{name}/bf16/grad")
 
 
@@ -158,6 +168,76 @@ def test_adam_loss_curve(golden, mode):
                 for k, v in ref_step.items():
                     assert abs(float(losses[k]) - v) <= (1e-3 if mode == "fp32" else 5e-2) * max(1.0, abs(v)), \
                         f"{name}/{mode}: loss curve {k}: {float(losses[k])} vs {v}"
+
+
+def test_adam_loss_curve_other_assemblies(golden):
+    """The 3-step Adam curves of golden_v2 (ragged text masks in the middle of the fused sequence, averaged fusion,
+    base classifier heads, the older MultimodalModel, class-weighted CE), fp32 mode."""
+    for name in ("c3x_three_modalities", "c3x_avg_fusion", "c3x_base_classifier", "c3x_old_multimodal_model", "c3_weighted_ce"):
+        case = golden["cases"][name]
+        spec = case["spec"]
+        model, batch = H.build_case(spec, M, DEV)
+        model.train()
+        opt = torch.optim.Adam(model.parameters())
+        with mar.precision("fp32"):
+            for ref_step in case["adam_curve"]:
+                opt.zero_grad()
+                _, losses = H.model_losses(spec, M, model, batch)
+                losses.backward()
+                opt.step()
+                for k, v in ref_step.items():
+                    assert abs(float(losses[k]) - v) <= 1e-3 * max(1.0, abs(v)), f"{name}: loss curve {k}: {float(losses[k])} vs {v}"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_c1_epoch_loss_curve_and_predictions(golden_c1_epoch, mode):
+    """BASELINE config 1 at full size (B=32, T=250, d=768, 2 layers) over "1 epoch" = 48 Adam steps on 48 different
+    batches: the per-step loss curve and the trained model's label predictions on a held-out batch, against what
+    the LIVE reference produced (tests/golden/golden_c1_epoch.pt, `python oracle/make_golden.py c1_epoch`)."""
+    g = golden_c1_epoch
+    torch.manual_seed(g["init_seed"])
+    model = W.perturb_norms(W.disable_dropout(W.build_c1(M)))
+    chk = float(sum(v.double().abs().sum() for v in model.state_dict().values()))
+    assert abs(chk - g["weights_checksum"]) <= 1e-9 * g["weights_checksum"]
+    model = model.to(DEV).train()
+    opt = torch.optim.Adam(model.parameters())
+    crit = M.MultiCrossEntropyLoss()
+    curve = []
+    with mar.precision(mode):
+        for i in range(g["steps"]):
+            x, y = W.batch_c1_learnable(seed=g["batch_seed0"] + i)
+            opt.zero_grad()
+            losses = crit({"loss": model(x.to(DEV))}, y.to(DEV))
+            losses.backward()
+            opt.step()
+            curve.append(losses["loss"].detach())
+        x, y = W.batch_c1_learnable(seed=g["eval_seed"])
+        model.eval()
+        with torch.no_grad():
+            logits = model(x.to(DEV)).float().cpu()
+    curve = [float(c) for c in curve]
+    ref = g["loss_curve"]
+    dev = [abs(a - b) for a, b in zip(curve, ref)]
+    epoch_loss, ref_epoch_loss = sum(curve) / len(curve), sum(ref) / len(ref)      # the per-epoch loss of trainer.py:258
+    print(f"C1 epoch {mode}: max |loss - reference| {max(dev):.3e} at step {dev.index(max(dev))}, mean {sum(dev) / len(dev):.3e}; "
+          f"epoch loss {epoch_loss:.5f} vs {ref_epoch_loss:.5f}")
+    # The reference's curve: a plateau around 0.7-1.8 for ~15 steps, a sharp learning transition over steps 14-22,
+    # then -> 1e-4.  WHEN the transition starts is sensitive to rounding: the fp32 oracle port is within 1e-5 of the
+    # reference on the plateau and 7e-4 off at step 18; the oracle's arithmetic done entirely in bf16 (CPU
+    # emulation, fp32 master weights) is 1e-2 off on the plateau and up to 9e-2 during the transition, 3 % on the
+    # per-epoch loss.  Bars: fp32 2e-3 outside / 2e-2 inside the transition; bf16 2x what all-bf16 arithmetic does.
+    plateau = [d for i, d in enumerate(dev) if i < 14 or i >= 24]
+    if mode == "fp32":
+        assert max(plateau) <= 2e-3 and max(dev) <= 2e-2
+        assert abs(epoch_loss - ref_epoch_loss) <= 2e-3 * ref_epoch_loss
+    else:
+        assert max(plateau) <= 0.1 and max(dev) <= 0.2 and sum(dev) / len(dev) <= 2.5e-2
+        assert abs(epoch_loss - ref_epoch_loss) <= 6e-2 * ref_epoch_loss
+    assert curve[-1] < 1e-2                                                          # it learned, like the reference
+    ref_logits, ref_pred = g["eval_logits"], g["eval_pred"]
+    assert float((ref_logits[:, 1] - ref_logits[:, 0]).abs().min()) > 5.0            # the reference decides every clip clearly
+    assert torch.equal(logits.argmax(1), ref_pred), f"{mode}: label predictions differ from the reference's"
+    H.assert_close(logits, ref_logits, 2e-2 if mode == "fp32" else 0.25, "held-out logits after the epoch")
 
 
 def test_train_eval_asymmetry_of_masked_tokens(golden):
@@ -339,3 +419,35 @@ def test_train_step_graphs_are_keyed_by_batch_signature():
             # dQ reduce); over 10 Adam steps that grows to a few 1e-4.  Replaying a graph captured for ANOTHER
             # signature gives errors of 1e-1 (other heads active, other batch size).
             assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), f"step {i} ({order[i]}) loss[{k}]: eager {a[k]} vs graph {b[k]}"
+
+
+def test_epoch_accumulator_on_the_graph_captured_step():
+    """training.EpochAccumulator fed from a graph-captured TrainStep (device tensors that the next replay overwrites,
+    argmax on the device, ONE read at the end) against the reference's per-step host bookkeeping (`.item()` per head,
+    argmax -> numpy per head, trainer.py:718-737) done on the same steps."""
+    from multimodalaggressionrecognition_b200 import training
+    kw = dict(t_audio=24, t_video=8)
+    torch.manual_seed(0)
+    model = W.build_c3(M, **kw).to(DEV).train()
+    crit = M.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(), "verb": torch.nn.CrossEntropyLoss()})
+    step = training.TrainStep(model, crit, lr=1e-3, graph=True, precision="bf16")
+    dev_acc = training.EpochAccumulator(H.trainer_metrics())
+    host_acc = training.EpochAccumulator(H.trainer_metrics())
+    n = 0
+    for i in range(8):
+        data, labels = W.batch_c3(B=8, seed=100 + i, empty="video" if i % 3 == 2 else None, **kw)
+        losses = step(W.to_device(data, DEV), W.to_device(labels, DEV))
+        dev_acc.add(losses, step.last_pred, W.to_device(labels, DEV), data=data)
+        # the reference's way: blocking reads every step
+        host_acc.add({k: torch.tensor(v.item()) for k, v in losses.items()},
+                     {k: v.detach().float().cpu() for k, v in step.last_pred.items()}, labels, data=data)
+        n += 8
+    got, ref = dev_acc.results(n), host_acc.results(n)
+    step.release_graphs()
+    assert list(got) == list(ref) and set(got) == {"phys", "verb"}
+    for h in ref:
+        assert abs(got[h]["loss"] - ref[h]["loss"]) <= 1e-6 * max(1.0, abs(ref[h]["loss"]))
+        for m in ("accuracy", "UAR"):
+            assert got[h][m] == ref[h][m]
+        assert (dev_acc.last_arrays[h]["pred"] == host_acc.last_arrays[h]["pred"]).all()
+        assert (dev_acc.last_arrays[h]["true"] == host_acc.last_arrays[h]["true"]).all()

@@ -24,6 +24,18 @@ def test_module_tree_equals_reference_printout(golden):
     assert str(W.build_c3(M)) == golden["c3_module_tree"]
 
 
+def test_module_trees_of_the_other_assemblies_equal_the_reference(golden):
+    """golden_v2: text branch, averaged fusion, base PhysVerbClassifier, the older MultimodalModel, AudioTextualModel —
+    the drop-in classes print the same module tree as the reference's (same sub-module names => same state_dict keys),
+    and the grad_norms recorded from the reference name exactly the drop-in's parameters."""
+    for name, tree in golden["module_trees"].items():
+        spec = golden["cases"][name]["spec"]
+        torch.manual_seed(0)
+        model = getattr(W, spec["builder"])(M, **spec["bkw"])
+        assert str(model) == tree, name
+        assert set(dict(model.named_parameters())) == set(golden["cases"][name]["grad_norms"]), name
+
+
 def test_state_dict_keys():
     sd = W.build_c3(M).state_dict()
     for k in ("modality_extractors_dict.audio.transformer_squence_processing.layers.0.self_attn.in_proj_weight",
