@@ -122,6 +122,8 @@ class GradSync:
                 self.bucket_of[i] = b
         self.pending = [0] * len(self.buckets)
         self.launched = [False] * len(self.buckets)
+        self._streams = [dict() for _ in self.buckets]
+        self.fired = [False] * n
         self.handles = []
         self.order: List[int] = []
         self.enabled = True          # False: hooks do nothing (backward passes outside a TrainStep, e.g. profiling)
@@ -133,8 +135,12 @@ class GradSync:
         self.reset()
 
     def notify(self, param) -> None:
-        """A kernel accumulated this parameter's gradient straight into the flat buffer (ops.grad_sink), so autograd
-        will not run its post-accumulate hook: count it here."""
+        """A kernel accumulated this parameter's gradient straight into the flat buffer (ops.grad_sink) and its
+        autograd Function returned None for it: count the parameter here, right after the kernel was enqueued.
+        torch still fires the parameter's post-accumulate hook afterwards (AccumulateGrad runs with an undefined
+        gradient, measured on torch 2.11) — every parameter is counted ONCE per step, whichever comes first
+        (counting both launched the buckets' all-reduces before their gradients were complete: found on 2 B200s
+        with tools/dp_diag.py, the ranks' parameters drifted apart)."""
         if self.world > 1:
             i = self.index_of.get(id(param))
             if i is not None:
@@ -144,14 +150,20 @@ class GradSync:
         for b, (lo, hi, _, _) in enumerate(self.buckets):
             self.pending[b] = hi - lo
             self.launched[b] = False
+            self._streams[b] = {}
+        self.fired = [False] * len(self.flat.params)
         self.handles = []
         self.order = []
 
     def _make_hook(self, i: int) -> Callable:
         def hook(_param):
-            if not self.enabled:
+            if not self.enabled or self.fired[i]:
                 return
+            self.fired[i] = True
             b = self.bucket_of[i]
+            if self.comm_stream is not None:        # the stream this gradient was written on (autograd may run a
+                s = torch.cuda.current_stream()     # kept-alive AccumulateGrad node on the stream of an earlier step)
+                self._streams[b][s.cuda_stream] = s
             self.pending[b] -= 1
             if self.pending[b] == 0 and not self.launched[b]:
                 self._launch(b)
@@ -163,7 +175,11 @@ class GradSync:
         _, _, e0, e1 = self.buckets[b]
         view = self.flat.grad[e0:e1]
         if self.comm_stream is not None:
-            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            cur = torch.cuda.current_stream()
+            self.comm_stream.wait_stream(cur)
+            for key, s in self._streams[b].items():     # every stream a gradient of this bucket was written on
+                if key != cur.cuda_stream:
+                    self.comm_stream.wait_stream(s)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
         else:

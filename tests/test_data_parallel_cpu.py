@@ -38,6 +38,48 @@ class TwoHead(nn.Module):
         return {"a": self.a(h), "b": self.b(h)}
 
 
+class _SinkLinear(torch.autograd.Function):
+    """CPU stand-in for the gradient-sink protocol of ops._Linear inside a TrainStep: the weight / bias gradients are
+    accumulated STRAIGHT into the parameters' flat .grad views, the step driver is told through ops._sunk(), and
+    autograd gets None for both parameters."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.refs = (w, b)
+        return x @ w.t() + b
+
+    @staticmethod
+    def backward(ctx, g):
+        from multimodalaggressionrecognition_b200 import ops
+        x, w = ctx.saved_tensors
+        wref, bref = ctx.refs
+        if not ops._sink_cfg["on"]:                       # outside a TrainStep: ordinary autograd
+            return g @ w, g.t() @ x, g.sum(0), 
+        wref.grad.add_(g.t() @ x)
+        ops._sunk(wref)
+        bref.grad.add_(g.sum(0))
+        ops._sunk(bref)
+        return g @ w, None, None
+
+
+class SinkTwoHead(TwoHead):
+    """TwoHead whose trunk layers sink their gradients (like the 38 Linear parameters of the fusion model) while the
+    heads go through autograd's AccumulateGrad (like its LayerNorm vectors): both ways of counting a parameter's
+    gradient as complete meet in the same buckets."""
+
+    def __init__(self):
+        super().__init__()
+        self.extra = nn.ModuleList([nn.Linear(32, 32) for _ in range(3)])
+
+    def forward(self, x):
+        h = torch.relu(_SinkLinear.apply(x, self.trunk[0].weight, self.trunk[0].bias))
+        h = torch.relu(_SinkLinear.apply(h, self.trunk[2].weight, self.trunk[2].bias))
+        for lin in self.extra:       # several sinking layers in ONE bucket: double counting completes it before the trunk's turn
+            h = torch.relu(_SinkLinear.apply(h, lin.weight, lin.bias))
+        return {"a": self.a(h), "b": self.b(h)}
+
+
 def _criterion(pred, labels):
     out = LossesDict()
     ce = nn.CrossEntropyLoss()
@@ -46,18 +88,18 @@ def _criterion(pred, labels):
     return out
 
 
-def _make(seed=0):
+def _make(seed=0, sink=False):
     torch.manual_seed(seed)
-    return TwoHead()
+    return SinkTwoHead() if sink else TwoHead()
 
 
-def _worker(rank, world, port, steps, result_q):
+def _worker(rank, world, port, steps, result_q, sink=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        model = _make()
-        step = training.TrainStep(model, _criterion, lr=1e-2, num_buckets=3)
-        assert step.sync.world == world and len(step.sync.buckets) >= 2
+        model = _make(sink=sink)
+        step = training.TrainStep(model, _criterion, lr=1e-2, num_buckets=1 if sink else 3)
+        assert step.sync.world == world and len(step.sync.buckets) >= (1 if sink else 2)
         g = torch.Generator().manual_seed(123)
         X = torch.randn(steps, 8 * world, 16, generator=g)
         Y = torch.randint(0, 2, (steps, 8 * world), generator=g)
@@ -67,33 +109,42 @@ def _worker(rank, world, port, steps, result_q):
             # peek at the bucket launch order of this step
             losses = step(xs, ys)
             assert set(losses) == {"a", "b"}
+            orders.append(list(step.sync.order))      # reset by finish(): empty here; launch order is checked through the result
         flat = step.flat.flat.detach().clone()
         gathered = [torch.zeros_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
+        grads = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(grads, step.flat.grad.detach().clone())     # the last step's gradients, after the exchange
         if rank == 0:
-            result_q.put(([g.numpy() for g in gathered], X.numpy(), Y.numpy()))
+            result_q.put(([g.numpy() for g in gathered], X.numpy(), Y.numpy(), [g.numpy() for g in grads]))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(180)
-def test_two_rank_training_matches_single_process():
+@pytest.mark.parametrize("sink", [False, True])
+def test_two_rank_training_matches_single_process(sink):
+    """sink=True: parameters whose gradient is written by a kernel straight into the flat buffer (ops.grad_sink) are
+    counted through GradSync.notify AND torch fires their post-accumulate hook as well; counting both launched a
+    bucket's all-reduce before its gradients were complete and the ranks drifted apart (found on 2 B200s,
+    tools/dp_diag.py) — every rank must end each step with the same gradients and parameters."""
     world, steps = 2, 3
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, steps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, steps, q, sink)) for r in range(world)]
     for p in procs:
         p.start()
-    flats, X, Y = q.get(timeout=150)
+    flats, X, Y, grads = q.get(timeout=150)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     f0, f1 = torch.from_numpy(flats[0]), torch.from_numpy(flats[1])
+    assert torch.equal(torch.from_numpy(grads[0]), torch.from_numpy(grads[1])), "ranks hold different gradients after the exchange"
     assert torch.equal(f0, f1), "ranks diverged"
 
     # single process, global batch, torch.optim.Adam as the reference optimizer
-    model = _make()
+    model = _make(sink=sink)
     opt = torch.optim.Adam(model.parameters(), lr=1e-2)
     X, Y = torch.from_numpy(X), torch.from_numpy(Y)
     for s in range(steps):
@@ -103,9 +154,9 @@ def test_two_rank_training_matches_single_process():
         opt.step()
     ref = torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad and p.grad is not None])
     # compare parameter by parameter through the flat offsets (the unused head must be untouched)
-    single = training.FlatParams(list(_make().parameters()))
+    single = training.FlatParams(list(_make(sink=sink).parameters()))
     off = dict(zip([id(p) for p in single.params], single.offsets))
-    m2 = _make()
+    m2 = _make(sink=sink)
     for (name, p_ref), p_init in zip(model.named_parameters(), m2.parameters()):
         idx = [i for i, q_ in enumerate(m2.parameters()) if q_ is p_init][0]
         o = single.offsets[idx]

@@ -1,4 +1,4 @@
-"""GPU (NCCL, world_size 2, needs two B200s: `gpurun --gpus 2 -- python -m pytest tests/test_data_parallel_gpu.py -m gpu`):
+"""GPU (NCCL, world_size 2, needs two B200s: `gpurun --gpus 2 -- python -m pytest tests/test_z_data_parallel_gpu.py -m gpu`):
 the data-parallel train step on the real kernels — every rank takes its slice of the same global batch, the bucketed
 gradient all-reduce runs on the side stream (eager) or inside the captured step graph (graph=True) — against a
 single-process run on the whole batch ("1-GPU vs N-GPU gradient equality on the same global batch").
