@@ -7,6 +7,7 @@ the whole step is CUDA-graph capturable.  No op has a PyTorch or CPU fallback.
 from __future__ import annotations
 
 import contextlib
+import weakref
 import threading
 from typing import Optional, Tuple
 
@@ -179,21 +180,33 @@ def rng_advance(device=None) -> None:
 
 # ---- compute-dtype copies of the fp32 master weights ---------------------------------------
 _wcache = {}
+_wepoch = [0]
 
 
 def clear_weight_cache() -> None:
     _wcache.clear()
 
 
+def weights_changed() -> None:
+    """Parameters were updated behind torch's back (the fused Adam kernel writes the flat buffer through raw
+    pointers, a graph replay does so without running any Python): their version counters did not move, so every
+    cached compute-dtype copy is stale from now on."""
+    _wepoch[0] += 1
+
+
 def compute_weight(w: torch.Tensor, dtype: torch.dtype, need_t: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """(W, Wᵀ) in the compute dtype.  fp32 mode uses the parameter itself.  bf16 copies are cached per
-    parameter version (optimizer steps bump it), so eval loops cast once."""
+    parameter version (torch optimizers bump it; `weights_changed()` covers updates torch does not see), so eval
+    loops cast once.  An entry belongs to ONE tensor object
+    (weak reference): a new model whose fresh parameter lands on a freed parameter's address with the same
+    version counter must not pick up the old model's copy."""
     if dtype == torch.float32:
         return (w if w.is_contiguous() else w.contiguous()), None
     key = (w.data_ptr(), tuple(w.shape), dtype)
     ent = _wcache.get(key)
     ver = w._version
-    if ent is not None and ent[0] == ver and (ent[2] is not None or not need_t) and not torch.cuda.is_current_stream_capturing():
+    if ent is not None and ent[0] == ver and ent[3]() is w and ent[4] == _wepoch[0] and (ent[2] is not None or not need_t) \
+            and not torch.cuda.is_current_stream_capturing():
         return ent[1], ent[2]
     src = w.detach()
     if not src.is_contiguous():
@@ -202,7 +215,7 @@ def compute_weight(w: torch.Tensor, dtype: torch.dtype, need_t: bool) -> Tuple[t
     wc = torch.empty((N, K), dtype=dtype, device=w.device)
     wt = torch.empty((K, N), dtype=dtype, device=w.device) if need_t else None
     call("mar_cast_weight", src.data_ptr(), wc.data_ptr(), _p(wt), N, K, _dt(wc), _stream())
-    _wcache[key] = (ver, wc, wt)
+    _wcache[key] = (ver, wc, wt, weakref.ref(w), _wepoch[0])
     return wc, wt
 
 

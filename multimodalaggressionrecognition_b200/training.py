@@ -73,6 +73,7 @@ class FlatAdam:
             call("mar_adam_step", f.flat.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
                  self.exp_avg_sq.data_ptr(), self.step_dev.data_ptr(), f.numel, self.lr, self.betas[0], self.betas[1],
                  self.eps, st)
+            ops.weights_changed()      # raw-pointer update: torch's version counters did not move
         else:  # host-side logic tests (gloo, no GPU): same arithmetic in torch
             self.step_dev += 1
             t = float(self.step_dev)
@@ -358,6 +359,7 @@ class TrainStep:
             cur["static_pred"] = self.last_pred     # this graph's own logits buffers
             cur["graph"] = g                        # capture records but does not execute: fall through to replay
         cur["graph"].replay()
+        ops.weights_changed()                       # the replay's Adam ran without any Python: cached bf16 copies are stale
         self.last_pred = cur["static_pred"]         # valid until this buffer set's next replay (two steps later)
         if cur["done"] is None:
             cur["done"] = torch.cuda.Event()

@@ -103,13 +103,10 @@ def _worker(rank, world, port, steps, result_q, sink=False):
         g = torch.Generator().manual_seed(123)
         X = torch.randn(steps, 8 * world, 16, generator=g)
         Y = torch.randint(0, 2, (steps, 8 * world), generator=g)
-        orders = []
         for s in range(steps):
             xs, ys = X[s, rank * 8:(rank + 1) * 8], Y[s, rank * 8:(rank + 1) * 8]
-            # peek at the bucket launch order of this step
             losses = step(xs, ys)
             assert set(losses) == {"a", "b"}
-            orders.append(list(step.sync.order))      # reset by finish(): empty here; launch order is checked through the result
         flat = step.flat.flat.detach().clone()
         gathered = [torch.zeros_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)

@@ -101,3 +101,39 @@ def test_two_gpu_step_matches_single_gpu_on_the_global_batch(graph):
             # same bar as the eager-vs-graph test: reduction order differs (two 8-clip gradients averaged by NCCL
             # instead of one 16-clip gradient), Adam amplifies that to a few 1e-4 over the steps
             assert abs(got - v) <= 2e-3 * max(1.0, abs(v)), f"step {s} loss[{k}]: {world} GPUs {got} vs single GPU {v}"
+
+
+def test_eager_bf16_train_step_sees_its_own_weight_updates():
+    """The fused Adam kernel updates the flat parameter buffer through raw pointers, which torch's version counters
+    do not see; the cached bf16 copies of the weights must still be refreshed every step (ops.weights_changed).
+    An eager bf16 TrainStep on a repeated batch is compared with the same loop driven by torch.optim.Adam (whose
+    in-place updates bump the versions): with stale copies the forward would never see an update."""
+    dev = torch.device("cuda", 0)
+    data, labels = W.batch_c3(B=8, seed=700, **KW)
+    data, labels = W.to_device(data, dev), W.to_device(labels, dev)
+    import multimodalaggressionrecognition_b200 as mar
+    ref_model = _model(dev)
+    opt = torch.optim.Adam(ref_model.parameters(), lr=1e-3)
+    crit = _crit()
+    ref_curve = []
+    with mar.precision("bf16"):
+        for _ in range(5):
+            opt.zero_grad()
+            losses = crit(ref_model(data), labels)
+            losses.backward()
+            opt.step()
+            ref_curve.append({k: float(v) for k, v in losses.items()})
+    step = training.TrainStep(_model(dev), _crit(), lr=1e-3, graph=False, precision="bf16")
+    curve = [{k: float(v) for k, v in step(data, labels).items()} for _ in range(5)]
+    assert max(abs(curve[-1][k] - curve[0][k]) for k in curve[0]) > 1e-2, "the loss never moved: stale weights"
+    for s, (a, b) in enumerate(zip(curve, ref_curve)):
+        for k in b:
+            assert abs(a[k] - b[k]) <= 5e-2 * max(1.0, abs(b[k])), f"step {s} loss[{k}]: TrainStep {a[k]} vs torch.optim.Adam loop {b[k]}"
+    # and an eval pass after training uses the trained weights, not a copy cast some steps ago
+    m = step.model.eval()
+    with torch.no_grad(), mar.precision("bf16"):
+        a = m(data)
+        from multimodalaggressionrecognition_b200 import ops
+        ops.clear_weight_cache()
+        b = m(data)
+    assert all(torch.equal(a[k], b[k]) for k in a)
