@@ -100,6 +100,34 @@ def _worker(rank, world, port, steps, result_q, sink=False):
         model = _make(sink=sink)
         step = training.TrainStep(model, _criterion, lr=1e-2, num_buckets=1 if sink else 3)
         assert step.sync.world == world and len(step.sync.buckets) >= (1 if sink else 2)
+        comm = None
+        if sink == "streams":
+            # Run GradSync's CUDA branch (side communication stream) without a GPU: fake stream objects that record
+            # who waited for whom, gradients "written" alternately on two compute streams, and gloo's missing AVG
+            # expressed as SUM / world.
+            import contextlib
+
+            class FakeStream:
+                def __init__(self, handle):
+                    self.cuda_stream, self.waited = handle, []
+
+                def wait_stream(self, other):
+                    self.waited.append(other.cuda_stream)
+
+            comm, compute, turn = FakeStream(99), [FakeStream(1), FakeStream(2)], [0]
+
+            def current_stream(*_a):
+                turn[0] += 1
+                return compute[turn[0] & 1]
+            torch.cuda.current_stream = current_stream
+            torch.cuda.stream = lambda _s: contextlib.nullcontext()
+            real_all_reduce = dist.all_reduce
+
+            def all_reduce(t, op=None, group=None):
+                real_all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                t.div_(world)
+            training.dist.all_reduce = all_reduce
+            step.sync.comm_stream = comm
         g = torch.Generator().manual_seed(123)
         X = torch.randn(steps, 8 * world, 16, generator=g)
         Y = torch.randint(0, 2, (steps, 8 * world), generator=g)
@@ -112,6 +140,10 @@ def _worker(rank, world, port, steps, result_q, sink=False):
         dist.all_gather(gathered, flat)
         grads = [torch.zeros_like(flat) for _ in range(world)]
         dist.all_gather(grads, step.flat.grad.detach().clone())     # the last step's gradients, after the exchange
+        if comm is not None:
+            # every launch waited for BOTH streams gradients of the bucket were written on, and finish() joined
+            assert {1, 2} <= set(comm.waited), comm.waited
+            assert any(99 in c.waited for c in compute)
         if rank == 0:
             result_q.put(([g.numpy() for g in gathered], X.numpy(), Y.numpy(), [g.numpy() for g in grads]))
     finally:
@@ -119,12 +151,13 @@ def _worker(rank, world, port, steps, result_q, sink=False):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("sink", [False, True])
+@pytest.mark.parametrize("sink", [False, True, "streams"])
 def test_two_rank_training_matches_single_process(sink):
     """sink=True: parameters whose gradient is written by a kernel straight into the flat buffer (ops.grad_sink) are
     counted through GradSync.notify AND torch fires their post-accumulate hook as well; counting both launched a
     bucket's all-reduce before its gradients were complete and the ranks drifted apart (found on 2 B200s,
-    tools/dp_diag.py) — every rank must end each step with the same gradients and parameters."""
+    tools/dp_diag.py) — every rank must end each step with the same gradients and parameters.
+    sink="streams": the same through GradSync's side-stream branch, with recording fake streams."""
     world, steps = 2, 3
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -85,3 +85,38 @@ def test_epoch_accumulator_reproduces_the_reference_trainers(name):
             same(got[h], ref[h], f"{name}/{h}")
     acc.reset()
     assert acc.results(1) == {}
+
+
+def test_weight_cache_invalidation(monkeypatch):
+    """ops.compute_weight's cache of bf16 weight copies (host logic; the cast kernel is stubbed out): one cast per
+    parameter version, a new cast after an update torch cannot see (the fused Adam kernel / a graph replay call
+    ops.weights_changed), after a torch in-place update, and for ANOTHER tensor object on the same address."""
+    casts = []
+    monkeypatch.setattr(ops, "call", lambda name, *a: casts.append(name))
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    ops.clear_weight_cache()
+    w = nn.Parameter(torch.randn(4, 3))
+    a = ops.compute_weight(w, torch.bfloat16, True)
+    b = ops.compute_weight(w, torch.bfloat16, True)
+    assert a[0] is b[0] and a[1] is b[1] and casts == ["mar_cast_weight"]
+    ops.weights_changed()
+    c = ops.compute_weight(w, torch.bfloat16, True)
+    assert c[0] is not a[0] and len(casts) == 2
+    with torch.no_grad():
+        w.add_(1.0)                                             # torch.optim.Adam's kind of update
+    ops.compute_weight(w, torch.bfloat16, True)
+    assert len(casts) == 3
+    w2 = nn.Parameter(w.data)                                   # a fresh parameter on the same address and shape
+    assert w2.data_ptr() == w.data_ptr()
+    ops.compute_weight(w2, torch.bfloat16, True)
+    assert len(casts) == 4
+    assert ops.compute_weight(w, torch.float32, True)[0] is w and len(casts) == 4      # fp32 mode: the parameter itself
+    ops.clear_weight_cache()
+
+
+def test_flat_adam_cuda_branch_marks_weights_changed():
+    """training.FlatAdam / TrainStep replay call ops.weights_changed (source-level check: the CUDA branches cannot run here)."""
+    import inspect
+    assert "ops.weights_changed()" in inspect.getsource(training.FlatAdam.step)
+    assert "ops.weights_changed()" in inspect.getsource(training.TrainStep._graphed)
