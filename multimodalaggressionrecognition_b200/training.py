@@ -214,6 +214,11 @@ class TrainStep:
         self.flat = FlatParams(list(model.parameters()))
         self.opt = FlatAdam(self.flat, lr=lr)
         self.sync = GradSync(self.flat, group=group, num_buckets=num_buckets)
+        if self.sync.world > 1 and self.flat.flat.is_cuda and ops._rng.seed is None:
+            # every rank seeds torch identically (same initial weights), which would also give every rank the SAME
+            # dropout masks for its different clips; a single process on the global batch draws independent masks per
+            # clip, so each rank gets its own mask stream unless the caller seeded ops.manual_seed() itself
+            ops.manual_seed((torch.initial_seed() + 0x9E3779B97F4A7C15 * dist.get_rank(group)) & 0x7FFFFFFFFFFFFFFF)
         self.use_graph = graph
         self.precision = precision
         # captured graphs are keyed by the batch SIGNATURE: tensor shapes/dtypes AND the non-tensor leaves (the
