@@ -104,3 +104,11 @@ def test_unsupported_layer_config_is_refused():
     enc = nn.TransformerEncoder(nn.TransformerEncoderLayer(64, 4, batch_first=True, norm_first=True), 1)
     with pytest.raises(NotImplementedError):
         M._check_layer(enc.layers[0])
+
+
+def test_audio_multi_nn_structure():
+    heads = W.build_c2(M, heads=("GRU_1L", "LSTM_1L")).models_dict
+    m = M.AudioMultiNN({k: v for k, v in heads.items()}, {"w2v": nn.Identity()})
+    assert m.get_models_names() == (["w2v"], ["GRU_1L", "LSTM_1L"])
+    assert not m.extractor_dict.training                      # the reference freezes the extractor at construction
+    assert str(pickle.loads(pickle.dumps(m))) == str(m)

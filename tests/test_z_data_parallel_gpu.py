@@ -137,3 +137,35 @@ def test_eager_bf16_train_step_sees_its_own_weight_updates():
         ops.clear_weight_cache()
         b = m(data)
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_audio_multi_nn_runs_its_heads_on_the_frozen_extractor_output():
+    """AudioMultiNN (models.py:198-223): frozen extractor(s) under no_grad, then every head on the extracted features —
+    the same heads through VideoMultiNN on those features give the same logits, and only the heads receive gradients."""
+    import multimodalaggressionrecognition_b200 as mar
+
+    class Scale(torch.nn.Module):                 # stands in for the out-of-scope wav2vec front end
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(0.5))
+
+        def forward(self, x):
+            return x * self.w
+
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    heads = W.build_c2(M, d=512, heads=("GRU_1L", "Avg_features")).models_dict
+    audio = M.AudioMultiNN({k: v for k, v in heads.items()}, {"ext": Scale()}).to(dev).eval()
+    video = M.VideoMultiNN({k: v for k, v in heads.items()}).to(dev).eval()
+    assert audio.get_models_names() == (["ext"], ["GRU_1L", "Avg_features"])
+    x, _ = W.batch_c2(B=4, T=6)
+    x = x.to(dev)
+    with mar.precision("fp32"):
+        with torch.no_grad():
+            a, v = audio(x), video(x * 0.5)
+        for k in v:
+            assert torch.allclose(a[k], v[k], rtol=1e-5, atol=1e-6), k
+        audio.train()
+        sum(t.sum() for t in audio(x).values()).backward()
+    assert audio.extractor_dict["ext"].w.grad is None
+    assert all(p.grad is not None for p in audio.models_dict.parameters())
