@@ -5,6 +5,8 @@ build container only) and pin the CPU oracle against them.
     python oracle/make_golden.py v2         # writes tests/golden/golden_v2.pt: the script's other assemblies (text
                                             # branch with ragged zero padding, averaged fusion, base classifier heads,
                                             # the older MultimodalModel, AudioTextualModel, class-weighted CE)
+    python oracle/make_golden.py alternating  # writes tests/golden/golden_alternating.pt: 10 Adam steps over alternating
+                                            # full / verb-only / phys-only batches (Adam skips inactive parameters)
     python oracle/make_golden.py c1_epoch   # writes tests/golden/golden_c1_epoch.pt: BASELINE config 1 at full size,
                                             # "1 epoch" = 48 Adam steps over 48 different batches (loss curve, predictions)
 
@@ -311,6 +313,60 @@ def main_c1_epoch():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+ALTERNATING = ["full", "video", "audio", "full", "video", "video", "audio", "full", "audio", "full"]
+
+
+def main_alternating():
+    """The reference's NORMAL regime: `AggrBatchSampler` (datasets.py:630-645) makes every batch homogeneous in
+    aggression type, so verb-only batches (video EMPTY, no phys loss) and phys-only batches (audio EMPTY, no verb
+    loss) alternate with full ones.  A head / branch that is inactive in a step has `.grad is None` after
+    `zero_grad()` and torch.optim.Adam skips it — no moment decay, no step-count increment.  10 Adam steps of the
+    small C3 model through the LIVE reference over such a stream (dropout off); the oracle trainer must follow."""
+    kw = dict(t_audio=50, t_video=16)
+    spec = dict(builder="build_c3", bkw=kw, batch="batch_c3", dkw={})
+    torch.manual_seed(INIT_SEED)
+    model = W.perturb_norms(W.disable_dropout(W.build_c3(ref, **kw))).train()
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam(model.parameters())
+    tr = O.OracleTrainer(sd0, lambda sd, d, t: oracle_forward(spec, sd, d, t, True), lambda p, t: oracle_loss(spec, p, t))
+    curve, worst = [], 0.0
+    for i, kind in enumerate(ALTERNATING):
+        batch = W.batch_c3(B=6, seed=3000 + i, empty=None if kind == "full" else kind, **kw)
+        opt.zero_grad()
+        _, losses = ref_loss(spec, model, batch)
+        losses.backward()
+        opt.step()
+        step = {k: float(v.detach()) for k, v in losses.items()}
+        got = tr.step(batch[0], batch[1], training=True)
+        assert set(got) == set(step), (i, kind, set(got), set(step))
+        worst = max([worst] + [abs(got[k] - v) for k, v in step.items()])
+        curve.append(step)
+        print(f"  step {i} ({kind:5s}): reference {step}  oracle {got}", flush=True)
+    final = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    # parameters: compare the UPDATE (final - initial) in norm.  Element-wise agreement is not defined: Adam divides
+    # by sqrt(v), so a component whose gradient is rounding noise (the key third of every in_proj_bias has an
+    # identically zero true gradient; weights fed by a ReLU-dead unit) moves by up to lr per step in a direction that
+    # differs between any two implementations, and no output depends on it (the losses agree to 1e-7).
+    num = den = 0.0
+    for k, v in final.items():
+        du_ref = (v - sd0[k]).double()
+        du_orc = (tr.sd[k].detach() - sd0[k]).double()
+        num += float((du_orc - du_ref).pow(2).sum())
+        den += float(du_ref.pow(2).sum())
+    pdev = (num / den) ** 0.5
+    print(f"  oracle vs reference over the stream: max |loss diff| {worst:.3e}, relative error of the parameter update {pdev:.3e}")
+    assert worst < 1e-4 and pdev < 5e-3
+    keep = ["classifiers.classifiers_dict.phys.3.bias", "classifiers.classifiers_dict.verb.3.bias",
+            "modality_extractors_dict.video.feature_extractor.embedding.0.bias",
+            "modality_fusion_module.modality_fusion_transformer.norm.bias"]
+    out = {"torch": torch.__version__, "init_seed": INIT_SEED, "kw": kw, "B": 6, "seed0": 3000, "pattern": ALTERNATING,
+           "weights_checksum": weights_checksum(sd0), "loss_curve": curve,
+           "final_params": {k: final[k] for k in keep}, "final_checksum": weights_checksum(final)}
+    path = os.path.join(ROOT, "tests", "golden", "golden_alternating.pt")
+    torch.save(out, path)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "v1"
-    {"v1": main_v1, "v2": main_v2, "c1_epoch": main_c1_epoch}[which]()
+    {"v1": main_v1, "v2": main_v2, "c1_epoch": main_c1_epoch, "alternating": main_alternating}[which]()

@@ -223,17 +223,22 @@ def focal_loss(logits: Tensor, labels: Tensor, alpha: Optional[Tensor] = None, g
 
 
 def adam_step(params: List[Tensor], grads: List[Optional[Tensor]], exp_avg: List[Tensor],
-              exp_avg_sq: List[Tensor], step: int, lr: float = 1e-3, beta1: float = 0.9,
+              exp_avg_sq: List[Tensor], step, lr: float = 1e-3, beta1: float = 0.9,
               beta2: float = 0.999, eps: float = 1e-8) -> None:
     """torch.optim.Adam defaults, no weight decay (train_multimodal.py:444):
     m=β1 m+(1-β1)g ; v=β2 v+(1-β2)g² ; p -= lr/(1-β1^t) · m / (sqrt(v)/sqrt(1-β2^t) + eps).
-    Parameters whose grad is None are skipped (as torch does)."""
-    bc1 = 1.0 - beta1 ** step
-    bc2 = 1.0 - beta2 ** step
+    Parameters whose grad is None are skipped entirely, as torch does (torch/optim/adam.py `_init_group`: only
+    parameters with a gradient enter the update) — and t is PER PARAMETER (torch keeps `state['step']` per
+    parameter and increments it only when the parameter is updated): the reference's batches are homogeneous in
+    aggression type (datasets.py:630-645), so a head, or a whole modality branch, sits out every other step.
+    `step`: one int for all parameters, or a list with each parameter's own update count (this update included)."""
+    steps = step if isinstance(step, (list, tuple)) else [step] * len(params)
     with torch.no_grad():
-        for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        for p, g, m, v, t in zip(params, grads, exp_avg, exp_avg_sq, steps):
             if g is None:
                 continue
+            bc1 = 1.0 - beta1 ** t
+            bc2 = 1.0 - beta2 ** t
             m.mul_(beta1).add_(g, alpha=1.0 - beta1)
             v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
             denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
@@ -437,6 +442,7 @@ class OracleTrainer:
         self.m = {k: torch.zeros_like(v) for k, v in self.sd.items()}
         self.v = {k: torch.zeros_like(v) for k, v in self.sd.items()}
         self.t = 0
+        self.steps = {k: 0 for k in self.sd}          # torch.optim.Adam's per-parameter state['step']
 
     def step(self, data, target, training: bool = True) -> Dict[str, float]:
         for p in self.sd.values():
@@ -448,6 +454,9 @@ class OracleTrainer:
             l.backward(retain_graph=i != len(items) - 1)
         self.t += 1
         keys = list(self.sd)
+        for k in keys:
+            if self.sd[k].grad is not None:
+                self.steps[k] += 1
         adam_step([self.sd[k] for k in keys], [self.sd[k].grad for k in keys],
-                  [self.m[k] for k in keys], [self.v[k] for k in keys], self.t, self.lr)
+                  [self.m[k] for k in keys], [self.v[k] for k in keys], [self.steps[k] for k in keys], self.lr)
         return {k: float(v.detach()) for k, v in items}

@@ -40,3 +40,9 @@ def _built_library():
         import __graft_entry__ as g
         g.build()
     yield
+
+
+@pytest.fixture(scope="session")
+def golden_alternating():
+    import torch
+    return torch.load(os.path.join(ROOT, "tests", "golden", "golden_alternating.pt"), weights_only=False)

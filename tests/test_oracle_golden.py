@@ -91,6 +91,33 @@ def test_oracle_c1_epoch_first_steps(golden_c1_epoch):
         assert abs(got - g["loss_curve"][i]) <= 1e-4, f"step {i}: oracle {got} vs reference {g['loss_curve'][i]}"
 
 
+def test_oracle_alternating_batches(golden_alternating):
+    """The reference's normal regime — full / verb-only / phys-only batches in turn (AggrBatchSampler makes batches
+    homogeneous in aggression type): torch.optim.Adam skips the parameters of an inactive head or branch and keeps a
+    step count PER PARAMETER.  10 steps recorded from the live reference (`make_golden.py alternating`); an Adam with
+    one global step count is 3e-2 off on this curve."""
+    from multimodalaggressionrecognition_b200 import workloads as W
+    g = golden_alternating
+    kw = g["kw"]
+    spec = dict(builder="build_c3", bkw=kw)
+    torch.manual_seed(g["init_seed"])
+    model = W.perturb_norms(W.disable_dropout(W.build_c3(mine, **kw)))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    tr = O.OracleTrainer(sd, lambda s, d, t: H.oracle_forward(spec, s, d, t, True), lambda p, t: H.oracle_losses(spec, p, t))
+    for i, kind in enumerate(g["pattern"]):
+        data, labels = W.batch_c3(B=g["B"], seed=g["seed0"] + i, empty=None if kind == "full" else kind, **kw)
+        got = tr.step(data, labels, training=True)
+        assert set(got) == set(g["loss_curve"][i])
+        for k, v in g["loss_curve"][i].items():
+            assert abs(got[k] - v) <= 1e-5, f"step {i} ({kind}) {k}: oracle {got[k]} vs reference {v}"
+    for k, v in g["final_params"].items():
+        H.assert_close(tr.sd[k].detach(), v, 1e-4, f"final {k}")
+    # an inactive head stood still: its per-parameter step count is the number of batches it saw
+    assert tr.steps["classifiers.classifiers_dict.phys.3.bias"] == sum(k != "video" for k in g["pattern"])
+    assert tr.steps["classifiers.classifiers_dict.verb.3.bias"] == sum(k != "audio" for k in g["pattern"])
+    assert tr.steps["modality_fusion_module.modality_fusion_transformer.norm.bias"] == len(g["pattern"])
+
+
 def test_adam_matches_torch():
     torch.manual_seed(0)
     p0 = torch.randn(1000)

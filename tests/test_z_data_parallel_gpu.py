@@ -169,3 +169,33 @@ def test_audio_multi_nn_runs_its_heads_on_the_frozen_extractor_output():
         sum(t.sum() for t in audio(x).values()).backward()
     assert audio.extractor_dict["ext"].w.grad is None
     assert all(p.grad is not None for p in audio.models_dict.parameters())
+
+
+def test_alternating_batches_with_torch_adam(golden_alternating):
+    """The reference's normal regime (full / verb-only / phys-only batches in turn, tests/golden/golden_alternating.pt
+    from the live reference): the drop-in modules under torch.optim.Adam — the reference's own trainer loop — leave
+    the parameters of an inactive head or branch without a gradient, so Adam skips them exactly as it does for the
+    reference; fp32 mode follows the recorded curve."""
+    import multimodalaggressionrecognition_b200 as mar
+    g = golden_alternating
+    kw = g["kw"]
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(g["init_seed"])
+    model = W.perturb_norms(W.disable_dropout(W.build_c3(M, **kw))).to(dev).train()
+    opt = torch.optim.Adam(model.parameters())
+    crit = _crit()
+    with mar.precision("fp32"):
+        for i, kind in enumerate(g["pattern"]):
+            data, labels = W.batch_c3(B=g["B"], seed=g["seed0"] + i, empty=None if kind == "full" else kind, **kw)
+            opt.zero_grad()
+            losses = crit(model(W.to_device(data, dev)), W.to_device(labels, dev))
+            losses.backward()
+            if kind == "video":          # verb-only batch: nothing reaches the phys head or the video branch
+                assert model.classifiers.classifiers_dict["phys"][3].bias.grad is None
+                assert model.modality_extractors_dict["video"].feature_extractor.embedding[0].weight.grad is None
+            if kind == "audio":
+                assert model.classifiers.classifiers_dict["verb"][3].bias.grad is None
+            opt.step()
+            assert set(losses) == set(g["loss_curve"][i])
+            for k, v in g["loss_curve"][i].items():
+                assert abs(float(losses[k]) - v) <= 1e-3 * max(1.0, abs(v)), f"step {i} ({kind}) {k}: {float(losses[k])} vs {v}"
