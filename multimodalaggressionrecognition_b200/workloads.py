@@ -221,6 +221,24 @@ def batch_audio_text(B: int = 4, t_audio: int = 50, t_text: int = 48, d: int = 7
     return [[('audio',) * B, audio], [('text',) * B, text]], torch.randint(0, 2, (B,), generator=g)
 
 
+def batch_c3_mixed(B: int = 6, t_audio: int = 250, t_video: int = 64, seed: int = 1000, no_video=(1, 4), no_audio=(2,)):
+    """A NON-homogeneous batch (the reference's sampler never builds one, its model and loss handle it row by row,
+    models.py:840-860, :244-258): clips `no_video` lack the video modality and their phys label, clips `no_audio`
+    lack audio and their verb label."""
+    data, labels = batch_c3(B=B, t_audio=t_audio, t_video=t_video, seed=seed)
+    names = {m: list(n) for m, (n, _) in zip(("audio", "video"), data)}
+    lab = {m: list(n) for m, (n, _) in zip(("verb", "phys"), labels)}
+    for i in no_video:
+        names["video"][i] = "video_EMPTY"; data[1][1][i] = -1.0
+        lab["phys"][i] = "phys_EMPTY"; labels[1][1][i] = -1
+    for i in no_audio:
+        names["audio"][i] = "audio_EMPTY"; data[0][1][i] = -1.0
+        lab["verb"][i] = "verb_EMPTY"; labels[0][1][i] = -1
+    data = [[tuple(names["audio"]), data[0][1]], [tuple(names["video"]), data[1][1]]]
+    labels = [[tuple(lab["verb"]), labels[0][1]], [tuple(lab["phys"]), labels[1][1]]]
+    return data, labels
+
+
 def to_device(batch, device):
     """Move a (nested list) batch to the device, as datasets.py does at construction (datasets.py:493-561)."""
     if isinstance(batch, torch.Tensor):

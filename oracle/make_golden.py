@@ -5,6 +5,7 @@ build container only) and pin the CPU oracle against them.
     python oracle/make_golden.py v2         # writes tests/golden/golden_v2.pt: the script's other assemblies (text
                                             # branch with ragged zero padding, averaged fusion, base classifier heads,
                                             # the older MultimodalModel, AudioTextualModel, class-weighted CE)
+    python oracle/make_golden.py v3         # writes tests/golden/golden_v3.pt: a batch whose rows lack different modalities
     python oracle/make_golden.py alternating  # writes tests/golden/golden_alternating.pt: 10 Adam steps over alternating
                                             # full / verb-only / phys-only batches (Adam skips inactive parameters)
     python oracle/make_golden.py c1_epoch   # writes tests/golden/golden_c1_epoch.pt: BASELINE config 1 at full size,
@@ -72,6 +73,12 @@ CASES_V2 = {
     "c3_weighted_ce": dict(builder="build_c3", bkw=dict(t_audio=50, t_video=16), batch="batch_c3",
                            dkw=dict(B=6, t_audio=50, t_video=16), ce_weights={"phys": [0.3, 1.7], "verb": [1.25, 0.6]}),
     "audio_text_model": dict(builder="build_audio_text", bkw={}, batch="batch_audio_text", dkw=dict(B=4, t_audio=30, t_text=12)),
+}
+CASES_V3 = {
+    # rows of one batch lack different modalities / labels: extractor on the present rows only, scatter into the zero
+    # stub, per-row loss filtering (models.py:840-860, :244-258)
+    "c3_mixed_rows": dict(builder="build_c3", bkw=dict(t_audio=50, t_video=16), batch="batch_c3_mixed",
+                          dkw=dict(B=6, t_audio=50, t_video=16)),
 }
 FULL_GRADS = {
     "build_c1": ["1.classifier.4.weight", "0.transformer_squence_processing.norm.weight",
@@ -271,6 +278,13 @@ def main_v2():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main_v3():
+    golden = {"torch": torch.__version__, "cases": {name: run_case(name, spec) for name, spec in CASES_V3.items()}}
+    path = os.path.join(ROOT, "tests", "golden", "golden_v3.pt")
+    torch.save(golden, path)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 C1_EPOCH_STEPS = 48     # "1 epoch" := 48 steps of 32 clips (1 536 clips, train_names.txt holds 1 539)
 
 
@@ -369,4 +383,4 @@ def main_alternating():
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "v1"
-    {"v1": main_v1, "v2": main_v2, "c1_epoch": main_c1_epoch, "alternating": main_alternating}[which]()
+    {"v1": main_v1, "v2": main_v2, "v3": main_v3, "c1_epoch": main_c1_epoch, "alternating": main_alternating}[which]()

@@ -22,6 +22,10 @@ def golden():
     assert not set(g["cases"]) & set(g2["cases"])
     g["cases"].update(g2["cases"])
     g["module_trees"] = g2["module_trees"]
+    # golden_v3: a batch whose rows lack different modalities — `python oracle/make_golden.py v3`
+    g3 = torch.load(os.path.join(ROOT, "tests", "golden", "golden_v3.pt"), weights_only=False)
+    assert not set(g["cases"]) & set(g3["cases"])
+    g["cases"].update(g3["cases"])
     return g
 
 

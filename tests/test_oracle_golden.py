@@ -11,6 +11,7 @@ CASES = ["c1_small", "c1_odd", "c2_small", "c3_small", "c3_video_empty", "c3_aud
 CASES_V2 = ["c3x_audio_text_ragged", "c3x_three_modalities", "c3x_three_video_empty", "c3x_avg_fusion",
             "c3x_avg_fusion_video_empty", "c3x_base_classifier", "c3x_old_multimodal_model", "c3_weighted_ce",
             "audio_text_model"]
+CASES_V3 = ["c3_mixed_rows"]
 
 
 @pytest.fixture(autouse=True)
@@ -21,7 +22,7 @@ def _no_dropout():
     O.DROPOUT_ENABLED = old
 
 
-@pytest.mark.parametrize("name", CASES + CASES_V2)
+@pytest.mark.parametrize("name", CASES + CASES_V2 + CASES_V3)
 def test_oracle_matches_reference_golden(golden, name):
     case = golden["cases"][name]
     spec = case["spec"]

@@ -199,3 +199,16 @@ def test_alternating_batches_with_torch_adam(golden_alternating):
             assert set(losses) == set(g["loss_curve"][i])
             for k, v in g["loss_curve"][i].items():
                 assert abs(float(losses[k]) - v) <= 1e-3 * max(1.0, abs(v)), f"step {i} ({kind}) {k}: {float(losses[k])} vs {v}"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_golden_parity_mixed_rows(golden, mode):
+    """golden_v3 `c3_mixed_rows` (rows of one batch lack different modalities and labels: extractor on the present rows,
+    scatter into the zero stub, per-row loss filtering) through the same checks as tests/test_models_gpu.py's golden
+    parity test.  Written after the round's GPU budget was spent: first run on B200 is the round-end run."""
+    from multimodalaggressionrecognition_b200 import ops
+    from oracle import oracle as O
+    from tests.test_models_gpu import test_golden_parity
+    O.DROPOUT_ENABLED = False
+    ops.clear_weight_cache()
+    test_golden_parity(golden, "c3_mixed_rows", mode)
