@@ -1,8 +1,14 @@
-"""GPU (NCCL, world_size 2, needs two B200s: `gpurun --gpus 2 -- python -m pytest tests/test_z_data_parallel_gpu.py -m gpu`):
-the data-parallel train step on the real kernels — every rank takes its slice of the same global batch, the bucketed
-gradient all-reduce runs on the side stream (eager) or inside the captured step graph (graph=True) — against a
-single-process run on the whole batch ("1-GPU vs N-GPU gradient equality on the same global batch").
-Skipped on a one-GPU box; tests/test_data_parallel_cpu.py covers the same host logic with gloo."""
+"""GPU tests added at the end of round 1, after the round's GPU budget was spent (their first run on B200 is the
+round-end run; the file sorts last so that `pytest -x` reaches every verified test first):
+
+* NCCL, world_size 2, needs two B200s (`gpurun --gpus 2 -- python -m pytest tests/test_z_data_parallel_gpu.py -m gpu`):
+  the data-parallel train step on the real kernels — every rank takes its slice of the same global batch, the bucketed
+  gradient all-reduce runs on the side stream (eager) or inside the captured step graph (graph=True) — against a
+  single-process run on the whole batch ("1-GPU vs N-GPU gradient equality on the same global batch").
+  Skipped on a one-GPU box; tests/test_data_parallel_cpu.py covers the same host logic with gloo.  Its first run (before
+  the GradSync fix) is what found the double count of sunk gradients.
+* one GPU: the eager bf16 TrainStep sees its own weight updates (weight-cache invalidation), AudioMultiNN, the
+  reference's alternating full / verb-only / phys-only batch regime under torch.optim.Adam, golden_v3's mixed rows."""
 import os
 import socket
 
