@@ -249,7 +249,14 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
 
+    # ---- data-parallel proof: every rank holds bit-identical parameters after the timed steps --------------------
+    ranks_identical = None
     if world > 1:
+        bits = step.flat.flat.view(torch.int32)
+        digest = torch.stack([bits.sum(dtype=torch.int64), (bits[::7].to(torch.int64) * 31).sum(), bits.to(torch.int64).abs().max()])
+        gathered = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(gathered, digest)
+        ranks_identical = all(torch.equal(gathered[0], g_) for g_ in gathered[1:])
         dist.barrier()
     if rank != 0:
         shutdown()
@@ -275,6 +282,7 @@ def run_ours(args):
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "ranks_identical": ranks_identical,
         "losses_last_step": loss_vals,
         "flops_per_clip_train": 3 * W.c3_flops_per_clip(T_AUDIO, T_VIDEO)["total"],
         "model_tflops": 3 * W.c3_flops_per_clip(T_AUDIO, T_VIDEO)["total"] * global_batch / (ms_dev / 1e3) / 1e12,

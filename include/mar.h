@@ -193,6 +193,21 @@ int mar_lstm_bwd(const void* dhseq, const float* saved, const void* w_hh, void* 
 int mar_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* step_dev,
                   int64_t n, float lr, float beta1, float beta2, float eps, void* stream);
 int mar_adam_tick(float* step_dev, void* stream);
+/* torch.optim.Adam as the reference drives it (train_multimodal.py:444 + trainer.py:140-150: zero_grad leaves the
+ * gradients of an inactive head / branch None, and its AggrBatchSampler makes every batch homogeneous in aggression
+ * type, datasets.py:630-645): a parameter WITHOUT a gradient this step is skipped — no moment decay, no update, no
+ * step-count increment — and every parameter carries its own step count.  One segment per parameter over the flat
+ * buffers; every segment starts on a multiple of `chunk` floats (a power of two); chunk_seg (n / chunk, int32) names
+ * the segment of each chunk (< 0: padding); seg_active (nseg fp32) > 0 marks the parameters that received a gradient;
+ * seg_steps (nseg fp32) are the per-parameter step counts (advanced here); seg_coef (2·nseg fp32, 8 B aligned) is
+ * scratch.  Two launches, graph-capturable. */
+int mar_adam_step_segments(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           const int32_t* chunk_seg, float* seg_steps, const float* seg_active, float* seg_coef,
+                           int64_t n, int chunk, int nseg, float lr, float beta1, float beta2, float eps, void* stream);
+/* out[0] = sum over rows with 0 <= label < C of class_weight[label] (1 per row when class_weight is NULL): the
+ * denominator of nn.CrossEntropyLoss(reduction='mean') (models.py:232-263).  Data-parallel ranks exchange it to weigh
+ * their gradients so that the reduced gradient is the one of the loss over the GLOBAL batch. */
+int mar_label_weight_sum(const int64_t* labels, const float* class_weight, float* out, int64_t B, int64_t C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -424,6 +424,64 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 __global__ void adam_tick_kernel(float* step_dev) { step_dev[0] += 1.f; }
 
+// ---- per-parameter Adam (torch.optim.Adam skips a parameter whose .grad is None: no moment decay, no step count) ----
+// One segment per parameter.  seg_active[s] > 0 ⇔ the parameter received a gradient this step.  The tick kernel
+// advances the step count of the active segments and leaves their bias-correction pair in seg_coef.
+__global__ void adam_seg_tick_kernel(float* __restrict__ seg_steps, const float* __restrict__ seg_active,
+                                     float2* __restrict__ seg_coef, int nseg, float lr, float b1, float b2) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  if (!(seg_active[s] > 0.f)) { seg_coef[s] = make_float2(0.f, 0.f); return; }
+  const float step = seg_steps[s] + 1.f;
+  seg_steps[s] = step;
+  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  seg_coef[s] = make_float2(lr / bc1, rsqrtf(bc2));       // x = step size, y = 1/sqrt(bias correction 2); x == 0 ⇔ skip
+}
+// chunk_seg[i / chunk]: segment of the chunk (every segment starts on a chunk boundary), < 0 for padding.
+__global__ void __launch_bounds__(256)
+adam_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                const int32_t* __restrict__ chunk_seg, const float2* __restrict__ seg_coef, int64_t n, int chunk_shift,
+                float b1, float b2, float eps) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const int seg = chunk_seg[i >> chunk_shift];
+  if (seg < 0) return;
+  const float2 coef = seg_coef[seg];
+  if (coef.x == 0.f) return;
+  float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
+  float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+  float* P = &pp.x; float* G = &gg.x; float* Mm = &mm.x; float* V = &vv.x;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    Mm[j] = b1 * Mm[j] + (1.f - b1) * G[j];
+    V[j] = b2 * V[j] + (1.f - b2) * G[j] * G[j];
+    P[j] -= coef.x * Mm[j] / (sqrtf(V[j]) * coef.y + eps);
+  }
+  *reinterpret_cast<float4*>(p + i) = pp;
+  *reinterpret_cast<float4*>(m + i) = mm;
+  *reinterpret_cast<float4*>(v + i) = vv;
+}
+
+// norm[0] = Σ_{rows with label >= 0} class_weight[label] (1 per row without weights): the denominator of
+// nn.CrossEntropyLoss(reduction='mean') — what a data-parallel rank needs from its peers to weigh its gradient.
+__global__ void label_weight_sum_kernel(const int64_t* __restrict__ labels, const float* __restrict__ w,
+                                        float* __restrict__ out, int64_t B, int64_t C) {
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+    const int64_t y = labels[i];
+    if (y >= 0 && y < C) acc += w ? w[y] : 1.f;
+  }
+  __shared__ float part[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = t;
+  }
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -573,6 +631,35 @@ int mar_adam_tick(float* step_dev, void* stream) {
   MAR_CHECK_ARG(step_dev, "mar_adam_tick: null");
   adam_tick_kernel<<<1, 1, 0, S(stream)>>>(step_dev);
   MAR_LAUNCH_CHECK("adam_tick");
+  return MAR_OK;
+}
+
+int mar_adam_step_segments(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           const int32_t* chunk_seg, float* seg_steps, const float* seg_active, float* seg_coef,
+                           int64_t n, int chunk, int nseg, float lr, float beta1, float beta2, float eps, void* stream) {
+  MAR_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && chunk_seg && seg_steps && seg_active && seg_coef && n >= 0 &&
+                    nseg > 0, "mar_adam_step_segments: bad arguments");
+  MAR_CHECK_ARG(chunk >= 4 && (chunk & (chunk - 1)) == 0, "mar_adam_step_segments: chunk must be a power of two >= 4");
+  MAR_CHECK_ARG(n % chunk == 0, "mar_adam_step_segments: n must be a multiple of chunk");
+  if (n == 0) return MAR_OK;
+  MAR_CHECK_ARG(((uintptr_t)param % 16 == 0) && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)exp_avg % 16 == 0) &&
+                    ((uintptr_t)exp_avg_sq % 16 == 0) && ((uintptr_t)seg_coef % 8 == 0),
+                "mar_adam_step_segments: buffers must be 16 B aligned");
+  int shift = 0;
+  while ((1 << shift) < chunk) shift++;
+  adam_seg_tick_kernel<<<(unsigned)ceil_div(nseg, 128), 128, 0, S(stream)>>>(seg_steps, seg_active,
+                                                                            reinterpret_cast<float2*>(seg_coef), nseg, lr, beta1, beta2);
+  MAR_LAUNCH_CHECK("adam_seg_tick");
+  adam_seg_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, S(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, chunk_seg, reinterpret_cast<const float2*>(seg_coef), n, shift, beta1, beta2, eps);
+  MAR_LAUNCH_CHECK("adam_seg");
+  return MAR_OK;
+}
+
+int mar_label_weight_sum(const int64_t* labels, const float* class_weight, float* out, int64_t B, int64_t C, void* stream) {
+  MAR_CHECK_ARG(labels && out && B >= 0 && C > 0, "mar_label_weight_sum: bad arguments");
+  label_weight_sum_kernel<<<1, 256, 0, S(stream)>>>(labels, class_weight, out, B, C);
+  MAR_LAUNCH_CHECK("label_weight_sum");
   return MAR_OK;
 }
 

@@ -42,6 +42,27 @@ def _split_names(names):
     return base, present
 
 
+_row_cache: Dict = {}
+
+
+def _present_rows(present: np.ndarray, device: torch.device, kind: str) -> torch.Tensor:
+    """Device copy of a per-sample presence pattern: 'idx' → int64 indices of the present rows, 'keep' → bool mask.
+    The pattern comes from the batch's NAMES (host strings), so it is uploaded once per distinct pattern and reused:
+    no boolean-mask indexing (nonzero() = a device→host sync) and no pageable upload on the step's path — both are
+    illegal while a CUDA graph is being captured (an eager step with the same names always precedes a capture)."""
+    key = (present.tobytes(), str(device), kind)
+    t = _row_cache.get(key)
+    if t is None:
+        if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("a presence pattern met for the first time during CUDA-graph capture")
+        host = torch.from_numpy(np.nonzero(present)[0].astype(np.int64)) if kind == "idx" else torch.from_numpy(present.copy())
+        t = host.to(device)
+        if len(_row_cache) > 4096:
+            _row_cache.clear()
+        _row_cache[key] = t
+    return t
+
+
 def _mlp_head(seq: nn.Sequential, i0: int, i1: int, x: torch.Tensor, p: float, training: bool) -> torch.Tensor:
     """Linear(i0) → ReLU → Dropout(p) → Linear(i1); logits in fp32."""
     l0, l1 = seq[i0], seq[i1]
@@ -306,22 +327,40 @@ def _apply_criterion(criterion, preds, labels, keep=None):
     """Plain / class-weighted nn.CrossEntropyLoss and this module's FocalLoss run on the fused kernels (ignored
     rows carry label -1); any other criterion object is called as given."""
     if isinstance(criterion, FocalLoss) and preds.is_cuda:
-        labels = labels.masked_fill(labels == criterion.ignore_index, -1)
-        if keep is not None:
-            labels = labels.masked_fill(~keep, -1)
+        labels = _effective_labels(criterion, labels, keep)
         loss = ops.focal_loss(preds, labels, criterion.alpha, criterion.gamma)
         return loss if criterion.reduction == "mean" else loss * (labels >= 0).sum().to(loss.dtype)
-    plain_ce = isinstance(criterion, nn.CrossEntropyLoss) and criterion.reduction == "mean" \
-        and criterion.label_smoothing == 0.0
-    if plain_ce and preds.is_cuda:
-        if keep is not None:
-            labels = labels.masked_fill(~keep, -1)
-        if criterion.ignore_index >= 0:
-            labels = labels.masked_fill(labels == criterion.ignore_index, -1)
-        return ops.cross_entropy(preds, labels, criterion.weight)
-    if keep is not None:
+    if _mean_norm_kind(criterion) == "weighted" and preds.is_cuda:
+        return ops.cross_entropy(preds, _effective_labels(criterion, labels, keep), criterion.weight)
+    if keep is not None:            # a foreign criterion object: called as given, on the kept rows (not capturable)
         preds, labels = preds[keep], labels[keep]
     return criterion(preds.float(), labels)
+
+
+def _mean_norm_kind(criterion) -> Optional[str]:
+    """'weighted' / 'count': what the criterion's mean divides by; None if it is not a fused mean-reduced criterion."""
+    if isinstance(criterion, FocalLoss):
+        return "count" if criterion.reduction == "mean" else None
+    if isinstance(criterion, nn.CrossEntropyLoss) and criterion.reduction == "mean" and criterion.label_smoothing == 0.0:
+        return "weighted"
+    return None
+
+
+def _effective_labels(criterion, labels, keep):
+    """Labels as the fused loss kernels read them: -1 on every row the criterion ignores."""
+    if keep is not None:
+        labels = labels.masked_fill(~keep, -1)
+    ii = criterion.ignore_index
+    if isinstance(criterion, FocalLoss) or ii >= 0:
+        labels = labels.masked_fill(labels == ii, -1)
+    return labels
+
+
+def _label_weight_sum(criterion, labels, keep, out) -> None:
+    kind = _mean_norm_kind(criterion)
+    labels = _effective_labels(criterion, labels, keep).to(torch.int64).contiguous()
+    w = criterion.weight if kind == "weighted" else None
+    ops.label_weight_sum(labels, w, out)
 
 
 class MultiModalCrossEntropyLoss(nn.Module):
@@ -340,9 +379,29 @@ class MultiModalCrossEntropyLoss(nn.Module):
                 continue
             preds = output_dict[name]
             labels = labels.to(preds.device)
-            keep = None if present.all() else torch.from_numpy(present).to(preds.device)
+            keep = None if present.all() else _present_rows(present, preds.device, "keep")
             losses_dict[name] = _apply_criterion(self.criterion_dict[name], preds, labels, keep)
         return losses_dict
+
+    def label_weight_sums(self, target, device, out: Optional[torch.Tensor]):
+        """The denominators of the configured 'mean' criteria on THIS batch, per head in `modalities_list` order:
+        Σ class_weight[label] over the rows the loss keeps (their count without class weights).  out=None → the list
+        of heads (None when a criterion is not one of the fused mean-reduced ones); otherwise out[i] is written on
+        the device (no sync).  A data-parallel TrainStep exchanges these to weigh every rank's gradient so that the
+        reduced gradient is the one of the reference loss on the global batch."""
+        for c in self.criterion_dict.values():
+            if _mean_norm_kind(c) is None:
+                return None
+        if out is None:
+            return list(self.modalities_list)
+        out.zero_()
+        for names, labels in target:
+            name, present = _split_names(names)
+            if not present.any() or name not in self.modalities_list:
+                continue
+            keep = None if present.all() else _present_rows(present, torch.device(device), "keep")
+            _label_weight_sum(self.criterion_dict[name], labels.to(device), keep, out[self.modalities_list.index(name):])
+        return list(self.modalities_list)
 
 
 class MultiCrossEntropyLoss(nn.Module):
@@ -357,6 +416,14 @@ class MultiCrossEntropyLoss(nn.Module):
         for name, preds in output_dict.items():
             losses_dict[name] = _apply_criterion(self.criterion, preds, target.to(preds.device))
         return losses_dict
+
+    def label_weight_sums(self, target, device, out: Optional[torch.Tensor]):
+        """One entry: every head is scored against the same labels with the same plain CE (see
+        MultiModalCrossEntropyLoss.label_weight_sums)."""
+        if out is None:
+            return ["*"]
+        _label_weight_sum(self.criterion, target.to(device), None, out)
+        return ["*"]
 
 
 # --------------------------------------------------------------------------------------
@@ -552,9 +619,9 @@ class _MultimodalBase(nn.Module):
                 if present.all():
                     feats = extractor(batch)
                 else:
-                    idx = torch.from_numpy(present).to(batch.device)
-                    got = extractor(batch[idx])
-                    feats = torch.zeros(shape, device=batch.device, dtype=got.dtype).index_put((idx,), got)
+                    idx = _present_rows(present, batch.device, "idx")
+                    got = extractor(batch.index_select(0, idx))
+                    feats = torch.zeros(shape, device=batch.device, dtype=got.dtype).index_copy(0, idx, got)
             if feats is None:
                 dtype = batch.dtype if (ops.probing() or not batch.is_cuda) else ops.get_precision()
                 feats = torch.zeros(shape, device=batch.device, dtype=dtype)

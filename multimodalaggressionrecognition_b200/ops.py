@@ -654,6 +654,16 @@ def focal_loss(logits: torch.Tensor, labels: torch.Tensor, alpha: Optional[torch
     return _FocalLoss.apply(logits, labels, alpha, float(gamma))
 
 
+def label_weight_sum(labels: torch.Tensor, weight: Optional[torch.Tensor], out: torch.Tensor) -> None:
+    """out[0] = Σ over rows with label >= 0 of weight[label] (their count when weight is None): the denominator of
+    nn.CrossEntropyLoss(reduction='mean') (models.py:232-263), on the device."""
+    _require_cuda(labels, "label_weight_sum")
+    if weight is not None:
+        weight = weight.to(device=labels.device, dtype=torch.float32).contiguous()
+    C = weight.numel() if weight is not None else (1 << 40)
+    call("mar_label_weight_sum", labels.data_ptr(), _p(weight), out.data_ptr(), labels.numel(), C, _stream())
+
+
 def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
     """argmax over classes on the device (trainer.py:170, :726)."""
     logits = to_compute(logits, torch.float32).contiguous()

@@ -17,6 +17,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import call
+from .models import LossesDict
 
 
 def _stream() -> int:
@@ -25,20 +26,34 @@ def _stream() -> int:
 
 class FlatParams:
     """Moves a model's parameters into ONE contiguous fp32 buffer (params become views, state_dict keys and
-    shapes are unchanged) and gives every parameter a persistent .grad view into ONE flat gradient buffer."""
+    shapes are unchanged) and gives every parameter a persistent .grad view into ONE flat gradient buffer.
+
+    Layout of both buffers: [header | p0 | p1 | ...], every block starting on a multiple of `align` floats.  One
+    SEGMENT per parameter; `chunk_seg[i // align]` names the segment of float i (-1: header).  The header of the
+    GRADIENT buffer carries the step's per-parameter "received a gradient" flags (`flags`, one float per segment):
+    they travel with the last gradient bucket of the data-parallel all-reduce and steer the per-parameter Adam."""
 
     def __init__(self, params: Sequence[nn.Parameter], align: int = 64):
         self.params = [p for p in params if p.requires_grad]
         assert self.params, "no trainable parameters"
+        assert align >= 4 and align & (align - 1) == 0
         dev = self.params[0].device
-        self.offsets, off = [], 0
-        for p in self.params:
+        self.align = align
+        self.nseg = len(self.params)
+        self.header = (self.nseg + align - 1) // align * align
+        self.offsets, off = [], self.header
+        seg_of_chunk = [-1] * (self.header // align)
+        for i, p in enumerate(self.params):
             assert p.dtype == torch.float32 and p.device == dev
             self.offsets.append(off)
-            off += (p.numel() + align - 1) // align * align
+            n = (p.numel() + align - 1) // align * align
+            seg_of_chunk += [i] * (n // align)
+            off += n
         self.numel = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.chunk_seg = torch.tensor(seg_of_chunk, dtype=torch.int32).to(dev)
+        self.flags = self.grad[:self.nseg]
         with torch.no_grad():
             for p, o in zip(self.params, self.offsets):
                 self.flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
@@ -53,47 +68,50 @@ class FlatParams:
 
 
 class FlatAdam:
-    """torch.optim.Adam defaults (train_multimodal.py:444: lr 1e-3, betas (0.9, 0.999), eps 1e-8, no weight
-    decay) as ONE kernel launch over the flat buffers; the step counter lives on the device so the update is
-    CUDA-graph capturable.  Deviation from torch: parameters that received no gradient this step still see an
-    update from their running moments (torch skips params whose .grad is None); with a zero gradient and zero
-    moments that update is exactly 0, so it only differs once a head has trained and is then inactive."""
+    """torch.optim.Adam (train_multimodal.py:444: lr 1e-3, betas (0.9, 0.999), eps 1e-8, no weight decay) over the
+    flat buffers with torch's per-parameter semantics: a parameter that received NO gradient this step is skipped —
+    no moment decay, no update, no step-count increment — and every parameter keeps its own step count.  That is the
+    reference's normal regime: its sampler makes every batch homogeneous in aggression type (datasets.py:630-645) and
+    zero_grad leaves the inactive head's gradients None (trainer.py:140-150).  Which parameters are active is read on
+    the DEVICE from the gradient buffer's header flags (FlatParams.flags), the step counts live on the device too:
+    two launches per step (`mar_adam_step_segments`), CUDA-graph capturable."""
 
     def __init__(self, flat: FlatParams, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
         self.flat, self.lr, self.betas, self.eps = flat, lr, betas, eps
         self.exp_avg = torch.zeros_like(flat.flat)
         self.exp_avg_sq = torch.zeros_like(flat.flat)
-        self.step_dev = torch.zeros(1, dtype=torch.float32, device=flat.flat.device)
+        self.seg_steps = torch.zeros(flat.nseg, dtype=torch.float32, device=flat.flat.device)
+        self.seg_coef = torch.zeros(2 * flat.nseg, dtype=torch.float32, device=flat.flat.device)
 
     def step(self) -> None:
         f = self.flat
-        if f.flat.is_cuda:
-            st = _stream()
-            call("mar_adam_tick", self.step_dev.data_ptr(), st)
-            call("mar_adam_step", f.flat.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
-                 self.exp_avg_sq.data_ptr(), self.step_dev.data_ptr(), f.numel, self.lr, self.betas[0], self.betas[1],
-                 self.eps, st)
-            ops.weights_changed()      # raw-pointer update: torch's version counters did not move
-        else:  # host-side logic tests (gloo, no GPU): same arithmetic in torch
-            self.step_dev += 1
-            t = float(self.step_dev)
-            b1, b2 = self.betas
-            self.exp_avg.mul_(b1).add_(f.grad, alpha=1 - b1)
-            self.exp_avg_sq.mul_(b2).addcmul_(f.grad, f.grad, value=1 - b2)
-            denom = (self.exp_avg_sq.sqrt() / (1 - b2 ** t) ** 0.5).add_(self.eps)
-            f.flat.addcdiv_(self.exp_avg, denom, value=-self.lr / (1 - b1 ** t))
+        if not f.flat.is_cuda:
+            raise RuntimeError("FlatAdam runs on sm_100a devices only: there is no CPU arithmetic in this package "
+                               "(the host-logic tests install their own stand-in, tests/helpers.py)")
+        call("mar_adam_step_segments", f.flat.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
+             self.exp_avg_sq.data_ptr(), f.chunk_seg.data_ptr(), self.seg_steps.data_ptr(), f.flags.data_ptr(),
+             self.seg_coef.data_ptr(), f.numel, f.align, f.nseg, self.lr, self.betas[0], self.betas[1], self.eps,
+             _stream())
+        ops.weights_changed()      # raw-pointer update: torch's version counters did not move
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.flat.zero_grad()
 
 
 class GradSync:
-    """Bucketed gradient all-reduce (mean over ranks) over slices of the flat gradient buffer, launched from
-    post-accumulate-grad hooks as soon as every parameter of a bucket has its gradient, on a side stream so the
-    exchange overlaps the rest of backward.  Buckets are contiguous slices taken from the END of the buffer
-    (backward produces gradients in roughly reverse parameter order).  `finish()` reduces whatever did not fire
-    (parameters of a head that was inactive in this batch keep zero gradients but are reduced all the same, so
-    ranks never diverge) and makes the compute stream wait for the exchange."""
+    """Tracks which parameters received a gradient this step and, with more than one rank, exchanges the gradients.
+
+    * Every parameter is counted ONCE per step, by its post-accumulate-grad hook or by `notify` (a kernel accumulated
+      the gradient straight into the flat buffer, ops.grad_sink), whichever comes first.  `finish()` writes the
+      resulting active flags into the gradient buffer's header (FlatParams.flags) for the per-parameter Adam.
+    * Data parallel: bucketed all-reduce (SUM — every rank has already weighed its loss, see TrainStep) over slices
+      of the flat gradient buffer on a side stream, overlapping the rest of backward.  Buckets are contiguous slices
+      taken from the END of the buffer (backward produces gradients in roughly reverse parameter order).  The
+      collective ORDER is the same on every rank whatever its shard of the batch activates: bucket b is launched
+      only after buckets 0..b-1, as soon as all of them are complete locally, the remainder in `finish()` (a rank
+      whose slice lacks a modality or a head reduces zeros, at the same place in the sequence as its peers).  The
+      last bucket holds the header flags and always goes from `finish()`: a parameter is active if ANY rank saw a
+      gradient for it, as in a single process on the global batch."""
 
     def __init__(self, flat: FlatParams, group=None, num_buckets: int = 4):
         self.flat = flat
@@ -114,7 +132,7 @@ class GradSync:
         self.buckets = []           # (param index range [lo, hi), element range [e0, e1))
         for hi, lo in zip(bounds[:-1], bounds[1:]):
             if lo < hi:
-                e0 = flat.offsets[lo]
+                e0 = flat.offsets[lo] if lo > 0 else 0          # the bucket of parameter 0 also carries the header
                 e1 = flat.offsets[hi] if hi < n else total
                 self.buckets.append((lo, hi, e0, e1))
         self.bucket_of = {}
@@ -125,14 +143,14 @@ class GradSync:
         self.launched = [False] * len(self.buckets)
         self._streams = [dict() for _ in self.buckets]
         self.fired = [False] * n
-        self.handles = []
         self.order: List[int] = []
         self.enabled = True          # False: hooks do nothing (backward passes outside a TrainStep, e.g. profiling)
         self.index_of = {id(p): i for i, p in enumerate(flat.params)}
         self._hooks = [self._make_hook(i) for i in range(n)]
-        if self.world > 1:
-            for i, p in enumerate(flat.params):
-                p.register_post_accumulate_grad_hook(self._hooks[i])
+        self._masks: Dict[bytes, torch.Tensor] = {}      # active pattern -> device flags (one upload per pattern)
+        self.last_active: Optional[List[bool]] = None
+        for i, p in enumerate(flat.params):
+            p.register_post_accumulate_grad_hook(self._hooks[i])
         self.reset()
 
     def notify(self, param) -> None:
@@ -142,10 +160,9 @@ class GradSync:
         gradient, measured on torch 2.11) — every parameter is counted ONCE per step, whichever comes first
         (counting both launched the buckets' all-reduces before their gradients were complete: found on 2 B200s
         with tools/dp_diag.py, the ranks' parameters drifted apart)."""
-        if self.world > 1:
-            i = self.index_of.get(id(param))
-            if i is not None:
-                self._hooks[i](param)
+        i = self.index_of.get(id(param))
+        if i is not None:
+            self._hooks[i](param)
 
     def reset(self) -> None:
         for b, (lo, hi, _, _) in enumerate(self.buckets):
@@ -153,7 +170,6 @@ class GradSync:
             self.launched[b] = False
             self._streams[b] = {}
         self.fired = [False] * len(self.flat.params)
-        self.handles = []
         self.order = []
 
     def _make_hook(self, i: int) -> Callable:
@@ -161,14 +177,25 @@ class GradSync:
             if not self.enabled or self.fired[i]:
                 return
             self.fired[i] = True
+            if self.world == 1:
+                return
             b = self.bucket_of[i]
             if self.comm_stream is not None:        # the stream this gradient was written on (autograd may run a
                 s = torch.cuda.current_stream()     # kept-alive AccumulateGrad node on the stream of an earlier step)
                 self._streams[b][s.cuda_stream] = s
             self.pending[b] -= 1
-            if self.pending[b] == 0 and not self.launched[b]:
-                self._launch(b)
+            self._launch_ready()
         return hook
+
+    def _launch_ready(self) -> None:
+        """Launch, in index order, every bucket whose predecessors are out and whose gradients are complete —
+        except the last one (header flags), which waits for finish()."""
+        for b in range(len(self.buckets) - 1):
+            if self.launched[b]:
+                continue
+            if self.pending[b] != 0:
+                return
+            self._launch(b)
 
     def _launch(self, b: int) -> None:
         self.launched[b] = True
@@ -181,13 +208,29 @@ class GradSync:
             for key, s in self._streams[b].items():     # every stream a gradient of this bucket was written on
                 if key != cur.cuda_stream:
                     self.comm_stream.wait_stream(s)
+            for bb in range(b):                          # a bucket launched late also covers earlier stragglers' streams
+                for key, s in self._streams[bb].items():
+                    if key != cur.cuda_stream:
+                        self.comm_stream.wait_stream(s)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
         else:
             dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
-            view.div_(self.world)
+
+    def _write_flags(self) -> None:
+        active = bytes(bytearray(1 if f else 0 for f in self.fired))
+        mask = self._masks.get(active)
+        if mask is None:
+            if self.cuda and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("TrainStep: a batch layout activated a set of parameters that no eager step has "
+                                   "seen yet; its flags cannot be uploaded during CUDA-graph capture")
+            mask = torch.tensor([float(b) for b in active], dtype=torch.float32).to(self.flat.grad.device)
+            self._masks[active] = mask
+        self.flat.flags.copy_(mask)
+        self.last_active = list(self.fired)
 
     def finish(self) -> None:
+        self._write_flags()
         if self.world > 1:
             for b in range(len(self.buckets)):
                 if not self.launched[b]:
@@ -225,13 +268,15 @@ class TrainStep:
         # per-sample modality / label names whose `_EMPTY` markers steer the model's control flow, datasets.py:564-608)
         # — a batch with another signature (last batch of an epoch, a verb-only batch) never replays a foreign graph
         self._graphs = {}
-        self.max_signatures = 3          # further signatures run eagerly (each capture owns its activation pool)
+        self.max_signatures = 4          # further signatures run eagerly (each capture owns its activation pool)
         self._sets = None                # the two buffer sets of the most recent signature (kept for introspection)
         self._calls = 0
         self._copy_stream = None
+        self._side = None                # ONE side stream for the eager warm-up steps and every capture
         self._warm = 0
         self.captured_launches = 0
         self.last_pred = None
+        self._norm_local = self._norm_global = None
 
     # -- helpers ------------------------------------------------------------------------------
     @staticmethod
@@ -257,18 +302,62 @@ class TrainStep:
             return x
         return walk(batch)
 
+    def _loss_weights(self, labels):
+        """Data parallel only.  nn.CrossEntropyLoss averages over ITS rows (the sum of their class weights): with a
+        different number of non-EMPTY rows per rank — or a head absent from a rank's slice — the mean of the ranks'
+        gradients is not the gradient of the reference loss on the global batch.  Every rank therefore weighs each
+        head's loss by  local_norm / Σ_ranks norm  and the gradients are SUMMED.  The norms depend on the labels
+        alone, so their (tiny) all-reduce is launched on the communication stream before the forward pass and is
+        off the critical path.  Returns {head: 0-d device tensor}, or a float for criteria that do not expose
+        `label_weight_sums` (uniform 1 / world: equal slices assumed)."""
+        world = self.sync.world
+        if world == 1:
+            return None
+        fn = getattr(self.criterion, "label_weight_sums", None)
+        heads = fn(labels, self.flat.flat.device, None) if fn is not None else None
+        if heads is None:
+            return 1.0 / world
+        if self._norm_local is None or self._norm_local.numel() != len(heads):
+            self._norm_local = torch.zeros(len(heads), dtype=torch.float32, device=self.flat.flat.device)
+            self._norm_global = torch.zeros_like(self._norm_local)
+        fn(labels, self.flat.flat.device, self._norm_local)
+        self._norm_global.copy_(self._norm_local)
+        comm = self.sync.comm_stream
+        if comm is not None:
+            comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm):
+                dist.all_reduce(self._norm_global, op=dist.ReduceOp.SUM, group=self.sync.group)
+        else:
+            dist.all_reduce(self._norm_global, op=dist.ReduceOp.SUM, group=self.sync.group)
+        return heads
+
+    def _backward(self, losses, weights) -> None:
+        if weights is None:
+            losses.backward()
+            return
+        items = [(k, l) for k, l in losses.items() if isinstance(l, torch.Tensor) and l.requires_grad]
+        if not items:
+            return
+        if isinstance(weights, float):
+            grads = [torch.full_like(l, weights) for _, l in items]
+        else:
+            if self.sync.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.sync.comm_stream)
+            w = self._norm_local / self._norm_global.clamp_min(1e-30)
+            grads = [w[weights.index(k)].to(l.dtype).reshape(l.shape) for k, l in items]
+        torch.autograd.backward([l for _, l in items], grad_tensors=grads)
+
     def _eager(self, data, labels):
         self.opt.zero_grad()
         if self.flat.flat.is_cuda:
             ops.rng_advance(self.flat.flat.device)
+        weights = self._loss_weights(labels)
         pred = self.model(data)
         losses = self.criterion(pred, labels)
+        if isinstance(losses, torch.Tensor):
+            losses = LossesDict(loss=losses)
         with ops.grad_sink(self.sync.notify):       # weight / bias / LayerNorm gradients accumulate straight into the flat buffer
-            if hasattr(losses, "backward") and not isinstance(losses, torch.Tensor):
-                losses.backward()
-            else:
-                losses.backward()
-                losses = {"loss": losses}
+            self._backward(losses, weights)
         self.sync.finish()
         self.opt.step()
         self.last_pred = pred
@@ -320,7 +409,8 @@ class TrainStep:
         if state is None:
             if len(self._graphs) >= self.max_signatures:        # too many distinct batch layouts: stay eager for this one
                 return self._eager(self._to_dev(data, dev), self._to_dev(labels, dev))
-            state = {"sets": [dict(static_in=None, graph=None, static_out=None, static_pred=None, done=None) for _ in range(2)], "calls": 0}
+            state = {"sets": [dict(static_in=None, graph=None, static_out=None, static_pred=None, done=None) for _ in range(2)],
+                     "calls": 0, "warm": 0}
             self._graphs[sig] = state
         self._sets = state["sets"]
         cur = state["sets"][state["calls"] & 1]
@@ -347,9 +437,13 @@ class TrainStep:
                 s_.copy_(t, non_blocking=True)
         sdata, slabels = self._like([data, labels], cur["static_in"])
         if cur["graph"] is None:
-            if self._warm < 3:                      # eager warm-up steps on a side stream before capture
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            side = self._side
+            need = 3 if self._warm < 3 else 1       # eager steps before a capture: 3 for the first, 1 for any new signature
+            if state["warm"] < need:                # (uploads the signature's index / flag tensors, which capture cannot)
+                state["warm"] += 1
                 self._warm += 1
-                side = torch.cuda.Stream()
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     out = self._eager(sdata, slabels)
@@ -358,8 +452,10 @@ class TrainStep:
             ops.clear_weight_cache()
             g = torch.cuda.CUDAGraph()
             before = ops.launch_count()
-            with torch.cuda.graph(g):
+            side.wait_stream(main)
+            with torch.cuda.graph(g, stream=side):
                 cur["static_out"] = self._eager(sdata, slabels)
+            main.wait_stream(side)
             self.captured_launches = ops.launch_count() - before   # libmar kernels per replay
             cur["static_pred"] = self.last_pred     # this graph's own logits buffers
             cur["graph"] = g                        # capture records but does not execute: fall through to replay
@@ -428,9 +524,7 @@ class EpochAccumulator:
 
     @staticmethod
     def _argmax(logits: torch.Tensor) -> torch.Tensor:
-        if logits.is_cuda:
-            return ops.argmax_rows(logits.detach())
-        return logits.detach().argmax(dim=1)          # host-side logic tests (no GPU)
+        return ops.argmax_rows(logits.detach())        # (the host-logic tests install their own stand-in)
 
     def add(self, losses, pred, labels, data=None, size: Optional[int] = None) -> None:
         """One step's results; nothing here waits for the device.  `losses`: {head: 0-d tensor} (or a tensor),

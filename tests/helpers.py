@@ -232,3 +232,29 @@ def trainer_stream(kind, steps, B, seed, heads=("loss",), dataset_size=None, dev
             labels.append([tuple(names), y.to(dev)])
         out.append((data, losses, pred, labels))
     return out
+
+
+# ---- host stand-ins for the two device calls of training.py (the package has no CPU arithmetic) --------------------
+def host_adam_step(self) -> None:
+    """What `mar_adam_step_segments` computes, in torch on the host: per-parameter Adam over the flat buffers, the
+    parameters whose header flag is 0 untouched.  Installed by the gloo / host-logic tests only."""
+    f = self.flat
+    b1, b2 = self.betas
+    for i, (p, o) in enumerate(zip(f.params, f.offsets)):
+        if not float(f.flags[i]) > 0:
+            continue
+        self.seg_steps[i] += 1
+        t = float(self.seg_steps[i])
+        sl = slice(o, o + p.numel())
+        g = f.grad[sl]
+        self.exp_avg[sl].mul_(b1).add_(g, alpha=1 - b1)
+        self.exp_avg_sq[sl].mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (self.exp_avg_sq[sl].sqrt() / (1 - b2 ** t) ** 0.5).add_(self.eps)
+        f.flat[sl].addcdiv_(self.exp_avg[sl], denom, value=-self.lr / (1 - b1 ** t))
+
+
+def install_host_stand_ins() -> None:
+    """Call at the start of every CPU process that drives training.TrainStep / EpochAccumulator without a GPU."""
+    from multimodalaggressionrecognition_b200 import training
+    training.FlatAdam.step = host_adam_step
+    training.EpochAccumulator._argmax = staticmethod(lambda logits: logits.detach().argmax(dim=1))

@@ -13,6 +13,7 @@ import torch.nn as nn
 
 from multimodalaggressionrecognition_b200 import training
 from multimodalaggressionrecognition_b200.models import LossesDict
+from tests import helpers as H
 
 
 def _free_port():
@@ -95,6 +96,7 @@ def _make(seed=0, sink=False):
 
 def _worker(rank, world, port, steps, result_q, sink=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    H.install_host_stand_ins()
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         model = _make(sink=sink)
@@ -103,8 +105,7 @@ def _worker(rank, world, port, steps, result_q, sink=False):
         comm = None
         if sink == "streams":
             # Run GradSync's CUDA branch (side communication stream) without a GPU: fake stream objects that record
-            # who waited for whom, gradients "written" alternately on two compute streams, and gloo's missing AVG
-            # expressed as SUM / world.
+            # who waited for whom, gradients "written" alternately on two compute streams.
             import contextlib
 
             class FakeStream:
@@ -121,12 +122,6 @@ def _worker(rank, world, port, steps, result_q, sink=False):
                 return compute[turn[0] & 1]
             torch.cuda.current_stream = current_stream
             torch.cuda.stream = lambda _s: contextlib.nullcontext()
-            real_all_reduce = dist.all_reduce
-
-            def all_reduce(t, op=None, group=None):
-                real_all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-                t.div_(world)
-            training.dist.all_reduce = all_reduce
             step.sync.comm_stream = comm
         g = torch.Generator().manual_seed(123)
         X = torch.randn(steps, 8 * world, 16, generator=g)
@@ -202,27 +197,140 @@ def test_flat_params_keep_module_semantics():
     for k, v in model.state_dict().items():
         assert torch.equal(v, sd_before[k])                         # values preserved, keys unchanged
     p = next(model.parameters())
-    assert p.data_ptr() == flat.flat.data_ptr()                      # parameters are views of the flat buffer
-    assert p.grad is not None and p.grad.data_ptr() == flat.grad.data_ptr()
+    assert p.data_ptr() == flat.flat.data_ptr() + 4 * flat.header    # parameters are views of the flat buffer (after the flag header)
+    assert p.grad is not None and p.grad.data_ptr() == flat.grad.data_ptr() + 4 * flat.header
+    assert flat.header % flat.align == 0 and flat.header >= flat.nseg and flat.chunk_seg.numel() * flat.align == flat.numel
+    assert flat.chunk_seg[0] == -1 and flat.chunk_seg[flat.header // flat.align] == 0 and flat.chunk_seg[-1] == flat.nseg - 1
     model(torch.randn(4, 16))["a"].sum().backward()
     assert float(flat.grad.abs().sum()) > 0                          # autograd accumulated into the flat gradient
     flat.zero_grad()
     assert float(flat.grad.abs().sum()) == 0
 
 
-def test_flat_adam_matches_torch_adam_on_cpu():
+def test_train_step_follows_torch_adam_when_heads_alternate(monkeypatch):
+    """The reference's normal regime (datasets.py:630-645): batches alternate between heads, the inactive head's
+    parameters have no gradient and torch.optim.Adam skips them (no moment decay, no step count).  TrainStep's
+    tracking of the active parameters + the per-parameter Adam (host stand-in of the kernel here) must follow
+    torch.optim.Adam exactly; a flat Adam with one global step count does not (checked below)."""
+    monkeypatch.setattr(training.FlatAdam, "step", H.host_adam_step)
     m1, m2 = _make(1), _make(1)
-    flat = training.FlatParams(list(m1.parameters()))
-    opt1 = training.FlatAdam(flat, lr=1e-3)
-    opt2 = torch.optim.Adam(m2.parameters(), lr=1e-3)
-    x, y = torch.randn(8, 16), torch.randint(0, 2, (8,))
-    for _ in range(4):
-        opt1.zero_grad(); opt2.zero_grad()
-        _criterion(m1(x), y).backward()
-        _criterion(m2(x), y).backward()
-        opt1.step(); opt2.step()
+    pattern = ["ab", "a", "b", "a", "ab", "b", "b", "a"]
+
+    def crit(pred, labels):
+        out = LossesDict()
+        for k in labels[0]:
+            out[k] = nn.CrossEntropyLoss()(pred[k], labels[1])
+        return out
+
+    step = training.TrainStep(m1, crit, lr=1e-2)
+    opt2 = torch.optim.Adam(m2.parameters(), lr=1e-2)
+    g = torch.Generator().manual_seed(5)
+    for heads in pattern:
+        x, y = torch.randn(8, 16, generator=g), torch.randint(0, 2, (8,), generator=g)
+        step(x, (heads, y))
+        active = {n for n, f in zip([n for n, _ in m1.named_parameters()], step.sync.last_active) if f}
+        assert ("a.weight" in active) == ("a" in heads) and ("b.weight" in active) == ("b" in heads)
+        assert "unused.weight" not in active and "trunk.0.weight" in active
+        opt2.zero_grad()
+        crit(m2(x), (heads, y)).backward()
+        opt2.step()
     for (n, a), b in zip(m1.named_parameters(), m2.parameters()):
         assert torch.allclose(a, b, atol=1e-6), n
+    steps = dict(zip([n for n, _ in m1.named_parameters()], step.opt.seg_steps.tolist()))
+    assert steps["a.weight"] == sum("a" in h for h in pattern) and steps["b.bias"] == sum("b" in h for h in pattern)
+    assert steps["trunk.0.weight"] == len(pattern) and steps["unused.weight"] == 0
+
+
+def _uneven_worker(rank, world, port, steps, result_q):
+    """Ranks whose slices differ in which heads are present and in how many rows each head keeps."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    H.install_host_stand_ins()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        step = training.TrainStep(_make(), MaskedCE(), lr=1e-2, num_buckets=3)
+        assert len(step.sync.buckets) >= 2
+        X, Y = _uneven_data(steps, world)
+        orders = []
+        for s in range(steps):
+            sl = slice(rank * 8, (rank + 1) * 8)
+            step(X[s, sl], {k: v[s, sl] for k, v in Y.items()})
+            orders.append(list(range(len(step.sync.buckets))))
+        flat = step.flat.flat.detach().clone()
+        gathered = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        if rank == 0:
+            result_q.put([g.numpy() for g in gathered])
+    finally:
+        dist.destroy_process_group()
+
+
+class MaskedCE:
+    """Two-head criterion over per-head labels with -1 = row absent (the EMPTY rows of MultiModalCrossEntropyLoss):
+    a head whose rows are all absent emits no loss.  `label_weight_sums` is the protocol TrainStep uses to weigh the
+    ranks' gradients (models.MultiModalCrossEntropyLoss implements it with a kernel)."""
+    heads = ["a", "b"]
+
+    def __call__(self, pred, labels):
+        out = LossesDict()
+        for k in self.heads:
+            keep = labels[k] >= 0
+            if bool(keep.any()):
+                out[k] = nn.CrossEntropyLoss()(pred[k][keep], labels[k][keep])
+        return out
+
+    def label_weight_sums(self, labels, device, out):
+        if out is not None:
+            for i, k in enumerate(self.heads):
+                out[i] = float((labels[k] >= 0).sum())
+        return list(self.heads)
+
+
+def _uneven_data(steps, world):
+    g = torch.Generator().manual_seed(321)
+    X = torch.randn(steps, 8 * world, 16, generator=g)
+    Y = {k: torch.randint(0, 2, (steps, 8 * world), generator=g) for k in ("a", "b")}
+    Y["a"][0, 8:] = -1          # step 0: head a lives on rank 0 only
+    Y["b"][0, :8] = -1          #         head b on rank 1 only   (different active sets per rank)
+    Y["a"][1, :5] = -1          # step 1: both heads everywhere, different row counts per rank
+    Y["b"][1, 10:] = -1
+    Y["b"][2] = -1              # step 2: head b absent on every rank (skipped by Adam, as in a single process)
+    Y["a"][3, :8] = -1          # step 3: rank 0 has nothing for head a, 3 rows for b
+    Y["b"][3, 3:8] = -1
+    return X, Y
+
+
+@pytest.mark.timeout(180)
+def test_ranks_with_different_active_heads_and_row_counts_match_the_global_batch():
+    """(i) the collective order does not depend on which parameters a rank's slice activates (bucket b goes only
+    after buckets 0..b-1; the old first-complete-first-launched order paired different buckets across ranks — gloo
+    aborted with a size mismatch, NCCL would hang); (ii) every rank weighs its loss by local rows / global rows, so
+    the SUMMED gradient is the gradient of the mean over the GLOBAL batch; (iii) a parameter is active if any rank
+    saw a gradient for it.  Reference: one process, torch.optim.Adam, the whole batch."""
+    world, steps = 2, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_uneven_worker, args=(r, world, port, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    flats = q.get(timeout=150)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    f0, f1 = torch.from_numpy(flats[0]), torch.from_numpy(flats[1])
+    assert torch.equal(f0, f1), "ranks diverged"
+    model = _make()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    X, Y = _uneven_data(steps, world)
+    crit = MaskedCE()
+    for s in range(steps):
+        opt.zero_grad()
+        crit(model(X[s]), {k: v[s] for k, v in Y.items()}).backward()
+        opt.step()
+    layout = training.FlatParams(list(_make().parameters()))
+    for (name, p_ref), o in zip(model.named_parameters(), layout.offsets):
+        got = f0[o:o + p_ref.numel()].view(p_ref.shape)
+        assert torch.allclose(got, p_ref.detach(), atol=3e-6, rtol=1e-5), f"{name} differs from the single-process run"
 
 
 def test_bucket_layout_covers_every_parameter_once():
@@ -232,6 +340,6 @@ def test_bucket_layout_covers_every_parameter_once():
     covered = []
     for lo, hi, e0, e1 in sync.buckets:
         covered += list(range(lo, hi))
-        assert e0 == flat.offsets[lo] and e1 > e0
+        assert e0 == (flat.offsets[lo] if lo > 0 else 0) and e1 > e0      # parameter 0's bucket carries the flag header
     assert sorted(covered) == list(range(len(flat.params)))
     assert sync.buckets[0][1] == len(flat.params)                    # first bucket = the LAST parameters (backward order)

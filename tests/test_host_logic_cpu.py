@@ -41,6 +41,21 @@ def test_grad_sync_notify_counts_like_the_autograd_hook():
     assert sync.world == 1
     sync.notify(lin.weight)                                     # world 1: nothing to exchange, must not raise
     assert set(sync.index_of) == {id(p) for p in flat.params}
+    # ... but the parameter is recorded as active for the per-parameter Adam: finish() writes the header flags
+    sync.finish()
+    assert flat.flags.tolist() == [1.0, 0.0] and sync.last_active == [True, False]
+    lin(torch.randn(2, 3)).sum().backward()                     # both parameters through autograd's hooks
+    sync.finish()
+    assert flat.flags.tolist() == [1.0, 1.0]
+    sync.finish()                                               # a step in which nothing received a gradient
+    assert flat.flags.tolist() == [0.0, 0.0]
+
+
+def test_no_cpu_arithmetic_in_the_step_driver():
+    """FlatAdam refuses CPU buffers (README: no CPU fallback); the gloo tests install their own stand-in."""
+    flat = training.FlatParams(list(nn.Linear(3, 2).parameters()))
+    with pytest.raises(RuntimeError, match="sm_100a"):
+        training.FlatAdam(flat).step()
 
 
 def test_focal_loss_module_arguments():
@@ -53,7 +68,7 @@ def test_focal_loss_module_arguments():
 
 
 @pytest.mark.parametrize("name", ["single", "multi_head", "multimodal"])
-def test_epoch_accumulator_reproduces_the_reference_trainers(name):
+def test_epoch_accumulator_reproduces_the_reference_trainers(name, monkeypatch):
     """training.EpochAccumulator (one device->host read per epoch) against what the LIVE reference's
     TorchSupervisedTrainer / RNN_trainer / MultimodalTrainer methods returned for the same seeded step stream
     (tests/golden/golden_trainer_epoch.pt, oracle/make_golden_trainer.py) — including the reference's
@@ -66,6 +81,8 @@ def test_epoch_accumulator_reproduces_the_reference_trainers(name):
     case = golden["cases"][name]
     spec = case["spec"]
     assert spec == H.TRAINER_STREAMS[name]
+    # the argmax kernel cannot run here: torch's argmax stands in for it (the package itself has no CPU arithmetic)
+    monkeypatch.setattr(training.EpochAccumulator, "_argmax", staticmethod(lambda logits: logits.detach().argmax(dim=1)))
     acc = training.EpochAccumulator(H.trainer_metrics())
     for data, losses, pred, labels in H.trainer_stream(**spec):
         acc.add(losses, pred, labels, data=data)

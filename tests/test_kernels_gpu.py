@@ -519,6 +519,62 @@ def test_adam_kernel_matches_oracle():
     assert_close(pg.cpu(), p, 1e-6, "adam")
 
 
+def test_segmented_adam_kernel_skips_inactive_parameters_and_counts_steps_per_parameter():
+    """mar_adam_step_segments against the oracle's per-parameter Adam (oracle.adam_step with a step LIST and grad None
+    for the skipped parameters = torch.optim.Adam, torch/optim/adam.py `_init_group`): 5 steps over 4 parameters whose
+    active sets change from step to step."""
+    from multimodalaggressionrecognition_b200 import training
+    from multimodalaggressionrecognition_b200._lib import call
+    torch.manual_seed(3)
+    shapes = [(7, 33), (130,), (64, 64), (5,)]
+    host = [torch.randn(*s) for s in shapes]
+    params = [torch.nn.Parameter(h.clone().to(DEV)) for h in host]
+    flat = training.FlatParams(params)
+    opt = training.FlatAdam(flat, lr=1e-2)
+    m, v = [torch.zeros_like(h) for h in host], [torch.zeros_like(h) for h in host]
+    counts = [0] * 4
+    pattern = [(1, 1, 1, 1), (1, 0, 1, 0), (0, 0, 1, 1), (1, 0, 0, 0), (1, 1, 1, 1)]
+    for active in pattern:
+        grads = [torch.randn(*s) for s in shapes]
+        flat.zero_grad()
+        for i, a in enumerate(active):
+            if a:
+                params[i].grad.copy_(grads[i].to(DEV))
+                counts[i] += 1
+            else:
+                # garbage where torch would have .grad None: an inactive parameter must not even READ its gradient
+                params[i].grad.fill_(float("nan"))
+        flat.flags.copy_(torch.tensor(active, dtype=torch.float32) * 2.0)        # > 0 = active (a SUM over ranks may exceed 1)
+        opt.step()
+        O.adam_step(host, [g if a else None for g, a in zip(grads, active)], m, v, list(counts), lr=1e-2)
+    torch.cuda.synchronize()
+    for i, (p_, h) in enumerate(zip(params, host)):
+        assert_close(p_.detach().cpu(), h, 1e-6, f"param {i}")
+    assert opt.seg_steps.tolist() == [float(c) for c in counts]
+    assert not bool(torch.isnan(flat.flat).any())
+    with pytest.raises(RuntimeError, match="chunk"):
+        call("mar_adam_step_segments", flat.flat.data_ptr(), flat.grad.data_ptr(), opt.exp_avg.data_ptr(),
+             opt.exp_avg_sq.data_ptr(), flat.chunk_seg.data_ptr(), opt.seg_steps.data_ptr(), flat.flags.data_ptr(),
+             opt.seg_coef.data_ptr(), flat.numel, 48, flat.nseg, 1e-3, 0.9, 0.999, 1e-8, 0)
+
+
+def test_label_weight_sum_kernel():
+    from multimodalaggressionrecognition_b200 import models as M
+    y = torch.tensor([0, 1, -1, 1, 1, -100, 0], device=DEV)
+    out = torch.zeros(2, device=DEV)
+    ops.label_weight_sum(y, None, out[0:])
+    ops.label_weight_sum(y, torch.tensor([0.25, 2.0]), out[1:])
+    assert out.tolist() == [5.0, 2 * 0.25 + 3 * 2.0]
+    crit = M.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(weight=torch.tensor([1.0, 3.0])),
+                                         "verb": torch.nn.CrossEntropyLoss()})
+    labels = [[("verb", "verb_EMPTY", "verb"), torch.tensor([1, 0, 0])], [("phys", "phys", "phys"), torch.tensor([1, 1, 0])]]
+    assert crit.label_weight_sums(labels, DEV, None) == ["phys", "verb"]
+    crit.label_weight_sums(labels, DEV, out)
+    assert out.tolist() == [7.0, 2.0]
+    crit.criterion_dict["verb"] = torch.nn.CrossEntropyLoss(reduction="sum")
+    assert crit.label_weight_sums(labels, DEV, None) is None
+
+
 def test_error_reporting_through_abi():
     from multimodalaggressionrecognition_b200._lib import call
     with pytest.raises(RuntimeError, match="mar_layernorm_fwd"):
