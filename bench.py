@@ -100,36 +100,72 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # the reference arm / cpu baseline: oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_clips_per_s(steps: int, warmup: int, budget_s: float, batch: int = 8):
-    """C3 train step (fwd + per-head backward + Adam, dropout ON like the reference in train mode) with the
-    oracle restatement, all host threads, on a bounded sample: `batch` clips per step (full config is 256)."""
+def load_reference_models():
+    """oracle/_ref/models.py: the reference's own module, copied verbatim by oracle/build_ref.py in the build container
+    (git-ignored, travels to the GPU box).  None when absent."""
+    path = os.path.join(ROOT, "oracle", "_ref", "models.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_models", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_clips_per_s(steps: int, warmup: int, budget_s: float):
+    """The reference's CPU path on this box's host cores, all threads, on a bounded sample of the C3 workload.
+
+    kind "reference": the LIVE reference classes (oracle/_ref/models.py: PhysVerbModel assembly of
+    train_multimodal.py:298-420, MultiModalCrossEntropyLoss, per-head backward, torch.optim.Adam — the step of
+    trainer.py:140-149), train mode (dropout on), 32 clips/step.
+    kind "port": the oracle restatement on 8 clips/step, when oracle/_ref is absent."""
     from multimodalaggressionrecognition_b200 import models as M, workloads as W
-    from oracle import oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    O.DROPOUT_ENABLED = True
+    ref = load_reference_models()
     torch.manual_seed(0)
-    model = W.build_c3(M, T_AUDIO, T_VIDEO)          # parameter containers only (torch init), never run here
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    cfg = W.c3_oracle_cfg(T_AUDIO, T_VIDEO)
-    data, labels = W.batch_c3(B=batch, t_audio=T_AUDIO, t_video=T_VIDEO)
-    tr = O.OracleTrainer(sd, lambda s, d, t: O.physverb_model(d, s, cfg, t, True),
-                         lambda p, t: O.multimodal_ce(p, t, heads=["phys", "verb"]))
+    if ref is not None:
+        kind, batch = "reference", 32
+        model = W.build_c3(ref, T_AUDIO, T_VIDEO).train()
+        crit = ref.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(), "verb": torch.nn.CrossEntropyLoss()})
+        opt = torch.optim.Adam(model.parameters())
+        data, labels = W.batch_c3(B=batch, t_audio=T_AUDIO, t_video=T_VIDEO)
+
+        def one():
+            opt.zero_grad()
+            losses = crit(model(data), labels)
+            losses.backward()
+            opt.step()
+    else:
+        from oracle import oracle as O
+        kind, batch = "port", 8
+        O.DROPOUT_ENABLED = True
+        model = W.build_c3(M, T_AUDIO, T_VIDEO)          # parameter containers only (torch init), never run here
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        cfg = W.c3_oracle_cfg(T_AUDIO, T_VIDEO)
+        data, labels = W.batch_c3(B=batch, t_audio=T_AUDIO, t_video=T_VIDEO)
+        tr = O.OracleTrainer(sd, lambda s, d, t: O.physverb_model(d, s, cfg, t, True),
+                             lambda p, t: O.multimodal_ce(p, t, heads=["phys", "verb"]))
+
+        def one():
+            tr.step(data, labels, True)
     t0 = time.perf_counter()
-    tr.step(data, labels, True)
+    one()
     first = time.perf_counter() - t0
     # bound the run: shrink the number of timed steps (never below 2) to stay inside the budget
     steps = max(2, min(steps, int(budget_s / max(first, 1e-3)) - warmup))
     for _ in range(max(0, warmup - 1)):
-        tr.step(data, labels, True)
+        one()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        tr.step(data, labels, True)
+        one()
         times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
-    return {"value": batch / (ms / 1e3), "ms_per_step": ms, "steps": steps, "cores": cores, "batch": batch,
-            "sample": f"C3 train step on {batch} clips/step (full config 256), {steps} timed steps, dropout on, "
+    what = "live reference classes (oracle/_ref/models.py) + torch.optim.Adam" if kind == "reference" else "oracle port"
+    return {"value": batch / (ms / 1e3), "ms_per_step": ms, "steps": steps, "cores": cores, "batch": batch, "kind": kind,
+            "sample": f"C3 train step on {batch} clips/step (full config 256), {what}, {steps} timed steps, dropout on, "
                       f"{cores} host threads, torch {torch.__version__} CPU fp32"}
 
 
@@ -137,14 +173,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_oracle_clips_per_s(args.steps, args.warmup, budget_s=150.0)
+    r = cpu_clips_per_s(args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C3 audio+video transformer fusion train step, T_a={T_AUDIO}x768, T_v={T_VIDEO}x512, "
                                f"CPU sample of {r['batch']} clips/step"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -264,8 +300,8 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_oracle_clips_per_s(steps=3, warmup=1, budget_s=25.0)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        r = cpu_clips_per_s(steps=3, warmup=1, budget_s=25.0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
     global_batch = B * world
     line = {

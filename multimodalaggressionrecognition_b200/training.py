@@ -256,7 +256,12 @@ class TrainStep:
         self.model, self.criterion = model, criterion
         self.flat = FlatParams(list(model.parameters()))
         self.opt = FlatAdam(self.flat, lr=lr)
-        self.sync = GradSync(self.flat, group=group, num_buckets=num_buckets)
+        # The hooks' AccumulateGrad nodes remember the stream they were created on: create them on the stream the graph-
+        # captured step runs on (the warm-up steps and every capture use this ONE side stream), or autograd inserts a
+        # cross-stream synchronisation per parameter and warns about the mismatch on every backward.
+        self._side = torch.cuda.Stream() if (graph and self.flat.flat.is_cuda) else None
+        with (torch.cuda.stream(self._side) if self._side is not None else _null()):
+            self.sync = GradSync(self.flat, group=group, num_buckets=num_buckets)
         if self.sync.world > 1 and self.flat.flat.is_cuda and ops._rng.seed is None:
             # every rank seeds torch identically (same initial weights), which would also give every rank the SAME
             # dropout masks for its different clips; a single process on the global batch draws independent masks per
@@ -272,7 +277,6 @@ class TrainStep:
         self._sets = None                # the two buffer sets of the most recent signature (kept for introspection)
         self._calls = 0
         self._copy_stream = None
-        self._side = None                # ONE side stream for the eager warm-up steps and every capture
         self._warm = 0
         self.captured_launches = 0
         self.last_pred = None
