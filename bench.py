@@ -268,6 +268,11 @@ def run_ours(args):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 
+    # ---- the other BASELINE.json configurations, time-bounded, inside the same line ---------------------------
+    other = None
+    if not args.no_extras:
+        other = other_configs(args, world, rank, dev, timed, M, ops, training, W)
+
     # ---- roofline of the dominant kernel: events around every GEMM launch of one eager step --------
     roof = None
     if rank == 0:
@@ -319,6 +324,7 @@ def run_ours(args):
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "ranks_identical": ranks_identical,
+        "other_configs": other,
         "losses_last_step": loss_vals,
         "flops_per_clip_train": 3 * W.c3_flops_per_clip(T_AUDIO, T_VIDEO)["total"],
         "model_tflops": 3 * W.c3_flops_per_clip(T_AUDIO, T_VIDEO)["total"] * global_batch / (ms_dev / 1e3) / 1e12,
@@ -327,6 +333,83 @@ def run_ours(args):
     line["model_frac_of_bf16_peak"] = line["model_tflops"] / (peaks["bf16_tflops_sustained"] * world)
     print(json.dumps(line), flush=True)
     shutdown()
+
+
+def other_configs(args, world, rank, dev, timed, M, ops, training, W):
+    """BASELINE.json configs[1], [3], [4] as sub-results of the same line (the headline stays configs[2], 256 clips/GPU):
+    * c4_global1024 — the C3 model data-parallel at a GLOBAL batch of 1024 (1024 / N clips per GPU, strong scaling in N);
+    * c2 — the video GRU classifier, B = 64, T = 64, d = 512 (N = 1 only: the config names one B200);
+    * c5 — the fusion model at T_a = T_v = T in {128, 512, 2048} (fused length 2T: the attention-bound regime), 65 536
+      audio tokens per GPU per step (weak scaling), train step and inference forward.
+    Every entry: CUDA-event time over `--extra-steps` steps after warm-up, max over ranks, whole-job clips/s, and the
+    model FLOP rate as a fraction of N x the measured sustained bf16 peak."""
+    peaks = measured_peaks()
+    peak = peaks["bf16_tflops_sustained"] * world
+    K = args.extra_steps
+    out = {}
+
+    def crit_c3():
+        return M.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(), "verb": torch.nn.CrossEntropyLoss()})
+
+    def fusion(ta, tv, B, infer):
+        torch.manual_seed(0)
+        model = W.build_c3(M, ta, tv).to(dev).train()
+        data, labels = W.batch_c3(B=B, t_audio=ta, t_video=tv, seed=2000 + rank)
+        gd, gl = W.to_device(data, dev), W.to_device(labels, dev)
+        st = training.TrainStep(model, crit_c3(), graph=not args.no_graph)
+        for _ in range(6):
+            st(gd, gl)
+        ms = timed(lambda: st(gd, gl), K)
+        fl = W.c3_flops_per_clip(ta, tv)
+        res = {"per_gpu_batch": B, "global_batch": B * world, "train_ms": ms, "train_clips_per_s": B * world / ms * 1e3,
+               "train_frac_of_bf16_peak": 3 * fl["total"] * B * world / ms / 1e9 / peak,
+               "attn_share_of_flops": fl["attn"] / fl["total"]}
+        st.release_graphs()
+        if infer:
+            model.eval()
+
+            def fwd():
+                with torch.no_grad():
+                    model(gd)
+            for _ in range(3):
+                fwd()
+            ms_i = timed(fwd, K)
+            res.update({"infer_ms": ms_i, "infer_clips_per_s": B * world / ms_i * 1e3,
+                        "infer_frac_of_bf16_peak": fl["total"] * B * world / ms_i / 1e9 / peak})
+        del st, model, gd, gl
+        ops.clear_weight_cache()
+        torch.cuda.empty_cache()
+        return res
+
+    if 1024 % world == 0:
+        out["c4_global1024"] = fusion(T_AUDIO, T_VIDEO, 1024 // world, False)
+    out["c5"] = {f"T{T}": fusion(T, T, max(1, 65536 // T), True) for T in (128, 512, 2048)}
+    if world == 1:
+        torch.manual_seed(0)
+        model = W.build_c2(M).to(dev).train()
+        x, y = W.batch_c2(64, 64, 512)
+        x, y = x.to(dev), y.to(dev)
+        st = training.TrainStep(model, M.MultiCrossEntropyLoss(), graph=not args.no_graph)
+        for _ in range(8):
+            st(x, y)
+        ms = timed(lambda: st(x, y), 4 * K)
+        fl = W.c2_flops_per_clip()
+        out["c2"] = {"batch": 64, "T": 64, "d": 512, "head": "GRU_1L", "train_ms": ms, "train_clips_per_s": 64 / ms * 1e3,
+                     "model_tflops": 3 * fl * 64 / ms / 1e9}
+        st.release_graphs()
+        with torch.no_grad():
+            gi = torch.randn(64, 64, 3 * 512, device=dev, dtype=torch.bfloat16)
+            gru = model.models_dict["GRU_1L"].sequence_nn
+            with ops.precision("bf16"):
+                rec = lambda: ops._GRU.apply(gi, gru.weight_hh_l0, gru.bias_hh_l0, False)
+                for _ in range(3):
+                    rec()
+                ms_r = timed(rec, 4 * K)
+        out["c2"]["recurrence_fwd_us_per_time_step"] = ms_r * 1e3 / 64
+        del st, model
+        ops.clear_weight_cache()
+        torch.cuda.empty_cache()
+    return out
 
 
 def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
@@ -404,6 +487,8 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="clips per GPU per step")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c2 / c4_global1024 / c5 sub-results")
+    ap.add_argument("--extra-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

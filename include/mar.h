@@ -115,14 +115,21 @@ int mar_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n
  * row is 0 — torch 2.11 safe-softmax behaviour).  Dropout on P with p_drop when > 0. */
 int mar_attention_fwd(const void* qkv, const uint8_t* key_mask, void* out, float* lse,
                       int64_t B, int64_t T, int64_t H, int64_t dh, int dtype, float p_drop,
-                      const uint64_t* rng_state, uint32_t site, int engine, void* stream);
+                      const uint64_t* rng_state, uint32_t site, uint32_t* drop_bits, int engine, void* stream);
+/* Dropout on P: the call draws ONE keep bit per (b, h, query, key) from (rng_state, site) into `drop_bits`
+ * (mar_attention_dropbits_words() 32-bit words, 16 B aligned, caller-owned; may be NULL when p_drop == 0) before the
+ * attention kernel runs: word (bh*T + q)*W + (k >> 5), bit k & 31, W = 4*ceil(T/128).  Every engine reads the same
+ * bits and mar_attention_bwd takes the same buffer, so the backward mask IS the forward mask.  The keep probability
+ * is quantised to m/256, m = round((1 - p_drop)*256) (the granularity of torch's fused SDPA kernels); kept scores are
+ * scaled by 256/m. */
+int64_t mar_attention_dropbits_words(int64_t B, int64_t T, int64_t H);
 /* dqkv (B,T,3d) from dout (B,T,d).  work: mar_attention_bwd_work_floats() floats of 16 B-aligned scratch
- * (delta = rowsum(dO ⊙ O) (B,H,T), then the tcgen05 engine's fp32 dQ accumulator (B,T,d) when T > 128). */
+ * (delta = rowsum(dO ⊙ O) (B,H,T), then the tcgen05 engine's fp32 dQ accumulator (B,T,d) when T > 128).
+ * drop_bits: the buffer the forward call filled (NULL when p_drop == 0). */
 int64_t mar_attention_bwd_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh);
 int mar_attention_bwd(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout,
                       const float* lse, float* work, void* dqkv, int64_t B, int64_t T, int64_t H,
-                      int64_t dh, int dtype, float p_drop, const uint64_t* rng_state, uint32_t site,
-                      int engine, void* stream);
+                      int64_t dh, int dtype, float p_drop, const uint32_t* drop_bits, int engine, void* stream);
 
 /* ---- LayerNorm ------------------------------------------------------------------------------ */
 /* y = LN(x)·gamma + beta over the last dim D, eps inside the sqrt, biased variance

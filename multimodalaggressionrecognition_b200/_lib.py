@@ -36,9 +36,9 @@ PROTOTYPES = {
     "mar_linear_wgrad": (c_int, [P, P, c_int64, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, P]),
     "mar_cast_weight": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
     "mar_cast": (c_int, [P, c_int, P, c_int, c_int64, P]),
-    "mar_attention_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, c_uint32, c_int, P]),
-    "mar_attention_bwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P,
-                                  c_uint32, c_int, P]),
+    "mar_attention_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, c_uint32, P, c_int, P]),
+    "mar_attention_dropbits_words": (c_int64, [c_int64, c_int64, c_int64]),
+    "mar_attention_bwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, c_int, P]),
     "mar_attention_bwd_work_floats": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
     "mar_layernorm_fwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_float, c_int, P]),
     "mar_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, P]),

@@ -151,45 +151,58 @@ int mar_linear_wgrad(const void* dz, const void* x, int64_t ldx, float* dw, int6
 
 // ------------------------------------------------------------------------------------------
 int mar_attention_fwd(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
-                      int64_t dh, int dtype, float p_drop, const uint64_t* rng_state, uint32_t site, int engine,
-                      void* stream) {
+                      int64_t dh, int dtype, float p_drop, const uint64_t* rng_state, uint32_t site, uint32_t* drop_bits,
+                      int engine, void* stream) {
   MAR_CHECK_ARG(qkv && out && lse, "mar_attention_fwd: null pointer");
   MAR_CHECK_ARG(B >= 0 && T > 0 && H > 0 && dh > 0, "mar_attention_fwd: bad shape");
   MAR_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "mar_attention_fwd: p_drop out of range");
-  MAR_CHECK_ARG(p_drop == 0.f || rng_state, "mar_attention_fwd: dropout needs rng_state");
+  MAR_CHECK_ARG(p_drop == 0.f || (rng_state && drop_bits), "mar_attention_fwd: dropout needs rng_state and the keep-bit buffer");
+  MAR_CHECK_ARG((uintptr_t)drop_bits % 16 == 0, "mar_attention_fwd: drop_bits must be 16 B aligned");
   MAR_CHECK_ARG(B * H < (1ll << 31) && T < (1ll << 31), "mar_attention_fwd: shape too large");
   if (B == 0) return MAR_OK;
+  if (p_drop > 0.f) {          // draw this call's keep bits once: every engine, and the backward pass, reads them
+    int rc = attention_dropbits(drop_bits, B, T, H, p_drop, rng_state, site, S(stream));
+    if (rc) return rc;
+  }
+  const uint32_t* dbits = p_drop > 0.f ? drop_bits : nullptr;
   const bool mma_ok = attention_mma_supported(T, dh, dtype);
   if (engine == MAR_ENGINE_TCGEN05 && !mma_ok) MAR_UNSUPPORTED("mar_attention_fwd: tensor-core engine cannot take dh=%lld dtype=%d", (long long)dh, dtype);
   if (engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && mma_ok && !env_flag("MAR_FORCE_SIMT"))) {
     mar_set_engine(MAR_ENGINE_TCGEN05);
     // tcgen05/TMEM kernel where it applies; the mma.sync kernel covers the remaining head dims (MAR_ATTN_MMA=1 forces it)
     if (attention_tc_supported(B, T, H, dh, dtype) && !env_flag("MAR_ATTN_MMA"))
-      return attention_fwd_tc(qkv, key_mask, out, lse, B, T, H, dh, p_drop, rng_state, site, S(stream));
-    return attention_fwd_mma(qkv, key_mask, out, lse, B, T, H, dh, p_drop, rng_state, site, S(stream));
+      return attention_fwd_tc(qkv, key_mask, out, lse, B, T, H, dh, p_drop, dbits, S(stream));
+    return attention_fwd_mma(qkv, key_mask, out, lse, B, T, H, dh, p_drop, dbits, S(stream));
   }
   mar_set_engine(MAR_ENGINE_SIMT);
-  return attention_fwd_simt(qkv, key_mask, out, lse, B, T, H, dh, dtype, p_drop, rng_state, site, S(stream));
+  return attention_fwd_simt(qkv, key_mask, out, lse, B, T, H, dh, dtype, p_drop, dbits, S(stream));
+}
+
+int64_t mar_attention_dropbits_words(int64_t B, int64_t T, int64_t H) {
+  if (B <= 0 || T <= 0 || H <= 0) return 0;
+  return attention_dropbits_words(B, T, H);
 }
 
 int mar_attention_bwd(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
                       float* delta, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, int dtype, float p_drop,
-                      const uint64_t* rng_state, uint32_t site, int engine, void* stream) {
+                      const uint32_t* drop_bits, int engine, void* stream) {
   MAR_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "mar_attention_bwd: null pointer");
   MAR_CHECK_ARG(B >= 0 && T > 0 && H > 0 && dh > 0, "mar_attention_bwd: bad shape");
   MAR_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "mar_attention_bwd: p_drop out of range");
-  MAR_CHECK_ARG(p_drop == 0.f || rng_state, "mar_attention_bwd: dropout needs rng_state");
+  MAR_CHECK_ARG(p_drop == 0.f || drop_bits, "mar_attention_bwd: dropout needs the keep bits of the forward call");
+  MAR_CHECK_ARG((uintptr_t)drop_bits % 16 == 0, "mar_attention_bwd: drop_bits must be 16 B aligned");
   if (B == 0) return MAR_OK;
+  const uint32_t* dbits = p_drop > 0.f ? drop_bits : nullptr;
   const bool mma_ok = attention_mma_supported(T, dh, dtype);
   if (engine == MAR_ENGINE_TCGEN05 && !mma_ok) MAR_UNSUPPORTED("mar_attention_bwd: tensor-core engine cannot take dh=%lld dtype=%d", (long long)dh, dtype);
   if (engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && mma_ok && !env_flag("MAR_FORCE_SIMT"))) {
     mar_set_engine(MAR_ENGINE_TCGEN05);
     if (attention_tc_supported(B, T, H, dh, dtype) && !env_flag("MAR_ATTN_MMA") && !env_flag("MAR_ATTN_BWD_MMA"))
-      return attention_bwd_tc(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p_drop, rng_state, site, S(stream));
-    return attention_bwd_mma(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p_drop, rng_state, site, S(stream));
+      return attention_bwd_tc(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p_drop, dbits, S(stream));
+    return attention_bwd_mma(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p_drop, dbits, S(stream));
   }
   mar_set_engine(MAR_ENGINE_SIMT);
-  return attention_bwd_simt(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, dtype, p_drop, rng_state, site, S(stream));
+  return attention_bwd_simt(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, dtype, p_drop, dbits, S(stream));
 }
 
 int64_t mar_attention_bwd_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh) {

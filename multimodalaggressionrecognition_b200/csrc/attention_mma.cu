@@ -114,7 +114,7 @@ struct Dims { int B, T, H; };
 template <int DH>
 __global__ void __launch_bounds__(128)
 attn_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ key_mask, bf16* __restrict__ out,
-                    float* __restrict__ lse, Dims dm, float p_drop, const uint64_t* __restrict__ rng, uint32_t site) {
+                    float* __restrict__ lse, Dims dm, float p_drop, const uint32_t* __restrict__ dbits) {
   constexpr int LD = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
@@ -129,9 +129,7 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ ke
   const int nkv = (T + BN - 1) / BN;
   const float scale2 = rsqrtf((float)DH) * LOG2E;
   const bool drop = p_drop > 0.f;
-  DropKey dk;
-  if (drop) dk = make_drop_key(rng, site, p_drop);
-  const uint64_t Tp = (uint64_t)((T + 1) & ~1);
+  const DropBits dk = make_drop_bits(dbits, T, p_drop);
 
   auto load_kv = [&](int j, int buf) {
     load_tile<DH>(sK + buf * BN * LD, base + d, pitch, j * BN, T);
@@ -201,15 +199,13 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ ke
 #pragma unroll
     for (int n = 0; n < DH / 8; n++) { o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1]; }
     if (drop) {
-      const uint64_t row0 = ((uint64_t)bh * T + (uint64_t)(q0 + warp * 16 + g)) * Tp + (uint64_t)(j * BN);
-      const uint64_t row1 = row0 + 8 * Tp;
+      const int64_t row0 = (int64_t)bh * T + (q0 + warp * 16 + g), row1 = row0 + 8;
 #pragma unroll
       for (int n = 0; n < 8; n++) {
-        const uint64_t c = (uint64_t)(n * 8 + t4 * 2);
-        bool k0, k1;
-        drop_keep2(dk, (row0 + c) >> 1, k0, k1);
+        const int c = j * BN + n * 8 + t4 * 2;
+        bool k0 = dropbit(dk, row0, c), k1 = dropbit(dk, row0, c + 1);
         s[n][0] = k0 ? s[n][0] * dk.scale : 0.f; s[n][1] = k1 ? s[n][1] * dk.scale : 0.f;
-        drop_keep2(dk, (row1 + c) >> 1, k0, k1);
+        k0 = dropbit(dk, row1, c); k1 = dropbit(dk, row1, c + 1);
         s[n][2] = k0 ? s[n][2] * dk.scale : 0.f; s[n][3] = k1 ? s[n][3] * dk.scale : 0.f;
       }
     }
@@ -276,7 +272,7 @@ template <int DH>
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ key_mask, const bf16* __restrict__ dout,
                        const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, Dims dm,
-                       float p_drop, const uint64_t* __restrict__ rng, uint32_t site) {
+                       float p_drop, const uint32_t* __restrict__ dbits) {
   constexpr int LD = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);   // Q, later dQ staging
@@ -292,9 +288,7 @@ attn_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__
   const int nkv = (T + BN - 1) / BN;
   const float scale = rsqrtf((float)DH), scale2 = scale * LOG2E;
   const bool drop = p_drop > 0.f;
-  DropKey dk;
-  if (drop) dk = make_drop_key(rng, site, p_drop);
-  const uint64_t Tp = (uint64_t)((T + 1) & ~1);
+  const DropBits dk = make_drop_bits(dbits, T, p_drop);
 
   auto load_kv = [&](int j, int buf) {
     load_tile<DH>(sK + buf * BN * LD, base + d, pitch, j * BN, T);
@@ -341,8 +335,7 @@ attn_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__
     }
     mma_a_xt<DH>(s, qf, k_s, lane);
     mma_a_xt<DH>(dp, of, v_s, lane);
-    const uint64_t row0 = ((uint64_t)bh * T + (uint64_t)(q0 + warp * 16 + g)) * Tp + (uint64_t)(j * BN);
-    const uint64_t row1 = row0 + 8 * Tp;
+    const int64_t row0 = (int64_t)bh * T + (q0 + warp * 16 + g), row1 = row0 + 8;
 #pragma unroll
     for (int n = 0; n < 8; n++) {
       const int c = n * 8 + t4 * 2;
@@ -351,10 +344,9 @@ attn_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__
       float p2 = v0 ? exp2f(s[n][2] * scale2 - l2[1]) : 0.f, p3 = v1 ? exp2f(s[n][3] * scale2 - l2[1]) : 0.f;
       float d0 = dp[n][0], d1 = dp[n][1], d2 = dp[n][2], d3 = dp[n][3];
       if (drop) {
-        bool k0, k1;
-        drop_keep2(dk, (row0 + (uint64_t)c) >> 1, k0, k1);
+        bool k0 = dropbit(dk, row0, j * BN + c), k1 = dropbit(dk, row0, j * BN + c + 1);
         d0 = k0 ? d0 * dk.scale : 0.f; d1 = k1 ? d1 * dk.scale : 0.f;
-        drop_keep2(dk, (row1 + (uint64_t)c) >> 1, k0, k1);
+        k0 = dropbit(dk, row1, j * BN + c); k1 = dropbit(dk, row1, j * BN + c + 1);
         d2 = k0 ? d2 * dk.scale : 0.f; d3 = k1 ? d3 * dk.scale : 0.f;
       }
       s[n][0] = p0 * (d0 - dl[0]); s[n][1] = p1 * (d1 - dl[0]);
@@ -390,7 +382,7 @@ template <int DH>
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ key_mask, const bf16* __restrict__ dout,
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, Dims dm,
-                        float p_drop, const uint64_t* __restrict__ rng, uint32_t site) {
+                        float p_drop, const uint32_t* __restrict__ dbits) {
   constexpr int LD = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* sK = reinterpret_cast<bf16*>(smem_raw);   // K (own keys), later dK staging
@@ -408,9 +400,7 @@ attn_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict_
   const int nq = (T + BN - 1) / BN;
   const float scale = rsqrtf((float)DH), scale2 = scale * LOG2E;
   const bool drop = p_drop > 0.f;
-  DropKey dk;
-  if (drop) dk = make_drop_key(rng, site, p_drop);
-  const uint64_t Tp = (uint64_t)((T + 1) & ~1);
+  const DropBits dk = make_drop_bits(dbits, T, p_drop);
 
   auto load_q = [&](int j, int buf) {
     load_tile<DH>(sQ + buf * BN * LD, base, pitch, j * BN, T);
@@ -473,10 +463,9 @@ attn_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict_
         float q0v = p0, q1v = p1, q2v = p2, q3v = p3;      // P~ (dropped, scaled)
         if (drop) {
           // element (query q, key k): index (bh*T + q)*Tp + k ; the two queries of this thread are adjacent COLUMNS
-          const uint64_t qrow0 = ((uint64_t)bh * T + (uint64_t)(j * BN + c)) * Tp;
-          const uint64_t qrow1 = qrow0 + Tp;
-          const bool a0 = drop_keep(dk, qrow0 + (uint64_t)ka), a1 = drop_keep(dk, qrow1 + (uint64_t)ka);
-          const bool b0 = drop_keep(dk, qrow0 + (uint64_t)kb), b1 = drop_keep(dk, qrow1 + (uint64_t)kb);
+          const int64_t qrow0 = (int64_t)bh * T + (j * BN + c), qrow1 = qrow0 + 1;
+          const bool a0 = dropbit(dk, qrow0, (int)ka), a1 = dropbit(dk, qrow1, (int)ka);
+          const bool b0 = dropbit(dk, qrow0, (int)kb), b1 = dropbit(dk, qrow1, (int)kb);
           q0v = a0 ? p0 * dk.scale : 0.f; q1v = a1 ? p1 * dk.scale : 0.f;
           q2v = b0 ? p2 * dk.scale : 0.f; q3v = b1 ? p3 * dk.scale : 0.f;
           d0 = a0 ? d0 * dk.scale : 0.f; d1 = a1 ? d1 * dk.scale : 0.f;
@@ -518,21 +507,21 @@ attn_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict_
 
 template <int DH>
 int fwd_launch(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H, float p,
-               const uint64_t* rng, uint32_t site, cudaStream_t st) {
+               const uint32_t* dbits, cudaStream_t st) {
   constexpr int LD = DH + 8;
   constexpr int smem = (BM + 4 * BN) * LD * 2 + 2 * BN;
   static bool cfg = false;
   if (!cfg) { MAR_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cfg = true; }
   Dims dm{(int)B, (int)T, (int)H};
   dim3 grid((unsigned)ceil_div(T, BM), (unsigned)(B * H));
-  attn_fwd_mma_kernel<DH><<<grid, 128, smem, st>>>((const bf16*)qkv, key_mask, (bf16*)out, lse, dm, p, rng, site);
+  attn_fwd_mma_kernel<DH><<<grid, 128, smem, st>>>((const bf16*)qkv, key_mask, (bf16*)out, lse, dm, p, dbits);
   MAR_LAUNCH_CHECK("attn_fwd_mma");
   return MAR_OK;
 }
 
 template <int DH>
 int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* delta,
-               void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
+               void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint32_t* dbits, cudaStream_t st) {
   constexpr int LD = DH + 8;
   {
     int64_t warps = B * T * H;
@@ -545,14 +534,14 @@ int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const 
     constexpr int smem = (2 * BM + 4 * BN) * LD * 2 + 2 * BN;
     static bool cfg = false;
     if (!cfg) { MAR_CUDA(cudaFuncSetAttribute(attn_bwd_dq_mma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cfg = true; }
-    attn_bwd_dq_mma_kernel<DH><<<grid, 128, smem, st>>>((const bf16*)qkv, key_mask, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, p, rng, site);
+    attn_bwd_dq_mma_kernel<DH><<<grid, 128, smem, st>>>((const bf16*)qkv, key_mask, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, p, dbits);
     MAR_LAUNCH_CHECK("attn_bwd_dq_mma");
   }
   {
     constexpr int smem = (2 * BM + 4 * BN) * LD * 2 + 4 * BN * 4;
     static bool cfg = false;
     if (!cfg) { MAR_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_mma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cfg = true; }
-    attn_bwd_dkv_mma_kernel<DH><<<grid, 128, smem, st>>>((const bf16*)qkv, key_mask, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, p, rng, site);
+    attn_bwd_dkv_mma_kernel<DH><<<grid, 128, smem, st>>>((const bf16*)qkv, key_mask, (const bf16*)dout, lse, delta, (bf16*)dqkv, dm, p, dbits);
     MAR_LAUNCH_CHECK("attn_bwd_dkv_mma");
   }
   return MAR_OK;
@@ -565,28 +554,28 @@ bool attention_mma_supported(int64_t T, int64_t dh, int dtype) {
 }
 
 int attention_fwd_mma(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
-                      int64_t dh, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
+                      int64_t dh, float p, const uint32_t* dbits, cudaStream_t st) {
   MAR_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), "attention: pointers must be 16 B aligned");
   MAR_CHECK_ARG(B * H <= 65535, "attention: B*H = %lld exceeds one launch (65535)", (long long)(B * H));
   switch (dh) {
-    case 32: return fwd_launch<32>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
-    case 64: return fwd_launch<64>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
-    case 96: return fwd_launch<96>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
-    case 128: return fwd_launch<128>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
+    case 32: return fwd_launch<32>(qkv, key_mask, out, lse, B, T, H, p, dbits, st);
+    case 64: return fwd_launch<64>(qkv, key_mask, out, lse, B, T, H, p, dbits, st);
+    case 96: return fwd_launch<96>(qkv, key_mask, out, lse, B, T, H, p, dbits, st);
+    case 128: return fwd_launch<128>(qkv, key_mask, out, lse, B, T, H, p, dbits, st);
   }
   MAR_UNSUPPORTED("attention (tensor-core engine): head dim %lld", (long long)dh);
 }
 
 int attention_bwd_mma(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
-                      float* delta, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, float p, const uint64_t* rng,
-                      uint32_t site, cudaStream_t st) {
+                      float* delta, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, float p, const uint32_t* dbits,
+                      cudaStream_t st) {
   MAR_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)dout % 16 == 0) &&
                     ((uintptr_t)dqkv % 16 == 0), "attention: pointers must be 16 B aligned");
   switch (dh) {
-    case 32: return bwd_launch<32>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, p, rng, site, st);
-    case 64: return bwd_launch<64>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, p, rng, site, st);
-    case 96: return bwd_launch<96>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, p, rng, site, st);
-    case 128: return bwd_launch<128>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, p, rng, site, st);
+    case 32: return bwd_launch<32>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, p, dbits, st);
+    case 64: return bwd_launch<64>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, p, dbits, st);
+    case 96: return bwd_launch<96>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, p, dbits, st);
+    case 128: return bwd_launch<128>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, p, dbits, st);
   }
   MAR_UNSUPPORTED("attention (tensor-core engine): head dim %lld", (long long)dh);
 }

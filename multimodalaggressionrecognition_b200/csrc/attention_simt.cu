@@ -31,7 +31,7 @@ __device__ __forceinline__ void load_rows_to_smem(float* dst, int ld, const T* s
 template <typename T>
 __global__ void __launch_bounds__(128)
 attn_fwd_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ key_mask, T* __restrict__ out,
-                     float* __restrict__ lse, AttnDims dm, float p_drop, const uint64_t* __restrict__ rng, uint32_t site) {
+                     float* __restrict__ lse, AttnDims dm, float p_drop, const uint32_t* __restrict__ dbits) {
   extern __shared__ float sm[];
   const int dh = (int)dm.dh, ldk = dh + 1;
   float* Ks = sm;
@@ -45,8 +45,7 @@ attn_fwd_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ key_
   const T* qbase = qkv + b * dm.T * rs + h * dm.dh;
   const float scale = rsqrtf((float)dh);
   const bool drop = p_drop > 0.f;
-  DropKey dk;
-  if (drop) dk = make_drop_key(rng, site, p_drop);
+  const DropBits dk = make_drop_bits(dbits, dm.T, p_drop);
 
   load_rows_to_smem<T>(Qs, dh, qbase, rs, q0, dm.T, dh, scale);
 
@@ -79,7 +78,7 @@ attn_fwd_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ key_
       else { p = valid ? expf(s - m_new) : 0.f; corr = expf(m[i] - m_new); }
       l[i] = l[i] * corr + warp_sum(p);
       m[i] = m_new;
-      if (drop) p = drop_keep(dk, ((uint64_t)bh * dm.T + q) * (uint64_t)((dm.T + 1) & ~1ll) + kk) ? p * dk.scale : 0.f;
+      if (drop) p = dropbit(dk, (int64_t)bh * dm.T + q, (int)kk) ? p * dk.scale : 0.f;
       Ps[warp * TILE + lane] = p;
       __syncwarp();
 #pragma unroll
@@ -130,7 +129,7 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ key_mask, const T* __restrict__ dout,
                         const float* __restrict__ lse, const float* __restrict__ delta, T* __restrict__ dqkv,
-                        AttnDims dm, float p_drop, const uint64_t* __restrict__ rng, uint32_t site) {
+                        AttnDims dm, float p_drop, const uint32_t* __restrict__ dbits) {
   extern __shared__ float sm[];
   const int dh = (int)dm.dh, ldk = dh + 1;
   float* Ks = sm;
@@ -145,8 +144,7 @@ attn_bwd_dq_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ k
   const T* qbase = qkv + b * dm.T * rs + h * dm.dh;
   const float scale = rsqrtf((float)dh);
   const bool drop = p_drop > 0.f;
-  DropKey dk;
-  if (drop) dk = make_drop_key(rng, site, p_drop);
+  const DropBits dk = make_drop_bits(dbits, dm.T, p_drop);
 
   load_rows_to_smem<T>(Qs, dh, qbase, rs, q0, dm.T, dh, scale);
   load_rows_to_smem<T>(dOs, dh, dout + b * dm.T * d + h * dm.dh, d, q0, dm.T, dh, 1.f);
@@ -179,7 +177,7 @@ attn_bwd_dq_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ k
         dp = fmaf(dOs[qi * dh + c], Vs[lane * ldk + c], dp);
       }
       float p = (valid && ls[i] != -INFINITY) ? expf(s - ls[i]) : 0.f;
-      if (drop) dp = drop_keep(dk, ((uint64_t)bh * dm.T + q) * (uint64_t)((dm.T + 1) & ~1ll) + kk) ? dp * dk.scale : 0.f;
+      if (drop) dp = dropbit(dk, (int64_t)bh * dm.T + q, (int)kk) ? dp * dk.scale : 0.f;
       const float ds = p * (dp - dl[i]);
       Ps[warp * TILE + lane] = ds;
       __syncwarp();
@@ -214,7 +212,7 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ key_mask, const T* __restrict__ dout,
                          const float* __restrict__ lse, const float* __restrict__ delta, T* __restrict__ dqkv,
-                         AttnDims dm, float p_drop, const uint64_t* __restrict__ rng, uint32_t site) {
+                         AttnDims dm, float p_drop, const uint32_t* __restrict__ dbits) {
   extern __shared__ float sm[];
   const int dh = (int)dm.dh, ldq = dh + 1;
   float* Qs = sm;                   // [TILE][dh+1] scaled queries
@@ -232,8 +230,7 @@ attn_bwd_dkv_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ 
   const T* qbase = qkv + b * dm.T * rs + h * dm.dh;
   const float scale = rsqrtf((float)dh);
   const bool drop = p_drop > 0.f;
-  DropKey dk;
-  if (drop) dk = make_drop_key(rng, site, p_drop);
+  const DropBits dk = make_drop_bits(dbits, dm.T, p_drop);
 
   load_rows_to_smem<T>(Ks, dh, qbase + d, rs, k0, dm.T, dh, 1.f);
   load_rows_to_smem<T>(Vs, dh, qbase + 2 * d, rs, k0, dm.T, dh, 1.f);
@@ -272,7 +269,7 @@ attn_bwd_dkv_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ 
       float p = qvalid ? expf(s - lq) : 0.f;
       float pd = p;
       if (drop) {
-        const bool keep = drop_keep(dk, ((uint64_t)bh * dm.T + q) * (uint64_t)((dm.T + 1) & ~1ll) + kk);
+        const bool keep = dropbit(dk, (int64_t)bh * dm.T + q, (int)kk);
         pd = keep ? p * dk.scale : 0.f;
         dp = keep ? dp * dk.scale : 0.f;
       }
@@ -313,21 +310,21 @@ attn_bwd_dkv_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ 
 
 template <typename T>
 int fwd_impl(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t Tn, int64_t H,
-             int64_t dh, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
+             int64_t dh, float p, const uint32_t* dbits, cudaStream_t st) {
   AttnDims dm{B, Tn, H, dh};
   size_t smem = (size_t)(2 * TILE * (dh + 1) + ROWS * dh + 4 * TILE) * sizeof(float);
   static size_t cfg_fwd = 0;
   if (smem > cfg_fwd) { cudaFuncSetAttribute(attn_fwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg_fwd = smem; }
   dim3 grid((unsigned)ceil_div(Tn, ROWS), (unsigned)(B * H));
-  attn_fwd_simt_kernel<T><<<grid, 128, smem, st>>>((const T*)qkv, key_mask, (T*)out, lse, dm, p, rng, site);
+  attn_fwd_simt_kernel<T><<<grid, 128, smem, st>>>((const T*)qkv, key_mask, (T*)out, lse, dm, p, dbits);
   MAR_LAUNCH_CHECK("attn_fwd_simt");
   return MAR_OK;
 }
 
 template <typename T>
 int bwd_impl(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
-             float* delta, void* dqkv, int64_t B, int64_t Tn, int64_t H, int64_t dh, float p, const uint64_t* rng,
-             uint32_t site, cudaStream_t st) {
+             float* delta, void* dqkv, int64_t B, int64_t Tn, int64_t H, int64_t dh, float p, const uint32_t* dbits,
+             cudaStream_t st) {
   AttnDims dm{B, Tn, H, dh};
   {
     int64_t warps = B * Tn * H;
@@ -340,7 +337,7 @@ int bwd_impl(const void* qkv, const uint8_t* key_mask, const void* out, const vo
     static size_t cfg_dq = 0;
     if (smem > cfg_dq) { cudaFuncSetAttribute(attn_bwd_dq_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg_dq = smem; }
     attn_bwd_dq_simt_kernel<T><<<grid, 128, smem, st>>>((const T*)qkv, key_mask, (const T*)dout, lse, delta, (T*)dqkv, dm,
-                                                        p, rng, site);
+                                                        p, dbits);
     MAR_LAUNCH_CHECK("attn_bwd_dq_simt");
   }
   {
@@ -348,7 +345,7 @@ int bwd_impl(const void* qkv, const uint8_t* key_mask, const void* out, const vo
     static size_t cfg_dkv = 0;
     if (smem > cfg_dkv) { cudaFuncSetAttribute(attn_bwd_dkv_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg_dkv = smem; }
     attn_bwd_dkv_simt_kernel<T><<<grid, 128, smem, st>>>((const T*)qkv, key_mask, (const T*)dout, lse, delta, (T*)dqkv, dm,
-                                                         p, rng, site);
+                                                         p, dbits);
     MAR_LAUNCH_CHECK("attn_bwd_dkv_simt");
   }
   return MAR_OK;
@@ -357,18 +354,18 @@ int bwd_impl(const void* qkv, const uint8_t* key_mask, const void* out, const vo
 }  // namespace
 
 int attention_fwd_simt(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
-                       int64_t dh, int dtype, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
+                       int64_t dh, int dtype, float p, const uint32_t* dbits, cudaStream_t st) {
   if (dh > 32 * NJMAX) MAR_UNSUPPORTED("attention (SIMT): head dim %lld > 128", (long long)dh);
-  if (dtype == MAR_BF16) return fwd_impl<bf16>(qkv, key_mask, out, lse, B, T, H, dh, p, rng, site, st);
-  if (dtype == MAR_F32) return fwd_impl<float>(qkv, key_mask, out, lse, B, T, H, dh, p, rng, site, st);
+  if (dtype == MAR_BF16) return fwd_impl<bf16>(qkv, key_mask, out, lse, B, T, H, dh, p, dbits, st);
+  if (dtype == MAR_F32) return fwd_impl<float>(qkv, key_mask, out, lse, B, T, H, dh, p, dbits, st);
   MAR_UNSUPPORTED("attention: dtype %d", dtype);
 }
 
 int attention_bwd_simt(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
                        float* delta, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, int dtype, float p,
-                       const uint64_t* rng, uint32_t site, cudaStream_t st) {
+                       const uint32_t* dbits, cudaStream_t st) {
   if (dh > 32 * NJMAX) MAR_UNSUPPORTED("attention (SIMT): head dim %lld > 128", (long long)dh);
-  if (dtype == MAR_BF16) return bwd_impl<bf16>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p, rng, site, st);
-  if (dtype == MAR_F32) return bwd_impl<float>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p, rng, site, st);
+  if (dtype == MAR_BF16) return bwd_impl<bf16>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p, dbits, st);
+  if (dtype == MAR_F32) return bwd_impl<float>(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p, dbits, st);
   MAR_UNSUPPORTED("attention: dtype %d", dtype);
 }

@@ -15,12 +15,12 @@
 //            tcgen05.st of P̃ into the columns S occupied.  The running max is only raised when the tile max
 //            exceeds it by 2^8 (lazy rescaling), in which case the O accumulator row is rescaled in TMEM.
 //
-// Dropout on P uses the shared counter hash (common.cuh) with the element index ((b·H+h)·T + q)·Tp + k, the
-// same function as the SIMT and mma.sync engines, so any engine's backward regenerates this forward's mask.
+// Dropout on P reads the call's keep bits (common.cuh DropBits: drawn once per call, shared by every engine and by
+// the backward pass): one 16 B load per query row and key tile, a bit test per score, no hashing in the loop.
 // Fully masked rows give O = 0 and LSE = -inf (torch 2.11 safe softmax).
 //
-// Roofline: tensor pipe (4·T²·dh FLOP per (b,h)); the softmax's exp2 (16/clk/SM) and the dropout hash
-// (integer ALU) bound it below the MMA rate — see DESIGN.md §4.2.
+// Roofline: tensor pipe (4·T²·dh FLOP per (b,h)); the softmax's exp2 (16/clk/SM) and its ALU work bound it below
+// the MMA rate — see DESIGN.md §4.2.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "attention.cuh"
@@ -42,12 +42,11 @@ struct FwdParams {
   float* lse;
   int B, T, H;
   float p_drop;
-  const uint64_t* rng;
-  uint32_t site;
+  const uint32_t* dbits;     // dropout keep bits (common.cuh DropBits), nullptr when p_drop == 0
 };
 
-// DROP: 0 = no dropout, 1 = dropout with 64-bit pair indices, 2 = dropout, every pair index of the launch fits 32 bits
-template <int DH, int DROP>
+// DROP: compile-time, the mask logic is not even compiled into the p = 0 kernel
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
   constexpr int NBOX = (DH + 63) / 64;
@@ -169,12 +168,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
     const int q = qt * BQ + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float scale2 = rsqrtf((float)DH) * LOG2E;
-    constexpr bool drop = DROP != 0;                        // compile-time: the hash is not even compiled into the p = 0 kernel
-    DropKey dk;
-    dk.key = 0; dk.thr16 = 0; dk.scale = 1.f;
-    if (drop) dk = make_drop_key(p.rng, p.site, p.p_drop);
-    const uint64_t Tp = (uint64_t)((T + 1) & ~1);
-    const uint64_t pair_row0 = (((uint64_t)bh * (uint64_t)T + (uint64_t)q) * Tp) >> 1;
+    constexpr bool drop = DROP;
+    // keep bits of this query row: 4 words per 128-key tile, one 16 B load per tile (rows >= T read the buffer's padding)
+    const DropBits db = make_drop_bits(p.dbits, T, drop ? p.p_drop : 0.f);
+    const uint4* brow = reinterpret_cast<const uint4*>(p.dbits + ((int64_t)bh * T + q) * db.W);
     float m_ref = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < n_kv; j++) {
@@ -225,8 +222,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
       }
       const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
 
-      // pass 2: P = exp2(s*scale2 - m), row sum, dropout, bf16 pack -> TMEM
-      const uint64_t pair_tile = pair_row0 + (uint64_t)(j * (BKV / 2));
+      // pass 2: P = exp2(s*scale2 - m), row sum, dropout (keep bits; the 1/(1-p) scale is applied to O at the end), bf16 pack -> TMEM
+      uint4 bw = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      if (drop) bw = __ldg(brow + j);
       for (int c = 0; c < nchunk; c++) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(lane_addr + COL_S + c * 32, r);
@@ -242,14 +240,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
         }
         uint32_t pk[16];
         if (drop) {
-          const uint64_t pair0 = pair_tile + (uint64_t)(c * 16);
+          const uint32_t dw = c == 0 ? bw.x : (c == 1 ? bw.y : (c == 2 ? bw.z : bw.w));
 #pragma unroll
-          for (int i = 0; i < 16; i++) {
-            bool k0, k1;
-            if (DROP == 2) drop_keep2_32(dk, (uint32_t)pair0 + (uint32_t)i, k0, k1);
-            else drop_keep2(dk, pair0 + (uint64_t)i, k0, k1);
-            pk[i] = pack_bf16x2(k0 ? pv[2 * i] * dk.scale : 0.f, k1 ? pv[2 * i + 1] * dk.scale : 0.f);
-          }
+          for (int i = 0; i < 16; i++)
+            pk[i] = pack_bf16x2(((dw >> (2 * i)) & 1u) ? pv[2 * i] : 0.f, ((dw >> (2 * i + 1)) & 1u) ? pv[2 * i + 1] : 0.f);
         } else {
 #pragma unroll
           for (int i = 0; i < 16; i++) pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
@@ -265,7 +259,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
     // epilogue: O / l -> bf16 -> global ; LSE
     mbar_wait(bar_pv, (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    const float inv = l_run > 0.f ? db.scale / l_run : 0.f;
     bf16* orow = p.out + ((int64_t)b * T + q) * d + h * DH;
 #pragma unroll
     for (int c = 0; c < DH / 32; c++) {
@@ -297,14 +291,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
 
 template <int DH>
 int fwd_launch(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H, float p,
-               const uint64_t* rng, uint32_t site, cudaStream_t st) {
+               const uint32_t* dbits, cudaStream_t st) {
   constexpr int NBOX = (DH + 63) / 64;
   constexpr int SMEM = 3 * NBOX * BOX_BYTES + MAX_KV_TILES * 16 + 64 + 1024;
   static bool cfg = false;
   if (!cfg) {
-    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     cfg = true;
   }
   CUtensorMap tm;
@@ -312,14 +305,11 @@ int fwd_launch(const void* qkv, const uint8_t* key_mask, void* out, float* lse, 
   if (rc) return rc;
   FwdParams prm;
   prm.key_mask = key_mask; prm.out = (bf16*)out; prm.lse = lse; prm.B = (int)B; prm.T = (int)T; prm.H = (int)H;
-  prm.p_drop = p; prm.rng = rng; prm.site = site;
+  prm.p_drop = p; prm.dbits = dbits;
   const int64_t q_tiles = ceil_div(T, BQ);
-  const int64_t Tp = (T + 1) & ~(int64_t)1;
-  const bool idx32 = (B * H * T + 128) * Tp / 2 + T < (int64_t)0xffffffffll;      // largest pair index any thread forms
   const unsigned grid = (unsigned)(B * H * q_tiles);
-  if (p > 0.f && idx32) attn_fwd_tc_kernel<DH, 2><<<grid, 192, SMEM, st>>>(tm, prm);
-  else if (p > 0.f) attn_fwd_tc_kernel<DH, 1><<<grid, 192, SMEM, st>>>(tm, prm);
-  else attn_fwd_tc_kernel<DH, 0><<<grid, 192, SMEM, st>>>(tm, prm);
+  if (p > 0.f) attn_fwd_tc_kernel<DH, true><<<grid, 192, SMEM, st>>>(tm, prm);
+  else attn_fwd_tc_kernel<DH, false><<<grid, 192, SMEM, st>>>(tm, prm);
   MAR_LAUNCH_CHECK("attn_fwd_tc");
   return MAR_OK;
 }
@@ -336,12 +326,14 @@ bool attention_tc_supported(int64_t B, int64_t T, int64_t H, int64_t dh, int dty
 }
 
 int attention_fwd_tc(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
-                     int64_t dh, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
-  MAR_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), "attention: pointers must be 16 B aligned");
+                     int64_t dh, float p, const uint32_t* dbits, cudaStream_t st) {
+  MAR_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)dbits % 16 == 0),
+                "attention: pointers must be 16 B aligned");
+  MAR_CHECK_ARG(p == 0.f || dbits, "attention: dropout needs the keep-bit buffer");
   switch (dh) {
-    case 64: return fwd_launch<64>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
-    case 96: return fwd_launch<96>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
-    case 128: return fwd_launch<128>(qkv, key_mask, out, lse, B, T, H, p, rng, site, st);
+    case 64: return fwd_launch<64>(qkv, key_mask, out, lse, B, T, H, p, dbits, st);
+    case 96: return fwd_launch<96>(qkv, key_mask, out, lse, B, T, H, p, dbits, st);
+    case 128: return fwd_launch<128>(qkv, key_mask, out, lse, B, T, H, p, dbits, st);
   }
   MAR_UNSUPPORTED("attention (tcgen05 engine): head dim %lld", (long long)dh);
 }

@@ -25,8 +25,9 @@
 //
 // TMEM columns: dK [0,dh) | dV [dh,2dh) | dQᵀ [2dh,2dh+64) | stage s: Sᵀ 64 (P̃ᵀ packed bf16 in its first 32)
 //               + dPᵀ 64 (dSᵀ packed in its first 32).   dh=96: 192+64+2·128 = 512.   dh=128: one stage.
-// Dropout: the shared counter hash with element index ((b·H+h)·T + q)·Tp + k (common.cuh), i.e. the mask the
-// forward of ANY engine drew.  Fully masked rows (LSE = -inf) contribute nothing.
+// Dropout: the keep bits the forward call drew (common.cuh DropBits), staged per query tile by the stager warp —
+// a thread's key is one bit position of its lane quarter's word, so the test is one AND per score.
+// Fully masked rows (LSE = -inf) contribute nothing.
 #include <algorithm>
 #include <type_traits>
 #include "common.cuh"
@@ -56,8 +57,7 @@ struct BwdParams {
   bf16* dqkv;         // (B,T,3d)
   int B, T, H;
   float p_drop;
-  const uint64_t* rng;
-  uint32_t site;
+  const uint32_t* dbits;     // dropout keep bits of the forward call (common.cuh DropBits), nullptr when p_drop == 0
   int smem_bytes;
 };
 
@@ -84,9 +84,8 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// DROP: 0 = no dropout (the mask hash is not compiled in), 1 = dropout with 64-bit pair indices, 2 = dropout and
-// every pair index of the launch fits 32 bits (true for all the reference's shapes)
-template <int DH, int DROP>
+// DROP: compile-time; the keep-bit logic is not compiled into the p = 0 kernel
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dq, const BwdParams p) {
@@ -111,7 +110,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
   float* sDQ = reinterpret_cast<float*>(sDS + 2 * DS_BYTES);   // [DQ_ROWS][DH] fp32 staging of a dQ block
   float* sL = sDQ + DQ_ROWS * DH;   // [LSTAGES][64] LSE in log2 units (+inf = no contribution)
   float* sD = sL + LSTAGES * BQ;                              // [LSTAGES][64] delta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + LSTAGES * BQ);
+  uint32_t* sB = reinterpret_cast<uint32_t*>(sD + LSTAGES * BQ);   // [LSTAGES][4 lane quarters][64 queries] dropout keep words
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + LSTAGES * 4 * BQ);
   uint64_t* bar_kv = bars + 0;
   uint64_t* bar_qdo = bars + 1;                 // [QSTAGES] Q_i / dO_i tiles landed
   uint64_t* bar_ld = bars + 5;                  // [LSTAGES] LSE / delta of tile i staged
@@ -253,7 +253,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- LSE / delta stager
+    // ---------------------------------------------------------------- LSE / delta / keep-bit stager
+    const int64_t bits_w = drop_words_per_row(T);
     for (int i = 0; i < n_q; i++) {
       const int s = i % LSTAGES;
       if (i >= LSTAGES) mbar_wait(bar_ldfree + s, ((i / LSTAGES) - 1) & 1);
@@ -267,6 +268,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
         }
         sL[s * BQ + k] = l;
         sD[s * BQ + k] = dl;
+        if (DROP) {     // the 4 keep words of (query q, this CTA's 128 keys), one per TMEM lane quarter
+          const uint4 w = q < T ? __ldg(reinterpret_cast<const uint4*>(p.dbits + ((int64_t)bh * T + q) * bits_w) + kt)
+                                : make_uint4(0u, 0u, 0u, 0u);
+          uint32_t* dst = sB + s * 4 * BQ + k;
+          dst[0] = w.x; dst[BQ] = w.y; dst[2 * BQ] = w.z; dst[3 * BQ] = w.w;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ld + s);
@@ -280,16 +287,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
     const bool kvalid = key < T && !(p.key_mask != nullptr && p.key_mask[(int64_t)b * T + key] != 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float scale = rsqrtf((float)DH), scale2 = scale * LOG2E;
-    constexpr bool drop = DROP != 0;
-    constexpr bool IDX32 = DROP == 2;
-    DropKey dk;
-    dk.key = 0; dk.thr16 = 0; dk.scale = 1.f;
-    if (drop) dk = make_drop_key(p.rng, p.site, p.p_drop);
-    const uint64_t Tp = (uint64_t)((T + 1) & ~1);
-    const uint64_t half_tp = Tp >> 1;
-    const uint32_t keep_shift = (key & 1) ? 0u : 16u;    // which 16-bit half of the pair hash belongs to this key
-    const uint32_t thr_hi = dk.thr16 << 16;
-    const uint32_t half_tp32 = (uint32_t)half_tp;
+    constexpr bool drop = DROP;
+    const float dscale = drop ? 256.f / (float)drop_keep_m(p.p_drop) : 1.f;     // 1 / keep probability (common.cuh DropBits)
+    const uint32_t lanebit = 1u << lane;                 // this key's bit in the keep word of its lane quarter
     // dSᵀ smem row of this key: [row][64 queries], 16 B chunks XOR-swizzled by (row % 8)
     const int ds_off0 = row * 128 + (((chunk * 2) ^ (row & 7)) << 4);
     const int ds_off1 = row * 128 + (((chunk * 2 + 1) ^ (row & 7)) << 4);
@@ -310,9 +310,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
         uint32_t rs[16], rp[16];
         tmem_ld_32x32b_x16(col + chunk * 16, rs);
         tmem_ld_32x32b_x16(col + 64 + chunk * 16, rp);
-        // pair index of element (q, key): (((bh*T + q) * Tp) >> 1) + (key >> 1)
-        uint64_t pair = (((uint64_t)bh * (uint64_t)T + (uint64_t)(q_tile(i) * BQ + chunk * 16)) * Tp >> 1) + (uint64_t)(key >> 1);
-        uint32_t pair32 = (uint32_t)pair;
+        const uint32_t b_addr = smem_u32(sB + (ls * 4 + quarter) * BQ + chunk * 16);
         const uint32_t l_addr = smem_u32(l_s), d_addr = smem_u32(d_s);
         // the whole 16-column chunk inside the sequence and every key of the warp valid: no per-element selects
         const bool fast = (chunk * 16 + 16 <= nq) && __all_sync(0xffffffffu, kvalid);
@@ -323,6 +321,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
           for (int e4 = 0; e4 < 16; e4 += 4) {
             const float4 l4 = lds128(l_addr + e4 * 4), d4 = lds128(d_addr + e4 * 4);
             const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (drop) b4 = lds128(b_addr + e4 * 4);
+            const uint32_t bv[4] = {__float_as_uint(b4.x), __float_as_uint(b4.y), __float_as_uint(b4.z), __float_as_uint(b4.w)};
             float pd[4], ds[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -332,16 +333,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
               if (!FAST) pr = ok ? pr : 0.f;
               float dp = __uint_as_float(rp[ql]);
               float pdv = pr;
-              if (drop) {
-                uint32_t r;
-                if (IDX32) { r = drop_rand_pair32(dk, pair32); pair32 += half_tp32; }
-                else { r = drop_rand_pair(dk, pair); pair += half_tp; }
-                const bool keep = (r << keep_shift) >= thr_hi;     // == (16-bit half of r) >= thr16
-                pdv = keep ? pr * dk.scale : 0.f;
-                dp = keep ? dp * dk.scale : 0.f;
+              if (drop) {               // P̃ goes unscaled into dV (scaled in the epilogue); dP = keep·dP̃ / keep-probability
+                const bool keep = (bv[u] & lanebit) != 0u;
+                pdv = keep ? pr : 0.f;
+                dp = keep ? dp : 0.f;
               }
               pd[u] = pdv;
-              ds[u] = pr * (dp - dv[u]);
+              ds[u] = pr * fmaf(dp, dscale, -dv[u]);
               if (!FAST) ds[u] = ok ? ds[u] : 0.f;
             }
             pk[e4 / 2] = pack_bf16x2(pd[0], pd[1]);
@@ -378,7 +376,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32b_x32(lane_addr + (which == 0 ? COL_DK : COL_DV) + chunk * 32, r);   // warp-collective
         tmem_ld_wait();
-        const float sc = which == 0 ? scale : 1.f;
+        const float sc = which == 0 ? scale : dscale;
         bf16* o = dst + (which == 0 ? d : 2 * d);
         if (key < T) {
 #pragma unroll
@@ -504,12 +502,12 @@ attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, i
   }
 }
 
-template <int DH, int DROP>
+template <int DH, bool DROP>
 int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
-               void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
+               void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint32_t* dbits, cudaStream_t st) {
   constexpr int NBOX = (DH + 63) / 64;
   constexpr int USED = 2 * NBOX * BOX_BYTES + 2 * QSTAGES * NBOX * QBOX_BYTES + 2 * BT * 128 + (DH <= 96 ? 32 : 16) * DH * 4 +
-                       2 * LSTAGES * BQ * 4 + 20 * 8 + 16;
+                       2 * LSTAGES * BQ * 4 + LSTAGES * 4 * BQ * 4 + 20 * 8 + 16;
   static_assert(USED + 1024 <= 232448, "attention backward: shared memory budget");
   constexpr int SMEM = USED + 1024;
   static_assert(SMEM <= 232448, "attention backward: shared memory budget");
@@ -543,7 +541,7 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
   }
   BwdParams prm;
   prm.key_mask = key_mask; prm.lse = lse; prm.delta = delta; prm.dq_acc = dq_acc; prm.dqkv = (bf16*)dqkv;
-  prm.B = (int)B; prm.T = (int)T; prm.H = (int)H; prm.p_drop = p; prm.rng = rng; prm.site = site; prm.smem_bytes = SMEM;
+  prm.B = (int)B; prm.T = (int)T; prm.H = (int)H; prm.p_drop = p; prm.dbits = dbits; prm.smem_bytes = SMEM;
   const int64_t n_t = ceil_div(T, BT);
   attn_bwd_tc_kernel<DH, DROP><<<(unsigned)(B * H * n_t), NTHREADS, SMEM, st>>>(tm_kv, tm_q, tm_do, tm_dq, prm);
   MAR_LAUNCH_CHECK("attn_bwd_tc");
@@ -558,12 +556,9 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
 
 template <int DH>
 int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
-               void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
-  const int64_t Tp = (T + 1) & ~(int64_t)1;
-  const bool idx32 = (B * H * T + 64) * Tp / 2 + T < (int64_t)0xffffffffll;      // largest pair index any thread forms
-  if (p <= 0.f) return bwd_launch_t<DH, 0>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st);
-  return idx32 ? bwd_launch_t<DH, 2>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st)
-               : bwd_launch_t<DH, 1>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st);
+               void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint32_t* dbits, cudaStream_t st) {
+  if (p <= 0.f) return bwd_launch_t<DH, false>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
+  return bwd_launch_t<DH, true>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
 }
 
 }  // namespace
@@ -573,14 +568,16 @@ int64_t attention_bwd_tc_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh
 }
 
 int attention_bwd_tc(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
-                     float* work, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, float p, const uint64_t* rng,
-                     uint32_t site, cudaStream_t st) {
+                     float* work, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, float p, const uint32_t* dbits,
+                     cudaStream_t st) {
   MAR_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)dout % 16 == 0) &&
-                    ((uintptr_t)dqkv % 16 == 0) && ((uintptr_t)work % 16 == 0), "attention: pointers must be 16 B aligned");
+                    ((uintptr_t)dqkv % 16 == 0) && ((uintptr_t)work % 16 == 0) && ((uintptr_t)dbits % 16 == 0),
+                "attention: pointers must be 16 B aligned");
+  MAR_CHECK_ARG(p == 0.f || dbits, "attention: dropout needs the keep-bit buffer of the forward call");
   switch (dh) {
-    case 64: return bwd_launch<64>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st);
-    case 96: return bwd_launch<96>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st);
-    case 128: return bwd_launch<128>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, rng, site, st);
+    case 64: return bwd_launch<64>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
+    case 96: return bwd_launch<96>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
+    case 128: return bwd_launch<128>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
   }
   MAR_UNSUPPORTED("attention backward (tcgen05 engine): head dim %lld", (long long)dh);
 }

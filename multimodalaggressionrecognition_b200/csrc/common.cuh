@@ -187,3 +187,37 @@ __device__ __forceinline__ void drop_keep2(const DropKey& k, uint64_t pair_index
   k0 = (r & 0xffffu) >= k.thr16;
   k1 = (r >> 16) >= k.thr16;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Attention dropout: ONE bit per (b, h, query, key), drawn once per attention call by attn_dropbits_kernel
+// (attention_dropbits.cu) from the same (seed, step, site) counter hash and kept for the backward pass
+// (1 bit per score: 16-25 MB per encoder layer at the reference's shapes).  Every engine — SIMT, mma.sync,
+// tcgen05, forward and backward — reads the same words, so their masks agree by construction, and none of
+// them spends ALU work on hashing inside the softmax loop (the hash was 8 of the forward's 13 and 11 of the
+// backward's 21 instructions per score).
+//   words[(bh·T + q)·W + (k >> 5)] bit (k & 31) = 1 ⇔ P[q,k] is kept;   W = 4·ceil(T / 128) words per query row.
+// The keep probability is quantised to 8 bits, keep = m / 256 with m = round((1 - p)·256) — the granularity torch's
+// own fused SDPA kernels use for their dropout threshold — and the kept scores are scaled by 256 / m, so the
+// expectation is exact.
+// ---------------------------------------------------------------------------------------------
+struct DropBits {
+  const uint32_t* words;
+  int64_t W;        // words per (b,h,q) row
+  float scale;      // 256 / m
+};
+__host__ __device__ __forceinline__ int drop_keep_m(float p) {
+  int m = (int)((1.f - p) * 256.f + 0.5f);
+  return m < 1 ? 1 : (m > 255 ? 255 : m);
+}
+__host__ __device__ __forceinline__ int64_t drop_words_per_row(int64_t T) { return 4 * ((T + 127) / 128); }
+__device__ __forceinline__ DropBits make_drop_bits(const uint32_t* words, int64_t T, float p) {
+  DropBits d;
+  d.words = words;
+  d.W = drop_words_per_row(T);
+  d.scale = p > 0.f ? 256.f / (float)drop_keep_m(p) : 1.f;
+  return d;
+}
+// keep flag of score (row = bh·T + q, key k).  Rows up to 256 past the end of the tensor are readable (padding).
+__device__ __forceinline__ bool dropbit(const DropBits& d, int64_t row, int k) {
+  return (d.words[row * d.W + (k >> 5)] >> (k & 31)) & 1u;
+}

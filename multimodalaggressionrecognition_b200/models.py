@@ -494,7 +494,7 @@ class EqualSizedTransformerModalitiesFusion(nn.Module):
         fused = encoder_forward(self.modality_fusion_transformer, concat, key_mask)
         if len(blocks) == 1:
             return {next(iter(feats)): fused}
-        return {name: ops.slice_time(fused, b0, b1) for name, (b0, b1) in bounds.items()}
+        return dict(zip(bounds.keys(), ops.split_time(fused, list(bounds.values()))))
 
     def forward(self, modalities_features_dict):
         return self._fuse(modalities_features_dict)

@@ -417,20 +417,22 @@ class _Attention(torch.autograd.Function):
         dh = d // H
         out = torch.empty((B, T, d), dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
-        rng, site = None, 0
+        rng, site, bits = None, 0, None
         if p > 0.0:
             rng = _rng.state(qkv.device)
             site = _rng.next_site()
+            # one keep bit per score, drawn by the call and kept for backward (T = 250: 16 MB)
+            bits = torch.empty(int(_lib.load().mar_attention_dropbits_words(B, T, H)), dtype=torch.int32, device=qkv.device)
         call("mar_attention_fwd", qkv.data_ptr(), _p(key_mask), out.data_ptr(), lse.data_ptr(), B, T, H, dh, _dt(qkv),
-             float(p), _p(rng), site, _eng(), _stream())
+             float(p), _p(rng), site, _p(bits), _eng(), _stream())
         ctx.dims = (B, T, H, dh)
-        ctx.p, ctx.site, ctx.rng, ctx.eng = float(p), site, rng, _eng()
-        ctx.save_for_backward(qkv, out, lse, key_mask)
+        ctx.p, ctx.eng = float(p), _eng()
+        ctx.save_for_backward(qkv, out, lse, key_mask, bits)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, out, lse, key_mask = ctx.saved_tensors
+        qkv, out, lse, key_mask, bits = ctx.saved_tensors
         B, T, H, dh = ctx.dims
         if dout.dtype != qkv.dtype:
             dout = _Cast.apply(dout, qkv.dtype)
@@ -439,7 +441,7 @@ class _Attention(torch.autograd.Function):
         nwork = int(_lib.load().mar_attention_bwd_work_floats(B, T, H, dh))
         work = torch.empty(nwork, dtype=torch.float32, device=qkv.device)
         call("mar_attention_bwd", qkv.data_ptr(), _p(key_mask), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-             work.data_ptr(), dqkv.data_ptr(), B, T, H, dh, _dt(qkv), ctx.p, _p(ctx.rng), ctx.site, ctx.eng, _stream())
+             work.data_ptr(), dqkv.data_ptr(), B, T, H, dh, _dt(qkv), ctx.p, _p(bits), ctx.eng, _stream())
         return dqkv, None, None, None
 
 
@@ -570,27 +572,51 @@ def concat_time(xs) -> torch.Tensor:
     return _ConcatT.apply(*xs)
 
 
-class _SliceT(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, t0, t1):
-        B, total, D = x.shape
-        out = torch.empty((B, t1 - t0, D), dtype=x.dtype, device=x.device)
-        call("mar_concat_rows", x.data_ptr(), out.data_ptr(), B, t1 - t0, total, t0, D, _dt(x), 0, _stream())
-        ctx.dims = (B, total, D, t0, t1)
-        return out
+class _SplitT(torch.autograd.Function):
+    """All time slices of x (B,total,D) at once.  Backward writes every incoming gradient into ITS rows of ONE buffer:
+    no zero-fill and no adds (one Function per slice gave autograd a zero-padded (B,total,D) tensor per slice to sum).
+    A slice nobody used downstream arrives as None and its rows are zeroed."""
 
     @staticmethod
-    def backward(ctx, g):
-        B, total, D, t0, t1 = ctx.dims
-        g = g.contiguous()
-        dx = torch.zeros((B, total, D), dtype=g.dtype, device=g.device)
-        call("mar_concat_rows", g.data_ptr(), dx.data_ptr(), B, t1 - t0, total, t0, D, _dt(g), 1, _stream())
-        return dx, None, None
+    def forward(ctx, x, *bounds):
+        B, total, D = x.shape
+        outs = []
+        for t0, t1 in zip(bounds[0::2], bounds[1::2]):
+            out = torch.empty((B, t1 - t0, D), dtype=x.dtype, device=x.device)
+            call("mar_concat_rows", x.data_ptr(), out.data_ptr(), B, t1 - t0, total, t0, D, _dt(x), 0, _stream())
+            outs.append(out)
+        ctx.dims = (B, total, D)
+        ctx.bounds = bounds
+        ctx.dtype = x.dtype
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        B, total, D = ctx.dims
+        dev = next(g for g in gs if g is not None).device
+        covered = sorted((t0, t1) for t0, t1 in zip(ctx.bounds[0::2], ctx.bounds[1::2]))
+        full = all(g is not None for g in gs) and covered[0][0] == 0 and covered[-1][1] == total and \
+            all(a[1] == b[0] for a, b in zip(covered[:-1], covered[1:]))
+        dx = (torch.empty if full else torch.zeros)((B, total, D), dtype=ctx.dtype, device=dev)
+        for g, t0, t1 in zip(gs, ctx.bounds[0::2], ctx.bounds[1::2]):
+            if g is None:
+                continue
+            if g.dtype != ctx.dtype:
+                g = _Cast.apply(g, ctx.dtype)
+            g = g.contiguous()
+            call("mar_concat_rows", g.data_ptr(), dx.data_ptr(), B, t1 - t0, total, t0, D, _dt(g), 1, _stream())
+        return (dx,) + (None,) * len(ctx.bounds)
+
+
+def split_time(x: torch.Tensor, bounds) -> Tuple[torch.Tensor, ...]:
+    """Contiguous copies of x[:, t0:t1] for every (t0, t1) of `bounds` (models.py:430)."""
+    flat = [int(v) for b in bounds for v in b]
+    return _SplitT.apply(x.contiguous(), *flat)
 
 
 def slice_time(x: torch.Tensor, t0: int, t1: int) -> torch.Tensor:
     """Contiguous copy of x[:, t0:t1] (models.py:430)."""
-    return _SliceT.apply(x.contiguous(), int(t0), int(t1))
+    return split_time(x, [(t0, t1)])[0]
 
 
 # --------------------------------------------------------------------------------------

@@ -179,6 +179,31 @@ def test_attention_fwd_bwd(B, T, H, dh, mode, masked):
     assert_close(qg.grad.float().cpu(), qr.grad, tol, "attention dqkv")
 
 
+@pytest.mark.parametrize("T,H", [(1024, 2), (4096, 1)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_attention_long_sequences_against_oracle(T, H, masked):
+    """BASELINE config 5's fused lengths (2T up to 4096): the tcgen05 forward and backward against the CPU oracle,
+    not only against this repo's other engine (nothing above T = 314 was checked against the oracle)."""
+    B, dh = 1, 96
+    d = H * dh
+    qkv = bf16_round(torch.randn(B, T, 3 * d))
+    go = bf16_round(torch.randn(B, T, d))
+    mask = None
+    if masked:
+        mask = torch.rand(B, T) < 0.3
+        mask[0, T - T // 5:] = True
+    qr = qkv.clone().requires_grad_(True)
+    outr = _attn_ref(qr, mask, H)
+    outr.backward(go)
+    qg = qkv.to(DEV).requires_grad_(True)
+    with mar.precision("bf16"), mar.engine("tensor"):
+        out = ops.attention(qg, None if mask is None else mask.to(DEV), H, 0.0)
+        out.backward(go.to(DEV).to(out.dtype))
+    assert_close(out.float().cpu(), outr, BF16_TOL, f"attention out T={T}")
+    for name, sl in (("dQ", slice(0, d)), ("dK", slice(d, 2 * d)), ("dV", slice(2 * d, 3 * d))):
+        assert_close(qg.grad.float().cpu()[..., sl], qr.grad[..., sl], BF16_TOL, f"attention {name} T={T}")
+
+
 @pytest.mark.parametrize("B,T,H,dh", [(2, 128, 2, 96), (2, 129, 2, 64), (1, 256, 8, 96), (2, 700, 2, 128), (1, 1100, 1, 96),
                                       (5, 17, 3, 64)])
 @pytest.mark.parametrize("p", [0.0, 0.2])
@@ -240,6 +265,54 @@ def test_attention_dropout_statistics_and_grad_consistency(mode):
     total_from_dv = dv.reshape(B, T, H, dh)[..., 0].sum(dim=1)      # (B,H)
     total_from_o = o.reshape(B, T, H, dh)[..., 0].sum(dim=1)
     assert_close(total_from_dv, total_from_o, 2e-2 if mode == "bf16" else 1e-4, "dropout mask fwd/bwd consistency")
+
+
+@pytest.mark.parametrize("p", [0.1, 0.25, 0.5, 0.9])
+def test_attention_keep_bits_are_bernoulli_and_shared_by_every_engine(p):
+    """The keep bits one attention call draws (include/mar.h, mar_attention_fwd): the fraction of set bits is the
+    quantised keep probability m/256 with m = round((1-p)*256), neighbouring bits and neighbouring rows are
+    uncorrelated, another site / step draws other bits, and all three engines — SIMT, mma.sync, tcgen05 — produce the
+    same P~ from them (same outputs up to their arithmetic)."""
+    from multimodalaggressionrecognition_b200 import _lib
+    from multimodalaggressionrecognition_b200._lib import call
+    B, T, H, dh = 3, 200, 4, 64
+    d = H * dh
+    qkv = torch.randn(B, T, 3 * d, device=DEV).to(torch.bfloat16)
+    nwords = int(_lib.load().mar_attention_dropbits_words(B, T, H))
+    W = 4 * ((T + 127) // 128)
+    assert nwords == (B * H * T + 256) * W
+    st = torch.cuda.current_stream().cuda_stream
+    rng = ops._rng.state(torch.device(DEV))
+    outs, bits_of = {}, {}
+    for name, eng, env in (("simt", _lib.ENGINE_SIMT, None), ("tc", _lib.ENGINE_TCGEN05, None)):
+        bits = torch.zeros(nwords, dtype=torch.int32, device=DEV)
+        out = torch.empty(B, T, d, device=DEV, dtype=torch.bfloat16)
+        lse = torch.empty(B, H, T, device=DEV)
+        call("mar_attention_fwd", qkv.data_ptr(), None, out.data_ptr(), lse.data_ptr(), B, T, H, dh, _lib.MAR_BF16, p,
+             rng.data_ptr(), 77, bits.data_ptr(), eng, st)
+        outs[name], bits_of[name] = out.float(), bits
+    assert torch.equal(bits_of["simt"], bits_of["tc"])
+    assert_close(outs["tc"], outs["simt"], 2e-2, "tcgen05 vs SIMT under the same keep bits")
+    words = bits_of["tc"][: B * H * T * W].view(B * H * T, W).cpu().numpy().astype("uint32")
+    import numpy as np
+    bitmat = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(B * H * T, W * 32)[:, :T].astype(np.float64)
+    m = max(1, min(255, int((1 - p) * 256 + 0.5)))
+    frac, n = bitmat.mean(), bitmat.size
+    assert abs(frac - m / 256) < 5 * (0.25 / n) ** 0.5 + 1e-4, (frac, m / 256)
+    c = bitmat - frac
+    for a, b_ in ((c[:, 1:], c[:, :-1]), (c[1:], c[:-1]), (c[:, 32:], c[:, :-32])):   # next key, next row, same bit of the next word
+        corr = float((a * b_).mean() / max(frac * (1 - frac), 1e-9))
+        assert abs(corr) < 6 / n ** 0.5 + 2e-3, corr
+    other = torch.zeros(nwords, dtype=torch.int32, device=DEV)
+    call("mar_attention_fwd", qkv.data_ptr(), None, out.data_ptr(), lse.data_ptr(), B, T, H, dh, _lib.MAR_BF16, p,
+         rng.data_ptr(), 78, other.data_ptr(), _lib.ENGINE_TCGEN05, st)
+    assert not torch.equal(other, bits_of["tc"])
+    # the scale of the kept scores makes the expectation exact: V = 1 -> O = rowsum(P~), mean 1
+    qkv1 = qkv.clone()
+    qkv1[..., 2 * d:] = 1.0
+    call("mar_attention_fwd", qkv1.data_ptr(), None, out.data_ptr(), lse.data_ptr(), B, T, H, dh, _lib.MAR_BF16, p,
+         rng.data_ptr(), 79, other.data_ptr(), _lib.ENGINE_TCGEN05, st)
+    assert abs(float(out.float().mean()) - 1.0) < 0.03
 
 
 # ------------------------------------------------------------------------------------------
