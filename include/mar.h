@@ -87,15 +87,22 @@ int mar_linear_fwd(const void* x, int64_t ldx, const void* w, const float* bias,
 
 /* Backward through the epilogue: dz = dout ⊙ d(epilogue)/dz, and dbias += column-sum(dz) (fp32,
  * accumulated; pass NULL to skip).  `out` is the forward output (needed for the ReLU flags, may be
- * NULL otherwise).  dz may alias dout.  All of (M,N), contiguous. */
+ * NULL otherwise).  dz may alias dout.  All of (M,N), contiguous.
+ * pooled_rows = T > 0: the epilogue's output went through a mean over T consecutive rows (SequenceAverageFeatures
+ * after an adaptor, models.py:693-699, :105): dout is the POOLED gradient (M/T, N) and row r of the result reads
+ * dout row r / T scaled by 1/T — the broadcast is never materialised. */
 int mar_linear_bwd_epilogue(const void* dout, const void* out, void* dz, float* dbias,
                             int64_t M, int64_t N, int dtype, int out_dtype, int flags, float p_drop,
-                            const uint64_t* rng_state, uint32_t site, void* stream);
+                            const uint64_t* rng_state, uint32_t site, int64_t pooled_rows, void* stream);
 
 /* dx = dz·W (+ add).  dz (M,N); w (N,K); wt (K,N) = Wᵀ in the same dtype, required by the tcgen05
- * engine (K-major B operand), may be NULL for SIMT; add (M,K) or NULL; dx (M,K) row stride lddx. */
-int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* add, void* dx,
-                     int64_t lddx, int64_t M, int64_t N, int64_t K, int dtype, int engine, void* stream);
+ * engine (K-major B operand), may be NULL for SIMT; add (M,K) or NULL; dx (M,K) row stride lddx.
+ * act (M,K) row stride lddx or NULL (not together with add): the forward VALUE of this linear's input when that input
+ * came out of a ReLU(+dropout) epilogue — zero exactly where the activation's derivative is zero — so that
+ * dx = (dz·W) ⊙ (act > 0 ? act_scale : 0) leaves the GEMM with the producer's activation backward already applied
+ * (FFN linear2 → linear1 of transformer.py:980-982: the (M, d_ff) gradient is written once, masked). */
+int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* add, const void* act, float act_scale,
+                     void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K, int dtype, int engine, void* stream);
 
 /* dw (N,K) fp32 (+)= dzᵀ·x.  dz (M,N) contiguous, x (M,K) row stride ldx.  accumulate=0 overwrites. */
 int mar_linear_wgrad(const void* dz, const void* x, int64_t ldx, float* dw, int64_t M, int64_t N,

@@ -31,8 +31,8 @@ PROTOTYPES = {
     "mar_rng_advance": (c_int, [P, P]),
     "mar_linear_fwd": (c_int, [P, c_int64, P, P, P, c_int64, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
                                c_int, c_float, P, c_uint32, c_int, P]),
-    "mar_linear_bwd_epilogue": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_float, P, c_uint32, P]),
-    "mar_linear_dgrad": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P]),
+    "mar_linear_bwd_epilogue": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_float, P, c_uint32, c_int64, P]),
+    "mar_linear_dgrad": (c_int, [P, P, P, P, P, c_float, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P]),
     "mar_linear_wgrad": (c_int, [P, P, c_int64, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, P]),
     "mar_cast_weight": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
     "mar_cast": (c_int, [P, c_int, P, c_int, c_int64, P]),

@@ -104,22 +104,24 @@ int mar_linear_fwd(const void* x, int64_t ldx, const void* w, const float* bias,
   return gemm_simt(x, in_dtype, ldx, 1, w, in_dtype, 1, K, out, out_dtype, ldo, M, N, K, epi, S(stream));
 }
 
-int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* add, void* dx, int64_t lddx, int64_t M,
-                     int64_t N, int64_t K, int dtype, int engine, void* stream) {
+int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* add, const void* act, float act_scale,
+                     void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K, int dtype, int engine, void* stream) {
   MAR_CHECK_ARG(dz && (w || wt) && dx, "mar_linear_dgrad: null pointer");
   MAR_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lddx >= K, "mar_linear_dgrad: bad shape");
   MAR_CHECK_ARG(dtype == MAR_F32 || dtype == MAR_BF16, "mar_linear_dgrad: bad dtype %d", dtype);
+  MAR_CHECK_ARG(!(add && act), "mar_linear_dgrad: add and act are mutually exclusive");
   if (M == 0) return MAR_OK;
   TcGemmArgs a;
   a.A = dz; a.lda = N; a.B = wt; a.ldb = N; a.out = dx; a.ldo = lddx; a.out_fp32 = 0;
-  a.M = M; a.N = K; a.Kr = N; a.residual = add; a.ldr = lddx;
+  a.M = M; a.N = K; a.Kr = N; a.residual = add; a.ldr = lddx; a.aux = act; a.ldaux = lddx; a.aux_scale = act_scale;
   const bool tc_ok = dtype == MAR_BF16 && wt != nullptr && gemm_tcgen05_supported(a);
   if (engine == MAR_ENGINE_TCGEN05 && !tc_ok) MAR_UNSUPPORTED("mar_linear_dgrad: tcgen05 engine cannot take M=%lld N=%lld K=%lld (needs bf16 and wt)", (long long)M, (long long)N, (long long)K);
   const bool use_tc = engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && tc_ok && M >= 64 && K >= 64 && !env_flag("MAR_FORCE_SIMT"));
   if (use_tc) return gemm_tcgen05(a, S(stream));
-  if (skinny_supported(N) && w != nullptr) return skinny_dgrad(dz, w, add, dx, lddx, M, N, K, dtype, S(stream));
+  if (skinny_supported(N) && w != nullptr && act == nullptr) return skinny_dgrad(dz, w, add, dx, lddx, M, N, K, dtype, S(stream));
   SimtEpilogue epi;
   epi.residual = add; epi.ldr = lddx; epi.res_is_bf16 = dtype == MAR_BF16;
+  epi.aux = act; epi.ldaux = lddx; epi.aux_scale = act_scale;
   if (w != nullptr)   // dx(m,k) = Σ_n dz(m,n) W(n,k):  B(kr=n, col=k) = w[n*K + k]
     return gemm_simt(dz, dtype, N, 1, w, dtype, K, 1, dx, dtype, lddx, M, K, N, epi, S(stream));
   return gemm_simt(dz, dtype, N, 1, wt, dtype, 1, N, dx, dtype, lddx, M, K, N, epi, S(stream));

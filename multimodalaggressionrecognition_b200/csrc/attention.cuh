@@ -20,6 +20,9 @@ int attention_bwd_mma(const void* qkv, const uint8_t* key_mask, const void* out,
 bool attention_tc_supported(int64_t B, int64_t T, int64_t H, int64_t dh, int dtype);
 int attention_fwd_tc(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
                      int64_t dh, float p, const uint32_t* dbits, cudaStream_t st);
+// the same for T > 128: two query tiles per CTA, two softmax warp-groups (attention_tc2.cu)
+int attention_fwd_tc2(const void* qkv, const uint8_t* key_mask, void* out, float* lse, int64_t B, int64_t T, int64_t H,
+                      int64_t dh, float p, const uint32_t* dbits, cudaStream_t st);
 // backward: `work` holds attention_bwd_tc_work_floats() floats (delta, then the fp32 dQ accumulator when T > 128)
 int64_t attention_bwd_tc_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh);
 int attention_bwd_tc(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,

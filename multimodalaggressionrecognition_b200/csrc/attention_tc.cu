@@ -2,18 +2,23 @@
 //
 //   O = softmax(Q·Kᵀ/√dh + key mask)·V   per (batch b, head h), flash-style (scores never reach HBM).
 //
-// One CTA owns 128 query rows of one (b,h); two CTAs are resident per SM (96 KB smem, 256 TMEM columns each)
-// so one CTA's softmax overlaps the other CTA's MMAs.  192 threads:
-//   warp 0   lane 0: TMA producer + MMA issuer.  Q / K / V tiles are [128 rows x dh] bf16, staged by TMA
-//            (3-D tensor map (col, t, b): rows t >= T are ZERO-filled by the hardware, so tiles never read the
-//            next batch element) as 128 B-swizzled boxes of 64 columns.
+// One CTA owns 128 query rows of one (b,h); two CTAs are resident per SM (96 KB smem, 256 TMEM columns, 32 K registers
+// each) so one CTA's softmax overlaps the other CTA's MMAs, loads, prologue and epilogue.  256 threads:
+//   warp 0   TMA producer + MMA issuer (converged warp, one elected lane issues).  Q / K / V tiles are [128 rows x dh]
+//            bf16, staged by TMA (3-D tensor map (col, t, b): rows t >= T are ZERO-filled by the hardware, so tiles
+//            never read the next batch element) as 128 B-swizzled boxes of 64 columns.
 //            S = Q·Kᵀ      : tcgen05.mma  M=128, N=keys (16..128), K=dh     A,B from smem (K-major)
 //            O += P̃·V      : tcgen05.mma  M=128, N=dh,             K=keys   A = P̃ from TMEM, B = V from smem (MN-major)
-//   warp 1   TMEM allocator; packs the key-padding mask into 128-bit validity words per key tile.
-//   warps 2-5 softmax: thread r owns query row r (TMEM lane r).  Two passes over the S row in TMEM
-//            (tcgen05.ld 32 columns at a time): row max, then exp2 / row sum / dropout / bf16 pack and
-//            tcgen05.st of P̃ into the columns S occupied.  The running max is only raised when the tile max
-//            exceeds it by 2^8 (lazy rescaling), in which case the O accumulator row is rescaled in TMEM.
+//   warp 1   TMEM allocator; packs the key-padding mask into 128-bit validity words per key tile.  (warps 2-3 idle:
+//            setmaxnreg works on aligned groups of 4 warps — the helper group gives its registers to the softmax group)
+//   warps 4-7 softmax: thread r owns query row r (TMEM lane r) and reads its WHOLE score row once (4 tcgen05.ld in
+//            flight, one wait, 128 registers), takes the row max with 3-input FMNMX and goes straight to exp2 / row
+//            sum / keep-bit select / bf16 pack from the same registers, then tcgen05.st of P̃ into the columns S
+//            occupied.  (Round 1 read S twice in 32-column pieces with a wait after each: a chain of dependent TMEM
+//            round trips, 2 warps per scheduler, 46 % issue utilisation.)  The running max is only raised when the tile
+//            max exceeds it by 2^8 (lazy rescaling), in which case the O accumulator row is rescaled in TMEM.
+// Sequences of more than 512 keys go to the pair kernel (attention_tc2.cu: two query tiles per CTA share every K / V
+// tile and their softmax warp-groups ping-pong against the tensor pipe).
 //
 // Dropout on P reads the call's keep bits (common.cuh DropBits: drawn once per call, shared by every engine and by
 // the backward pass): one 16 B load per query row and key tile, a bit test per score, no hashing in the loop.
@@ -21,6 +26,7 @@
 //
 // Roofline: tensor pipe (4·T²·dh FLOP per (b,h)); the softmax's exp2 (16/clk/SM) and its ALU work bound it below
 // the MMA rate — see DESIGN.md §4.2.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "attention.cuh"
@@ -46,8 +52,14 @@ struct FwdParams {
 };
 
 // DROP: compile-time, the mask logic is not even compiled into the p = 0 kernel
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float m;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
+  return m;
+}
+
 template <int DH, bool DROP>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
   constexpr int NBOX = (DH + 63) / 64;
   constexpr int OP_BYTES = NBOX * BOX_BYTES;
@@ -99,6 +111,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer + MMA issuer
@@ -161,7 +176,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
         load_tile(sV, bar_v, 2 * d + h * DH, (j + 1) * BKV);
       }
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 4) {
     // ---------------------------------------------------------------- softmax: thread <-> query row
     const int quarter = warp & 3;                        // TMEM lanes this warp may access
     const int row = quarter * 32 + lane;
@@ -183,21 +198,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
       mbar_wait(bar_s, ph);
       tc_fence_after();
 
-      // pass 1: tile max of the raw scores
+      // the whole score row, once
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      tmem_ld_32x32b_x32(lane_addr + COL_S, r0);
+      if (nchunk > 1) tmem_ld_32x32b_x32(lane_addr + COL_S + 32, r1);
+      if (nchunk > 2) tmem_ld_32x32b_x32(lane_addr + COL_S + 64, r2);
+      if (nchunk > 3) tmem_ld_32x32b_x32(lane_addr + COL_S + 96, r3);
+      tmem_ld_wait();
+
       float mx = -INFINITY;
-      for (int c = 0; c < nchunk; c++) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_addr + COL_S + c * 32, r);
-        tmem_ld_wait();
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
+      auto chunk_max = [&](uint32_t (&r)[32], int c) {
+        if (c >= nchunk) return;
+        if (!full) {
           const uint32_t word = vw[c];
 #pragma unroll
-          for (int i = 0; i < 32; i++) mx = fmaxf(mx, ((word >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY);
+          for (int i = 0; i < 32; i++) r[i] = ((word >> i) & 1u) ? r[i] : 0xff800000u;      // -inf
         }
-      }
+        float a = -INFINITY, bq = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          a = fmax3(a, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          bq = fmax3(bq, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
+        mx = fmax3(mx, a, bq);
+      };
+      chunk_max(r0, 0); chunk_max(r1, 1); chunk_max(r2, 2); chunk_max(r3, 3);
+
       const float mt = mx * scale2;                      // -inf if every key of the tile is masked
       const bool raise = mt > m_ref + RESCALE_THRESHOLD; // first finite tile: m_ref = -inf -> true
       if (__any_sync(0xffffffffu, raise)) {
@@ -210,46 +236,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p
         if (j > 0) {                                     // O holds the previous tiles' sum (P̃·V_{j-1} is complete)
 #pragma unroll
           for (int c = 0; c < DH / 32; c++) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(lane_addr + COL_O + c * 32, r);
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(lane_addr + COL_O + c * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
-            tmem_st_32x32b_x32(lane_addr + COL_O + c * 32, r);
+            for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st_32x32b_x32(lane_addr + COL_O + c * 32, o);
           }
           tmem_st_wait();
         }
       }
       const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
 
-      // pass 2: P = exp2(s*scale2 - m), row sum, dropout (keep bits; the 1/(1-p) scale is applied to O at the end), bf16 pack -> TMEM
+      // P = exp2(s*scale2 - m) (exp2(-inf) = 0 for masked keys), row sum, keep-bit select (the 1/(1-p) scale is applied
+      // to O at the end), bf16 pack -> TMEM
       uint4 bw = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
       if (drop) bw = __ldg(brow + j);
-      for (int c = 0; c < nchunk; c++) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_addr + COL_S + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
-        const uint32_t word = vw[c];
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          float e = ex2f(fmaf(__uint_as_float(r[i]), scale2, -m_use));
-          if (!full) e = ((word >> i) & 1u) ? e : 0.f;
-          pv[i] = e;
-          l_run += e;
-        }
+      auto chunk_p = [&](uint32_t (&r)[32], int c, uint32_t dw) {
+        if (c >= nchunk) return;
+        float l0 = 0.f, l1 = 0.f;
         uint32_t pk[16];
-        if (drop) {
-          const uint32_t dw = c == 0 ? bw.x : (c == 1 ? bw.y : (c == 2 ? bw.z : bw.w));
 #pragma unroll
-          for (int i = 0; i < 16; i++)
-            pk[i] = pack_bf16x2(((dw >> (2 * i)) & 1u) ? pv[2 * i] : 0.f, ((dw >> (2 * i + 1)) & 1u) ? pv[2 * i + 1] : 0.f);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; i++) pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+        for (int i = 0; i < 16; i++) {
+          const float e0 = ex2f(fmaf(__uint_as_float(r[2 * i]), scale2, -m_use));
+          const float e1 = ex2f(fmaf(__uint_as_float(r[2 * i + 1]), scale2, -m_use));
+          l0 += e0; l1 += e1;
+          if (drop) pk[i] = pack_bf16x2(((dw >> (2 * i)) & 1u) ? e0 : 0.f, ((dw >> (2 * i + 1)) & 1u) ? e1 : 0.f);
+          else pk[i] = pack_bf16x2(e0, e1);
         }
+        l_run += l0 + l1;
         tmem_st_32x32b_x16(lane_addr + COL_P + c * 16, pk);
-      }
+      };
+      chunk_p(r0, 0, bw.x); chunk_p(r1, 1, bw.y); chunk_p(r2, 2, bw.z); chunk_p(r3, 3, bw.w);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -308,8 +326,8 @@ int fwd_launch(const void* qkv, const uint8_t* key_mask, void* out, float* lse, 
   prm.p_drop = p; prm.dbits = dbits;
   const int64_t q_tiles = ceil_div(T, BQ);
   const unsigned grid = (unsigned)(B * H * q_tiles);
-  if (p > 0.f) attn_fwd_tc_kernel<DH, true><<<grid, 192, SMEM, st>>>(tm, prm);
-  else attn_fwd_tc_kernel<DH, false><<<grid, 192, SMEM, st>>>(tm, prm);
+  if (p > 0.f) attn_fwd_tc_kernel<DH, true><<<grid, 256, SMEM, st>>>(tm, prm);
+  else attn_fwd_tc_kernel<DH, false><<<grid, 256, SMEM, st>>>(tm, prm);
   MAR_LAUNCH_CHECK("attn_fwd_tc");
   return MAR_OK;
 }
@@ -330,6 +348,11 @@ int attention_fwd_tc(const void* qkv, const uint8_t* key_mask, void* out, float*
   MAR_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)dbits % 16 == 0),
                 "attention: pointers must be 16 B aligned");
   MAR_CHECK_ARG(p == 0.f || dbits, "attention: dropout needs the keep-bit buffer");
+  // more than one query tile: the pair kernel (two query tiles per CTA, ping-ponging softmax warp-groups);
+  // MAR_ATTN_FWD1=1 keeps this one-tile kernel for A/B measurements
+  static int fwd1 = -1;
+  if (fwd1 < 0) { const char* e = getenv("MAR_ATTN_FWD1"); fwd1 = (e && e[0] == '1') ? 1 : 0; }
+  if (T > 4 * BKV && !fwd1) return attention_fwd_tc2(qkv, key_mask, out, lse, B, T, H, dh, p, dbits, st);
   switch (dh) {
     case 64: return fwd_launch<64>(qkv, key_mask, out, lse, B, T, H, p, dbits, st);
     case 96: return fwd_launch<96>(qkv, key_mask, out, lse, B, T, H, p, dbits, st);

@@ -21,7 +21,9 @@ template <typename T, typename TO, int VEC>
 __global__ void __launch_bounds__(256)
 bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* __restrict__ dz,
                     float* __restrict__ dbias, int64_t M, int64_t N, int rows_per_block, int flags, float p,
-                    const uint64_t* __restrict__ rng, uint32_t site) {
+                    const uint64_t* __restrict__ rng, uint32_t site, int bcast) {
+  // bcast > 0: dout has M / bcast rows and row r reads dout row r / bcast scaled by 1 / bcast — the backward of a mean
+  // over `bcast` consecutive rows (SequenceAverageFeatures after an adaptor, models.py:693-699) without materialising it
   const int lane = threadIdx.x, ry = threadIdx.y;
   const int64_t c0 = ((int64_t)blockIdx.x * 32 + lane) * VEC;
   const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
@@ -30,7 +32,7 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
   const bool drop = (flags & MAR_EPI_DROPOUT) && p > 0.f;
   DropKey dk;
   if (drop) dk = make_drop_key(rng, site, p);
-  const float scale = drop ? dk.scale : 1.f;
+  const float scale = (drop ? dk.scale : 1.f) * (bcast > 0 ? 1.f / (float)bcast : 1.f);
   const bool idx32 = ((uint64_t)M * (uint64_t)N >> 1) < 0xffffffffull;     // every pair index fits 32 bits
   float csum[VEC];
 #pragma unroll
@@ -47,7 +49,8 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
         for (int u = 0; u < U; u++) {
           const int64_t rr = r + 8 * u;
           if (rr < r_end) {
-            gq[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(dout) + (rr * N + c0) * sizeof(T));
+            const int64_t rs = bcast > 0 ? rr / bcast : rr;
+            gq[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(dout) + (rs * N + c0) * sizeof(T));
             if (relu) oq[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(out) + (rr * N + c0) * sizeof(TO));
           }
         }
@@ -62,7 +65,7 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
 #pragma unroll
             for (int j = 0; j < 4; j++) { const float2 f2 = __bfloat1622float2(h2[j]); g[2 * j] = f2.x; g[2 * j + 1] = f2.y; }
           } else {
-            Vec8<T>::load(dout + e0, g);
+            Vec8<T>::load(dout + (bcast > 0 ? (rr / bcast) * N + c0 : e0), g);
           }
           if (relu) {
             if (sizeof(TO) == 2) {
@@ -83,6 +86,9 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
               g[2 * j] = k0 ? g[2 * j] * scale : 0.f;
               g[2 * j + 1] = k1 ? g[2 * j + 1] * scale : 0.f;
             }
+          } else if (bcast > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) g[j] *= scale;
           }
 #pragma unroll
           for (int j = 0; j < 8; j++) csum[j % VEC] += g[j];
@@ -96,7 +102,7 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
 #pragma unroll
         for (int j = 0; j < VEC; j++) {
           bool ok = c0 + j < N;
-          g[j] = ok ? to_f32<T>(dout[e0 + j]) : 0.f;
+          g[j] = ok ? to_f32<T>(dout[(bcast > 0 ? (r / bcast) * N + c0 : e0) + j]) : 0.f;
           o[j] = (ok && relu) ? to_f32<TO>(out[e0 + j]) : 0.f;
         }
 #pragma unroll
@@ -104,7 +110,7 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
           float f;
           if (relu) f = o[j] > 0.f ? scale : 0.f;
           else if (drop) f = drop_keep(dk, (uint64_t)(e0 + j)) ? scale : 0.f;
-          else f = 1.f;
+          else f = scale;
           g[j] *= f;
           csum[j] += g[j];
         }
@@ -132,7 +138,7 @@ bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* _
 
 template <typename T, typename TO>
 int launch_bwd_epilogue(const void* dout, const void* out, void* dz, float* dbias, int64_t M, int64_t N, int flags,
-                        float p, const uint64_t* rng, uint32_t site, cudaStream_t st) {
+                        float p, const uint64_t* rng, uint32_t site, int bcast, cudaStream_t st) {
   const bool vec = (N % 8 == 0);
   const int VECW = vec ? 8 : 1;
   int64_t gx = ceil_div(N, 32 * VECW);
@@ -144,10 +150,10 @@ int launch_bwd_epilogue(const void* dout, const void* out, void* dz, float* dbia
   dim3 grid((unsigned)gx, (unsigned)gy), block(32, 8);
   if (vec)
     bwd_epilogue_kernel<T, TO, 8><<<grid, block, 0, st>>>((const T*)dout, (const TO*)out, (T*)dz, dbias, M, N,
-                                                          (int)rows_per_block, flags, p, rng, site);
+                                                          (int)rows_per_block, flags, p, rng, site, bcast);
   else
     bwd_epilogue_kernel<T, TO, 1><<<grid, block, 0, st>>>((const T*)dout, (const TO*)out, (T*)dz, dbias, M, N,
-                                                          (int)rows_per_block, flags, p, rng, site);
+                                                          (int)rows_per_block, flags, p, rng, site, bcast);
   MAR_LAUNCH_CHECK("bwd_epilogue");
   return MAR_OK;
 }
@@ -504,22 +510,25 @@ int mar_rng_advance(uint64_t* rng_state, void* stream) {
 
 int mar_linear_bwd_epilogue(const void* dout, const void* out, void* dz, float* dbias, int64_t M, int64_t N,
                             int dtype, int out_dtype, int flags, float p_drop, const uint64_t* rng_state,
-                            uint32_t site, void* stream) {
+                            uint32_t site, int64_t pooled_rows, void* stream) {
   MAR_CHECK_ARG(dout && M >= 0 && N > 0, "mar_linear_bwd_epilogue: bad arguments");
   if (M == 0) return MAR_OK;
   const bool relu = flags & (MAR_EPI_RELU_PRE | MAR_EPI_RELU_POST);
   MAR_CHECK_ARG(!relu || out, "mar_linear_bwd_epilogue: ReLU backward needs the forward output");
   MAR_CHECK_ARG(!((flags & MAR_EPI_DROPOUT) && p_drop > 0.f) || rng_state, "mar_linear_bwd_epilogue: dropout needs rng_state");
   MAR_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "mar_linear_bwd_epilogue: p_drop out of range");
+  MAR_CHECK_ARG(pooled_rows >= 0 && pooled_rows < (1ll << 31) && (pooled_rows == 0 || (M % pooled_rows == 0 && dz)),
+                "mar_linear_bwd_epilogue: pooled_rows must divide M (and dz must be given)");
+  const int bcast = (int)pooled_rows;
   cudaStream_t st = S(stream);
   if (dtype == MAR_F32 && out_dtype == MAR_F32)
-    return launch_bwd_epilogue<float, float>(dout, out, dz, dbias, M, N, flags, p_drop, rng_state, site, st);
+    return launch_bwd_epilogue<float, float>(dout, out, dz, dbias, M, N, flags, p_drop, rng_state, site, bcast, st);
   if (dtype == MAR_BF16 && out_dtype == MAR_BF16)
-    return launch_bwd_epilogue<bf16, bf16>(dout, out, dz, dbias, M, N, flags, p_drop, rng_state, site, st);
+    return launch_bwd_epilogue<bf16, bf16>(dout, out, dz, dbias, M, N, flags, p_drop, rng_state, site, bcast, st);
   if (dtype == MAR_F32 && out_dtype == MAR_BF16)
-    return launch_bwd_epilogue<float, bf16>(dout, out, dz, dbias, M, N, flags, p_drop, rng_state, site, st);
+    return launch_bwd_epilogue<float, bf16>(dout, out, dz, dbias, M, N, flags, p_drop, rng_state, site, bcast, st);
   if (dtype == MAR_BF16 && out_dtype == MAR_F32)
-    return launch_bwd_epilogue<bf16, float>(dout, out, dz, dbias, M, N, flags, p_drop, rng_state, site, st);
+    return launch_bwd_epilogue<bf16, float>(dout, out, dz, dbias, M, N, flags, p_drop, rng_state, site, bcast, st);
   MAR_UNSUPPORTED("mar_linear_bwd_epilogue: dtype %d/%d", dtype, out_dtype);
 }
 

@@ -101,10 +101,13 @@ def encoder_layer_forward(layer: nn.TransformerEncoderLayer, h: torch.Tensor, B:
     pre1 = ops.linear(o.view(B * T, d), sa.out_proj.weight, sa.out_proj.bias, residual=h_res,
                       dropout_p=layer.dropout1.p if train else 0.0)
     x1 = ops.layer_norm(pre1, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
-    hid, x1_res = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu_pre=True,
-                             dropout_p=layer.dropout.p if train else 0.0, fork=True)
+    # linear1's ReLU+dropout backward is applied inside linear2's dgrad GEMM (hid is zero exactly where that derivative
+    # is zero): the (B*T, d_ff) gradient is written once, already masked, and linear1 only sums its bias gradient
+    p_ff = float(layer.dropout.p) if train else 0.0
+    hid, x1_res = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu_pre=True, dropout_p=p_ff, fork=True,
+                             defer_act=True)
     pre2 = ops.linear(hid, layer.linear2.weight, layer.linear2.bias, residual=x1_res,
-                      dropout_p=layer.dropout2.p if train else 0.0)
+                      dropout_p=layer.dropout2.p if train else 0.0, x_act_scale=1.0 / (1.0 - p_ff))
     return ops.layer_norm(pre2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
 
 
@@ -566,8 +569,10 @@ class PhysVerbClassifier(nn.Module):
         lin = seq[0]
         if ops.probing():
             return features.new_zeros(features.shape[0], lin.out_features)
-        a = ops.linear(features, lin.weight, lin.bias, dropout_p=seq[1].p if self.training else 0.0, relu_post=True)
-        return ops.mean_pool(a)
+        # Linear → Dropout → ReLU → mean over T as ONE autograd node: backward broadcasts the pooled gradient inside the
+        # epilogue kernel instead of materialising a (B, T, d) tensor for it
+        return ops.linear(features, lin.weight, lin.bias, dropout_p=seq[1].p if self.training else 0.0, relu_post=True,
+                          pool_T=features.shape[1])
 
     def _head(self, aggr_type, x):
         seq = self.classifiers_dict[aggr_type]

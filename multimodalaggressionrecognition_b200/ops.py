@@ -271,10 +271,11 @@ def grad_sink(notify=None):
 
 
 import os as _os
-# Which gradients are sunk: weights, biases (and "ln" = LayerNorm gains/offsets).  With ALL parameters sunk no
-# AccumulateGrad node runs at all and CUDA-graph capture of the step fails with cudaErrorStreamCaptureIsolation
-# (measured on torch 2.11), so the 18 small LayerNorm vectors keep going through autograd by default.
-_SINK_KINDS = set(_os.environ.get("MAR_SINK", "w,b").split(","))
+# Which gradients are sunk: weights, biases and "ln" = LayerNorm gains/offsets (MAR_SINK overrides, for A/B runs).  In
+# round 1 sinking ALL parameters broke CUDA-graph capture of the step (cudaErrorStreamCaptureIsolation, torch 2.11: no
+# AccumulateGrad node ran at all); since the step driver registers a post-accumulate hook on every parameter, created
+# on the capture stream, the nodes exist and capture works (measured on B200, round 2: 9.16 -> 9.05 ms per step).
+_SINK_KINDS = set(_os.environ.get("MAR_SINK", "w,b,ln").split(","))
 
 
 def _sink_target(param, kind: str = "w") -> Optional[torch.Tensor]:
@@ -296,11 +297,16 @@ def _sunk(param) -> None:
 # --------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, flags, p, out_dtype, need_dx, fork=False):
+    def forward(ctx, x, weight, bias, residual, flags, p, out_dtype, need_dx, fork=False, x_act_scale=None,
+                defer_act=False, pool_T=0):
         # x (M,K) compute dtype; weight (N,K) fp32 master; bias (N) fp32; residual (M,N) compute dtype
         # fork: also return x itself as a second output.  A consumer that uses x twice (the projection and the
         # residual branch of an encoder sub-layer) takes the residual from that output, so its gradient arrives
         # HERE and is added inside the dgrad GEMM's epilogue (dx = dz·W + d_fork) instead of in a separate pass.
+        # x_act_scale: x came out of a ReLU(+dropout) epilogue whose backward this op applies inside its dgrad GEMM
+        #   (dx = dz·W where x > 0, times x_act_scale, else 0) — the producer was called with defer_act=True and only
+        #   sums its bias gradient.  pool_T: the epilogue's output is mean-pooled over groups of pool_T rows and the
+        #   POOLED tensor is returned; backward broadcasts the pooled gradient inside the epilogue kernel.
         M, K = x.shape
         N = weight.shape[0]
         cd = x.dtype
@@ -327,10 +333,17 @@ class _Linear(torch.autograd.Function):
         ctx.wc, ctx.wt = wc, wt
         ctx.w_shape = tuple(weight.shape)
         ctx.eng = _eng()
-        need_out = bool(flags & (EPI_RELU_PRE | EPI_RELU_POST))
+        ctx.x_act_scale = x_act_scale
+        ctx.defer_act = bool(defer_act)
+        ctx.pool_T = int(pool_T)
+        need_out = bool(flags & (EPI_RELU_PRE | EPI_RELU_POST)) and not defer_act
         ctx.save_for_backward(x, out if need_out else None)
         ctx.fork = bool(fork)
         ctx.weight_ref, ctx.bias_ref = weight, bias
+        if pool_T:
+            pooled = torch.empty((M // pool_T, N), dtype=out_dtype, device=x.device)
+            call("mar_meanpool_fwd", out.data_ptr(), pooled.data_ptr(), M // pool_T, pool_T, N, _dt(out), _stream())
+            return pooled
         if fork:
             return out, x.view_as(x)
         return out
@@ -350,15 +363,16 @@ class _Linear(torch.autograd.Function):
         if ctx.has_bias and needs_b:
             sunk_b = _sink_target(ctx.bias_ref, "b")
             dbias = sunk_b if sunk_b is not None else torch.zeros(N, dtype=torch.float32, device=x.device)
-        if ctx.flags != 0:
-            dz = torch.empty_like(dout)
+        flags = 0 if ctx.defer_act else ctx.flags        # deferred: the consumer's dgrad GEMM already applied this mask
+        if flags != 0 or ctx.pool_T:
+            dz = torch.empty((M, N), dtype=cd, device=x.device)
             call("mar_linear_bwd_epilogue", dout.data_ptr(), _p(out), dz.data_ptr(), _p(dbias), M, N, _dt(dout),
-                 _dt(out) if out is not None else _dt(dout), ctx.flags, ctx.p, _p(ctx.rng), ctx.site, st)
+                 _dt(out) if out is not None else _dt(dout), flags, ctx.p, _p(ctx.rng), ctx.site, ctx.pool_T, st)
         else:
             dz = dout
             if dbias is not None:
                 call("mar_linear_bwd_epilogue", dout.data_ptr(), None, None, dbias.data_ptr(), M, N, _dt(dout),
-                     _dt(dout), 0, 0.0, None, 0, st)
+                     _dt(dout), 0, 0.0, None, 0, 0, st)
         dx = dw = None
         add = None
         if ctx.fork and dfork is not None:
@@ -366,8 +380,11 @@ class _Linear(torch.autograd.Function):
             add = add.contiguous()
         if needs_x:
             dx = torch.empty((M, K), dtype=cd, device=x.device)
-            call("mar_linear_dgrad", dz.data_ptr(), ctx.wc.data_ptr(), _p(ctx.wt), _p(add), dx.data_ptr(), K, M, N, K,
-                 _dt(dz), ctx.eng, st)
+            act = x if ctx.x_act_scale is not None else None
+            if act is not None and add is not None:
+                raise RuntimeError("linear: x_act_scale cannot be combined with fork (one staged epilogue input per GEMM)")
+            call("mar_linear_dgrad", dz.data_ptr(), ctx.wc.data_ptr(), _p(ctx.wt), _p(add), _p(act),
+                 float(ctx.x_act_scale or 1.0), dx.data_ptr(), K, M, N, K, _dt(dz), ctx.eng, st)
         if needs_w:
             sunk_w = _sink_target(ctx.weight_ref)
             if sunk_w is not None and tuple(sunk_w.shape) == ctx.w_shape:
@@ -382,15 +399,20 @@ class _Linear(torch.autograd.Function):
             dbias = None
             _sunk(ctx.bias_ref)
         dres = dout if (ctx.has_res and needs_r) else None
-        return dx, dw, dbias, dres, None, None, None, None, None
+        return dx, dw, dbias, dres, None, None, None, None, None, None, None, None
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, relu_pre: bool = False, dropout_p: float = 0.0,
-           relu_post: bool = False, out_dtype: Optional[torch.dtype] = None, fork: bool = False):
+           relu_post: bool = False, out_dtype: Optional[torch.dtype] = None, fork: bool = False,
+           x_act_scale: Optional[float] = None, defer_act: bool = False, pool_T: int = 0):
     """out = residual + relu_post(dropout(relu_pre(x·Wᵀ + b))) on the last dim of x.
     fork=True returns (out, x_fork): use x_fork wherever x is needed again (a residual branch) and its gradient is
-    folded into this linear's dgrad GEMM instead of a separate elementwise add."""
+    folded into this linear's dgrad GEMM instead of a separate elementwise add.
+    defer_act / x_act_scale (a pair): a ReLU(+dropout) producer called with defer_act=True leaves its activation
+    backward to its ONLY consumer, a linear called with x_act_scale = the producer's dropout scale 1/(1-p) (1.0
+    without dropout): the consumer's dgrad GEMM writes the gradient already masked (zero where x is zero).
+    pool_T > 0 (x must be (B, pool_T, K)): returns mean over the pool_T rows of every group, (B, N)."""
     shape = x.shape
     x2 = _rows(to_compute(x))
     r2 = None
@@ -398,10 +420,21 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         r2 = _rows(to_compute(residual, x2.dtype))
     flags = (EPI_RELU_PRE if relu_pre else 0) | (EPI_DROPOUT if dropout_p > 0 else 0) | (EPI_RELU_POST if relu_post else 0)
     need_dx = torch.is_grad_enabled() and x2.requires_grad
+    if defer_act and not (relu_pre or relu_post):
+        raise ValueError("defer_act needs a ReLU in the epilogue: the consumer reads the mask off the output's zeros")
+    if residual is not None and (relu_pre or relu_post):
+        raise ValueError("residual cannot be combined with a ReLU epilogue (the saved output would not carry the ReLU mask)")
+    if pool_T:
+        if fork or residual is not None or x.dim() != 3 or x.shape[1] != pool_T:
+            raise ValueError("pool_T needs x of shape (B, pool_T, K), no fork and no residual")
+        return _Linear.apply(x2, weight, bias, None, flags, float(dropout_p), out_dtype or x2.dtype, need_dx, False,
+                             x_act_scale, defer_act, int(pool_T))
     if fork and need_dx:
-        out, xf = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype, need_dx, True)
+        out, xf = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype, need_dx, True,
+                                x_act_scale, defer_act, 0)
         return out.view(*shape[:-1], weight.shape[0]), xf.view(shape)
-    out = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype, need_dx)
+    out = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype, need_dx, False,
+                        x_act_scale, defer_act, 0)
     out = out.view(*shape[:-1], weight.shape[0])
     return (out, x2.view(shape)) if fork else out
 
@@ -745,7 +778,7 @@ class _GRU(torch.autograd.Function):
              ctx.eng, st)
         db = torch.zeros(3 * H, dtype=torch.float32, device=hseq.device)
         call("mar_linear_bwd_epilogue", dgh.data_ptr(), None, None, db.data_ptr(), B * T, 3 * H, _dt(dgh), _dt(dgh), 0,
-             0.0, None, 0, st)
+             0.0, None, 0, 0, st)
         return dgi, dw, db, None
 
 
@@ -794,7 +827,7 @@ class _LSTM(torch.autograd.Function):
              ctx.eng, st)
         db = torch.zeros(4 * H, dtype=torch.float32, device=saved.device)
         call("mar_linear_bwd_epilogue", dg.data_ptr(), None, None, db.data_ptr(), B * T, 4 * H, _dt(dg), _dt(dg), 0,
-             0.0, None, 0, st)
+             0.0, None, 0, 0, st)
         return dg, dw, db, None
 
 

@@ -135,6 +135,59 @@ def test_linear_dropout_backward_uses_same_mask(mode):
         assert_close(gx.float(), expect, FP32_TOL if mode == "fp32" else BF16_TOL, f"dropout bwd {kw}")
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("p", [0.0, 0.3])
+def test_ffn_deferred_activation_backward_matches_the_unfused_path(mode, p):
+    """linear1 (ReLU + dropout) → linear2 with linear1's activation backward applied inside linear2's dgrad GEMM
+    (defer_act / x_act_scale) against the same two linears with the separate epilogue-backward pass: same dropout
+    mask (same seed and sites), same forward, same gradients."""
+    Mr, d, ff = 300, 256, 512
+    x = torch.randn(Mr, d, device=DEV)
+    w1, b1 = torch.randn(ff, d, device=DEV) / d ** 0.5, torch.randn(ff, device=DEV) * 0.1
+    w2, b2 = torch.randn(d, ff, device=DEV) / ff ** 0.5, torch.randn(d, device=DEV) * 0.1
+    go = torch.randn(Mr, d, device=DEV)
+    res = {}
+    for fused in (False, True):
+        mar.manual_seed(99)
+        leaves = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+        xx, a1, c1, a2, c2 = leaves
+        with mar.precision(mode):
+            hid, xr = ops.linear(xx, a1, c1, relu_pre=True, dropout_p=p, fork=True, defer_act=fused)
+            y = ops.linear(hid, a2, c2, residual=xr, x_act_scale=(1.0 / (1.0 - p)) if fused else None)
+            y.backward(go.to(y.dtype))
+        res[fused] = [y.detach().float()] + [t.grad.float() for t in leaves]
+    tol = 1e-5 if mode == "fp32" else 2e-2
+    for name, a, b in zip(("y", "dx", "dW1", "db1", "dW2", "db2"), res[True], res[False]):
+        assert_close(a, b, tol, f"deferred activation backward: {name}")
+    assert float(res[True][1].abs().max()) > 0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("p", [0.0, 0.3])
+def test_adaptor_with_fused_mean_pool_matches_linear_then_mean_pool(mode, p):
+    """Linear → Dropout → ReLU → mean over T as one node (pool_T) against linear followed by ops.mean_pool."""
+    B, T, d, n = 5, 37, 256, 192
+    x = torch.randn(B, T, d, device=DEV)
+    w, b = torch.randn(n, d, device=DEV) / d ** 0.5, torch.randn(n, device=DEV) * 0.1
+    go = torch.randn(B, n, device=DEV)
+    res = {}
+    for fused in (False, True):
+        mar.manual_seed(7)
+        xx, ww, bb = [t.clone().requires_grad_(True) for t in (x, w, b)]
+        with mar.precision(mode):
+            if fused:
+                y = ops.linear(xx, ww, bb, dropout_p=p, relu_post=True, pool_T=T)
+            else:
+                y = ops.mean_pool(ops.linear(xx, ww, bb, dropout_p=p, relu_post=True))
+            y.backward(go.to(y.dtype))
+        res[fused] = [y.detach().float(), xx.grad.float(), ww.grad.float(), bb.grad.float()]
+    tol = 1e-5 if mode == "fp32" else 2e-2
+    for name, a, b_ in zip(("pooled", "dx", "dW", "db"), res[True], res[False]):
+        assert_close(a, b_, tol, f"fused mean-pool adaptor: {name}")
+    with pytest.raises(ValueError):
+        ops.linear(x, w, b, relu_post=True, pool_T=T + 1)
+
+
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------
