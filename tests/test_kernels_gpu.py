@@ -232,6 +232,32 @@ def test_attention_fwd_bwd(B, T, H, dh, mode, masked):
     assert_close(qg.grad.float().cpu(), qr.grad, tol, "attention dqkv")
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("B,T", [(48, 314), (80, 250), (12, 700), (40, 129), (6, 1100)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_attention_forward_kernels_over_many_ctas(B, T, p, monkeypatch):
+    """Both tcgen05 forward kernels (one query tile per CTA up to T = 512, the pair kernel beyond: T = 700 has an odd
+    number of query tiles, so every third CTA runs without its second warp-group) on grids of several waves, with a
+    key-padding mask per batch element and dropout, against the mma.sync engine on the same keep bits."""
+    H, dh = 8, 96
+    d = H * dh
+    qkv = torch.randn(B, T, 3 * d, device=DEV).to(torch.bfloat16)
+    mask = torch.rand(B, T, device=DEV) < 0.15
+    mask[:, 0] = False
+    mask[1] = False
+    outs = {}
+    for eng in ("tc", "mma"):
+        monkeypatch.setenv("MAR_ATTN_MMA", "1" if eng == "mma" else "0")
+        mar.manual_seed(77)
+        with mar.precision("bf16"), torch.no_grad():
+            outs[eng] = ops.attention(qkv, mask, H, p).float()
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs["tc"]).all()
+    assert_close(outs["tc"], outs["mma"], 1e-2, "tcgen05 forward vs mma.sync engine")
+    worst = float((outs["tc"] - outs["mma"]).abs().amax(dim=(1, 2)).max())      # no single item may be off (a stale tile)
+    assert worst < 0.1, worst
+
+
 @pytest.mark.parametrize("T,H", [(1024, 2), (4096, 1)])
 @pytest.mark.parametrize("masked", [False, True])
 def test_attention_long_sequences_against_oracle(T, H, masked):
