@@ -152,6 +152,24 @@ int mar_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
                       const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t rows,
                       int64_t D, int dtype, void* stream);
 
+/* The same two kernels with a ROW MAP on the output (forward: y) / incoming-gradient (backward: dy) side, so that
+ * torch.cat along T (models.py:419) and the per-modality slices (models.py:430) cost no copy.  Rows are (b, t) =
+ * (row / Tin, row % Tin); segment k covers t in [t0[k], t1[k]) — the segments tile [0, Tin) in order, 1..4 of them —
+ * and places the row at  ptrs[k] + ((b * Tout[k]) + tout0[k] + (t - t0[k])) * D  (16 B aligned bases):
+ *  - an extractor's final LayerNorm writes straight into its slice of the fused (B, T_a+T_v, d) sequence:
+ *    one segment, Tout = T_a+T_v, tout0 = the modality's offset;
+ *  - the fusion encoder's final LayerNorm writes one contiguous (B, T_k, d) tensor per modality: Tin = T_a+T_v,
+ *    one segment per modality with Tout = T_k, tout0 = 0.
+ * nseg = 0 is the plain call (y / dy used).  Pointer and index arrays are HOST arrays read during the call. */
+int mar_layernorm_fwd_mapped(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                             const uint8_t* zero_rows, int64_t rows, int64_t D, float eps, int dtype, int nseg, int64_t Tin,
+                             const int64_t* t0, const int64_t* t1, const int64_t* Tout, const int64_t* tout0,
+                             void* const* y_ptrs, void* stream);
+int mar_layernorm_bwd_mapped(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                             void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t D, int dtype, int nseg, int64_t Tin,
+                             const int64_t* t0, const int64_t* t1, const int64_t* Tout, const int64_t* tout0,
+                             void* const* dy_ptrs, void* stream);
+
 /* ---- Pooling / masks ------------------------------------------------------------------------ */
 /* out (B,D) = mean over T of x (B,T,D) (SequenceAverageFeatures, models.py:105; :97). */
 int mar_meanpool_fwd(const void* x, void* out, int64_t B, int64_t T, int64_t D, int dtype, void* stream);

@@ -42,6 +42,8 @@ PROTOTYPES = {
     "mar_attention_bwd_work_floats": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
     "mar_layernorm_fwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_float, c_int, P]),
     "mar_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, P]),
+    "mar_layernorm_fwd_mapped": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_float, c_int, c_int, c_int64, P, P, P, P, P, P]),
+    "mar_layernorm_bwd_mapped": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_int64, P, P, P, P, P, P]),
     "mar_meanpool_fwd": (c_int, [P, P, c_int64, c_int64, c_int64, c_int, P]),
     "mar_meanpool_bwd": (c_int, [P, P, c_int64, c_int64, c_int64, c_int, P]),
     "mar_rowzero_mask": (c_int, [P, P, c_int64, c_int64, c_int, P]),

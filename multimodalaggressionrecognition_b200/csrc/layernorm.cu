@@ -8,11 +8,35 @@ namespace {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Where a row of the (rows, D) problem lives on the "mapped" side (the forward's y, the backward's dy): rows are
+// (b, t) = (row / Tin, row % Tin); segment k covers t in [t0, t1) and places the row at
+//   ptr[k] + ((b * Tout[k]) + tout0[k] + (t - t0[k])) * D.
+// nseg = 0: the plain contiguous (rows, D) layout.  This is how an encoder's final LayerNorm writes straight into its
+// slice of the fused (B, T_a+T_v, d) sequence (one segment, Tout = T_a+T_v) and how the fusion encoder's final LayerNorm
+// writes one contiguous tensor per modality (one segment each) — torch.cat / the per-modality slices of
+// models.py:419,430 without a copy; the backward reads its incoming gradient through the same map.
+struct RowMap {
+  int nseg, Tin;
+  int t0[4], t1[4], Tout[4], tout0[4];
+  void* ptr[4];
+};
+
+template <typename T>
+__device__ __forceinline__ T* mapped_row(const RowMap& m, T* plain, int64_t row, int D) {
+  if (m.nseg == 0) return plain + row * D;
+  const int64_t b = row / m.Tin;
+  const int t = (int)(row - b * m.Tin);
+  int k = 0;
+#pragma unroll
+  for (int i = 1; i < 4; i++) if (i < m.nseg && t >= m.t0[i]) k = i;
+  return reinterpret_cast<T*>(m.ptr[k]) + (b * m.Tout[k] + m.tout0[k] + (t - m.t0[k])) * (int64_t)D;
+}
+
 template <typename T, int NCH>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd,
-                     const uint8_t* __restrict__ zero_rows, int64_t rows, int D, float eps) {
+                     const uint8_t* __restrict__ zero_rows, int64_t rows, int D, float eps, const RowMap map) {
   const int lane = threadIdx.x % 32;
   const int warps_per_block = blockDim.x / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + threadIdx.x / 32;
@@ -46,6 +70,7 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, c
     }
     const float rs = rsqrtf(warp_sum(q) * invD + eps);
     if (lane == 0 && mean != nullptr) { mean[row] = mu; rstd[row] = rs; }
+    T* yrow = mapped_row<T>(map, y, row, D);
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
       int col = (c * 32 + lane) * 8;
@@ -55,7 +80,7 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, c
         Vec8<float>::load(beta + col, b);
 #pragma unroll
         for (int j = 0; j < 8; j++) o[j] = (v[c][j] - mu) * rs * g[j] + b[j];
-        Vec8<T>::store(y + row * D + col, o);
+        Vec8<T>::store(yrow + col, o);
       }
     }
   }
@@ -89,7 +114,7 @@ template <typename T, int NCH>
 __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int D) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int D, const RowMap map) {
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
   const int warps_per_block = blockDim.x / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + warp;
@@ -105,10 +130,11 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 
   for (int64_t row = warp_global; row < rows; row += warp_stride) {
     Raw8<T> ra[NCH], rb[NCH];
+    const T* dyrow = mapped_row<const T>(map, dy, row, D);
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
       const int col = (c * 32 + lane) * 8;
-      if (col < D) { ra[c].load(dy + row * D + col); rb[c].load(x + row * D + col); }
+      if (col < D) { ra[c].load(dyrow + col); rb[c].load(x + row * D + col); }
     }
     const float mu = mean[row], rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
@@ -172,14 +198,14 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 
 template <typename T>
 int launch_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-               const uint8_t* zero_rows, int64_t rows, int64_t D, float eps, cudaStream_t st) {
+               const uint8_t* zero_rows, int64_t rows, int64_t D, float eps, const RowMap& map, cudaStream_t st) {
   const int nch = (int)ceil_div(D, 256);
   int64_t blocks = ceil_div(rows, 8);
   int64_t cap = (int64_t)mar_sm_count() * 8;
   if (blocks > cap) blocks = cap;
 #define LN_FWD(N)                                                                                             \
   layernorm_fwd_kernel<T, N><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd,   \
-                                                               zero_rows, rows, (int)D, eps)
+                                                               zero_rows, rows, (int)D, eps, map)
   switch (nch) {
     case 1: LN_FWD(1); break;
     case 2: LN_FWD(2); break;
@@ -198,7 +224,7 @@ int launch_fwd(const void* x, const float* gamma, const float* beta, void* y, fl
 
 template <typename T>
 int launch_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
-               float* dgamma, float* dbeta, int64_t rows, int64_t D, cudaStream_t st) {
+               float* dgamma, float* dbeta, int64_t rows, int64_t D, const RowMap& map, cudaStream_t st) {
   const int nch = (int)ceil_div(D, 256);
   int64_t blocks = ceil_div(rows, 8 * 4);
   int64_t cap = (int64_t)mar_sm_count() * 2;    // one resident wave (2 blocks/SM): the column partials end in one atomic per block
@@ -213,7 +239,7 @@ int launch_bwd(const void* dy, const void* x, const float* mean, const float* rs
       cfg = true;                                                                                                 \
     }                                                                                                             \
     layernorm_bwd_kernel<T, N><<<(unsigned)blocks, 256, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, \
-                                                                    (T*)dx, dgamma, dbeta, rows, (int)D);         \
+                                                                    (T*)dx, dgamma, dbeta, rows, (int)D, map);    \
   } while (0)
   switch (nch) {
     case 1: LN_BWD(1); break;
@@ -233,27 +259,74 @@ int launch_bwd(const void* dy, const void* x, const float* mean, const float* rs
 
 }  // namespace
 
+namespace {
+int make_row_map(RowMap* m, int64_t rows, int nseg, int64_t Tin, const int64_t* t0, const int64_t* t1, const int64_t* Tout,
+                 const int64_t* tout0, void* const* ptrs, const char* who) {
+  m->nseg = 0; m->Tin = 1;
+  if (nseg == 0) return MAR_OK;
+  if (nseg < 0 || nseg > 4 || Tin <= 0 || Tin >= (1ll << 31) || rows % Tin != 0 || !t0 || !t1 || !Tout || !tout0 || !ptrs) {
+    mar_set_error("%s: bad row map (1..4 segments, rows a multiple of Tin)", who);
+    return MAR_ERR_INVALID;
+  }
+  int64_t expect = 0;
+  for (int k = 0; k < nseg; k++) {
+    if (t0[k] != expect || t1[k] <= t0[k] || !ptrs[k] || ((uintptr_t)ptrs[k] % 16) != 0 || Tout[k] < tout0[k] + (t1[k] - t0[k]) ||
+        Tout[k] >= (1ll << 31)) {
+      mar_set_error("%s: row-map segment %d is not contiguous with its predecessor, empty, unaligned or does not fit its target", who, k);
+      return MAR_ERR_INVALID;
+    }
+    m->t0[k] = (int)t0[k]; m->t1[k] = (int)t1[k]; m->Tout[k] = (int)Tout[k]; m->tout0[k] = (int)tout0[k]; m->ptr[k] = ptrs[k];
+    expect = t1[k];
+  }
+  if (expect != Tin) { mar_set_error("%s: row-map segments must cover [0, Tin)", who); return MAR_ERR_INVALID; }
+  m->nseg = nseg; m->Tin = (int)Tin;
+  return MAR_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int mar_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                       const uint8_t* zero_rows, int64_t rows, int64_t D, float eps, int dtype, void* stream) {
-  MAR_CHECK_ARG(x && gamma && beta && y && rows >= 0 && D > 0, "mar_layernorm_fwd: bad arguments");
+  return mar_layernorm_fwd_mapped(x, gamma, beta, y, mean, rstd, zero_rows, rows, D, eps, dtype, 0, 0, nullptr, nullptr,
+                                  nullptr, nullptr, nullptr, stream);
+}
+
+int mar_layernorm_fwd_mapped(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                             const uint8_t* zero_rows, int64_t rows, int64_t D, float eps, int dtype, int nseg, int64_t Tin,
+                             const int64_t* t0, const int64_t* t1, const int64_t* Tout, const int64_t* tout0,
+                             void* const* y_ptrs, void* stream) {
+  MAR_CHECK_ARG(x && gamma && beta && (y || nseg > 0) && rows >= 0 && D > 0, "mar_layernorm_fwd: bad arguments");
   MAR_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "mar_layernorm_fwd: mean and rstd go together");
   MAR_CHECK_ARG(D % 8 == 0, "mar_layernorm_fwd: D must be a multiple of 8 (got %lld)", (long long)D);
   if (rows == 0) return MAR_OK;
-  if (dtype == MAR_BF16) return launch_fwd<bf16>(x, gamma, beta, y, mean, rstd, zero_rows, rows, D, eps, S(stream));
-  if (dtype == MAR_F32) return launch_fwd<float>(x, gamma, beta, y, mean, rstd, zero_rows, rows, D, eps, S(stream));
+  RowMap map;
+  int rc = make_row_map(&map, rows, nseg, Tin, t0, t1, Tout, tout0, y_ptrs, "mar_layernorm_fwd_mapped");
+  if (rc) return rc;
+  if (dtype == MAR_BF16) return launch_fwd<bf16>(x, gamma, beta, y, mean, rstd, zero_rows, rows, D, eps, map, S(stream));
+  if (dtype == MAR_F32) return launch_fwd<float>(x, gamma, beta, y, mean, rstd, zero_rows, rows, D, eps, map, S(stream));
   MAR_UNSUPPORTED("mar_layernorm_fwd: dtype %d", dtype);
 }
 
 int mar_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                       void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t D, int dtype, void* stream) {
-  MAR_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && rows >= 0 && D > 0,
+  return mar_layernorm_bwd_mapped(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, dtype, 0, 0, nullptr, nullptr, nullptr,
+                                  nullptr, nullptr, stream);
+}
+
+int mar_layernorm_bwd_mapped(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                             void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t D, int dtype, int nseg, int64_t Tin,
+                             const int64_t* t0, const int64_t* t1, const int64_t* Tout, const int64_t* tout0,
+                             void* const* dy_ptrs, void* stream) {
+  MAR_CHECK_ARG((dy || nseg > 0) && x && mean && rstd && gamma && dx && dgamma && dbeta && rows >= 0 && D > 0,
                 "mar_layernorm_bwd: bad arguments");
   MAR_CHECK_ARG(D % 8 == 0, "mar_layernorm_bwd: D must be a multiple of 8 (got %lld)", (long long)D);
   if (rows == 0) return MAR_OK;
-  if (dtype == MAR_BF16) return launch_bwd<bf16>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, S(stream));
-  if (dtype == MAR_F32) return launch_bwd<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, S(stream));
+  RowMap map;
+  int rc = make_row_map(&map, rows, nseg, Tin, t0, t1, Tout, tout0, dy_ptrs, "mar_layernorm_bwd_mapped");
+  if (rc) return rc;
+  if (dtype == MAR_BF16) return launch_bwd<bf16>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, map, S(stream));
+  if (dtype == MAR_F32) return launch_bwd<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, map, S(stream));
   MAR_UNSUPPORTED("mar_layernorm_bwd: dtype %d", dtype);
 }
 

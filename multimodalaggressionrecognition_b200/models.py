@@ -116,12 +116,16 @@ def _left_aligned(key_mask: torch.Tensor) -> bool:
     return bool((valid[:, 1:] <= valid[:, :-1]).all())
 
 
-def encoder_forward(enc: nn.TransformerEncoder, x: torch.Tensor, key_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+def encoder_forward(enc: nn.TransformerEncoder, x: torch.Tensor, key_mask: Optional[torch.Tensor] = None, place=None,
+                    split=None):
     """nn.TransformerEncoder(layer, N, norm=LayerNorm) on (B,T,d) (transformer.py:407-553).
 
     Reproduces torch's eval-mode asymmetry: when the encoder is in eval mode, no
     grad is recorded, a key padding mask is given and it is left-aligned, torch's nested-tensor
     fast path re-inserts padded tokens as zeros before the final LayerNorm (transformer.py:455-548).
+
+    place = (buffer, t_off): the final norm writes into buffer[:, t_off:t_off+T] (the fused sequence) and that view is
+    returned; split = [(t0, t1), ...]: the final norm returns one contiguous tensor per time slice (a tuple).
     """
     B, T, d = x.shape
     for layer in enc.layers:
@@ -138,10 +142,19 @@ def encoder_forward(enc: nn.TransformerEncoder, x: torch.Tensor, key_mask: Optio
     for layer in enc.layers:
         h = encoder_layer_forward(layer, h, B, T, key_mask)
     if enc.norm is not None:
+        if place is not None or split is not None:
+            out = ops.layer_norm(h.view(B, T, d), enc.norm.weight, enc.norm.bias, enc.norm.eps, zero_rows=zero_rows,
+                                 place=place, split=split)
+            if place is not None:
+                out._mar_fused = (place[0], place[1])        # lets the fusion module recognise its own slices
+            return out
         h = ops.layer_norm(h, enc.norm.weight, enc.norm.bias, enc.norm.eps, zero_rows=zero_rows)
     elif zero_rows is not None:
         h = h.masked_fill(zero_rows.bool()[:, None], 0.0)
-    return h.view(B, T, d)
+    h = h.view(B, T, d)
+    if split is not None:
+        return ops.split_time(h, split)
+    return h
 
 
 # --------------------------------------------------------------------------------------
@@ -449,7 +462,10 @@ class TransformerSequenceProcessor(nn.Module):
         features = self.feature_extractor(x)
         if ops.probing():
             return features.new_zeros(features.shape)
-        return encoder_forward(self.transformer_squence_processing, features, None)
+        place = None
+        if features.dim() == 3 and features.is_cuda:     # a fusion model may have reserved this encoder's slice of its sequence
+            place = ops.take_final_norm_placement(features.shape[0], features.shape[1], features.shape[2], ops.get_precision())
+        return encoder_forward(self.transformer_squence_processing, features, None, place=place)
 
 
 class OutputClassifier(nn.Module):
@@ -494,10 +510,11 @@ class EqualSizedTransformerModalitiesFusion(nn.Module):
         blocks = list(feats.values())
         concat = blocks[0] if len(blocks) == 1 else ops.concat_time(blocks)
         key_mask = ops.rowzero_mask(concat)
-        fused = encoder_forward(self.modality_fusion_transformer, concat, key_mask)
         if len(blocks) == 1:
-            return {next(iter(feats)): fused}
-        return dict(zip(bounds.keys(), ops.split_time(fused, list(bounds.values()))))
+            return {next(iter(feats)): encoder_forward(self.modality_fusion_transformer, concat, key_mask)}
+        # the encoder's final norm writes every modality's time slice as its own contiguous tensor (models.py:430)
+        parts = encoder_forward(self.modality_fusion_transformer, concat, key_mask, split=list(bounds.values()))
+        return dict(zip(bounds.keys(), parts))
 
     def forward(self, modalities_features_dict):
         return self._fuse(modalities_features_dict)
@@ -611,10 +628,39 @@ class PhysVerbClassifierConcatFeatures(PhysVerbClassifier):
 # top-level multimodal models
 # --------------------------------------------------------------------------------------
 class _MultimodalBase(nn.Module):
+    def _fused_layout(self, input_data):
+        """When the fusion module concatenates the modalities along T (EqualSizedTransformerModalitiesFusion proper) and all
+        feature widths agree, the per-modality features can be produced straight inside the fused (B, ΣT, d) sequence:
+        {modality: (t_off, T)} in the sorted order the fusion sees, and the buffer's shape.  None otherwise."""
+        fusion = getattr(self, "modality_fusion_module", None)
+        if type(fusion) is not EqualSizedTransformerModalitiesFusion or ops.probing() or len(input_data) < 2:
+            return None
+        names = sorted(_split_names(n)[0] for n, _ in input_data)
+        shapes = [self.modality_features_shapes_dict.get(n) for n in names]
+        if any(s is None or len(s) != 2 for s in shapes) or len({s[1] for s in shapes}) != 1 or len(set(names)) != len(names):
+            return None
+        layout, off = {}, 0
+        for n, sh in zip(names, shapes):
+            layout[n] = (off, int(sh[0]))
+            off += int(sh[0])
+        return layout, off, int(shapes[0][1])
+
     def extract_features(self, input_data):
         """models.py:835-863 / :513-541: per modality a zeros stub (B,*shape); the extractor runs on the
         non-EMPTY rows only and its output is scattered back; result sorted by modality name."""
         out = {}
+        fused = self._fused_layout(input_data) if (input_data and input_data[0][1].is_cuda) else None
+        buffer = None
+        if fused is not None:
+            layout, total, width = fused
+            buffer = torch.empty((input_data[0][1].size(0), total, width), device=input_data[0][1].device, dtype=ops.get_precision())
+            # the zero stubs of EMPTY modalities are written first: once an extractor's output is a view of the buffer no
+            # other view of it may be modified in place (autograd's version check)
+            for names, batch in input_data:
+                name, present = _split_names(names)
+                if not (present.any() and name in self.modality_extractors_dict):
+                    t_off, T = layout[name]
+                    buffer[:, t_off:t_off + T].zero_()
         for names, batch in input_data:
             name, present = _split_names(names)
             shape = [batch.size(0)] + list(self.modality_features_shapes_dict[name])
@@ -622,14 +668,23 @@ class _MultimodalBase(nn.Module):
             if present.any() and name in self.modality_extractors_dict:
                 extractor = self.modality_extractors_dict[name]
                 if present.all():
-                    feats = extractor(batch)
+                    if buffer is not None:
+                        with ops.place_final_norm(buffer, *layout[name]):
+                            feats = extractor(batch)
+                    else:
+                        feats = extractor(batch)
                 else:
                     idx = _present_rows(present, batch.device, "idx")
                     got = extractor(batch.index_select(0, idx))
                     feats = torch.zeros(shape, device=batch.device, dtype=got.dtype).index_copy(0, idx, got)
             if feats is None:
                 dtype = batch.dtype if (ops.probing() or not batch.is_cuda) else ops.get_precision()
-                feats = torch.zeros(shape, device=batch.device, dtype=dtype)
+                if buffer is not None and dtype == buffer.dtype:
+                    t_off, T = layout[name]                   # the zero stub of an EMPTY modality, in place (zeroed above)
+                    feats = buffer[:, t_off:t_off + T]
+                    feats._mar_fused = (buffer, t_off)
+                else:
+                    feats = torch.zeros(shape, device=batch.device, dtype=dtype)
             out[name] = feats
         return dict(sorted(out.items()))
 

@@ -491,50 +491,150 @@ def attention(qkv: torch.Tensor, key_mask: Optional[torch.Tensor], num_heads: in
 # --------------------------------------------------------------------------------------
 # layer norm
 # --------------------------------------------------------------------------------------
+def _row_map_args(segs):
+    """ctypes arrays for mar_layernorm_*_mapped from [(t0, t1, Tout, tout0, ptr), ...] (kept alive by the caller)."""
+    import ctypes
+    n = len(segs)
+    I64 = ctypes.c_int64 * n
+    arrs = [I64(*[int(sg[i]) for sg in segs]) for i in range(4)]
+    ptrs = (ctypes.c_void_p * n)(*[int(sg[4]) for sg in segs])
+    return n, arrs, ptrs
+
+
+def _strided_rows(t: torch.Tensor, D: int):
+    """(B,T,D) tensor readable as rows of D with a batch pitch (no copy), or None."""
+    if t.dim() == 3 and t.shape[2] == D and t.stride(2) == 1 and t.stride(1) == D and t.stride(0) % D == 0 \
+            and t.stride(0) >= t.shape[1] * D and (t.data_ptr() % 16) == 0:
+        return t.stride(0) // D
+    return None
+
+
 class _LayerNorm(torch.autograd.Function):
+    """y = LN(x)·gamma + beta on (rows, D).  Plain: one (rows, D) output.  `place` = (buffer (B,Ttot,D), t_off, B, T): the
+    output is written straight into buffer[:, t_off:t_off+T] and that (strided) view is returned — an extractor's final
+    norm lands in its slice of the fused sequence, torch.cat along T costs nothing (models.py:419).  `split` =
+    (B, Ttot, bounds): one contiguous (B, T_k, D) output per (t0, t1) of bounds — the fusion encoder's final norm writes
+    every modality's slice (models.py:430) itself.  Backward reads the incoming gradient(s) through the same row map."""
+
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, zero_rows, need_grad, gamma_ref=None, beta_ref=None):
+    def forward(ctx, x, gamma, beta, eps, zero_rows, need_grad, gamma_ref=None, beta_ref=None, place=None, split=None):
         rows, D = x.shape
         ctx.gamma_ref, ctx.beta_ref = gamma_ref, beta_ref
-        y = torch.empty_like(x)
         if zero_rows is not None and need_grad:
             raise RuntimeError("layer_norm(zero_rows=...) is the eval-only nested-tensor zero fill; no backward")
         mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need_grad else None
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need_grad else None
-        call("mar_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _p(mean), _p(rstd),
-             _p(zero_rows), rows, D, float(eps), _dt(x), _stream())
+        ctx.mode = "plain"
+        if place is not None:
+            buf, t_off, B, T = place
+            assert rows == B * T and buf.dtype == x.dtype and buf.is_contiguous() and buf.shape[0] == B and buf.shape[2] == D
+            segs = [(0, T, buf.shape[1], t_off, buf.data_ptr())]
+            outs = buf[:, t_off:t_off + T]
+            ctx.mode, ctx.Tin = "place", T
+        elif split is not None:
+            B, Ttot, bounds = split
+            assert rows == B * Ttot
+            outs = tuple(torch.empty((B, t1 - t0, D), dtype=x.dtype, device=x.device) for t0, t1 in bounds)
+            segs = [(t0, t1, t1 - t0, 0, o.data_ptr()) for (t0, t1), o in zip(bounds, outs)]
+            ctx.mode, ctx.Tin, ctx.bounds, ctx.B = "split", Ttot, list(bounds), B
+        if ctx.mode == "plain":
+            y = torch.empty_like(x)
+            call("mar_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _p(mean), _p(rstd),
+                 _p(zero_rows), rows, D, float(eps), _dt(x), _stream())
+            outs = y
+        else:
+            n, arrs, ptrs = _row_map_args(segs)
+            call("mar_layernorm_fwd_mapped", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), None, _p(mean), _p(rstd),
+                 _p(zero_rows), rows, D, float(eps), _dt(x), n, ctx.Tin, arrs[0], arrs[1], arrs[2], arrs[3], ptrs, _stream())
         ctx.save_for_backward(x, gamma, mean, rstd)
-        return y
+        return outs
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, *dys):
         x, gamma, mean, rstd = ctx.saved_tensors
         rows, D = x.shape
-        if dy.dtype != x.dtype:
-            dy = _Cast.apply(dy, x.dtype)
-        dy = dy.contiguous()
+        segs = None
+        keep = []
+        if ctx.mode == "plain":
+            dy = dys[0]
+            if dy.dtype != x.dtype:
+                dy = _Cast.apply(dy, x.dtype)
+            dy = dy.contiguous()
+        else:
+            bounds = [(0, ctx.Tin)] if ctx.mode == "place" else ctx.bounds
+            segs = []
+            for (t0, t1), g in zip(bounds, dys):
+                if g is None:                         # a slice nobody used downstream
+                    g = torch.zeros((rows // ctx.Tin, t1 - t0, D), dtype=x.dtype, device=x.device)
+                if g.dtype != x.dtype:
+                    g = _Cast.apply(g, x.dtype)
+                pitch = _strided_rows(g, D)
+                if pitch is None:
+                    g = g.contiguous()
+                    pitch = g.shape[1]
+                keep.append(g)
+                segs.append((t0, t1, pitch, 0, g.data_ptr()))
         dx = torch.empty_like(x)
         sg, sb = _sink_target(ctx.gamma_ref, "ln"), _sink_target(ctx.beta_ref, "ln")
         sunk = sg is not None and sb is not None
         dgamma = sg if sunk else torch.zeros(D, dtype=torch.float32, device=x.device)
         dbeta = sb if sunk else torch.zeros(D, dtype=torch.float32, device=x.device)
-        call("mar_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-             dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D, _dt(x), _stream())
+        if segs is None:
+            call("mar_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                 dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D, _dt(x), _stream())
+        else:
+            n, arrs, ptrs = _row_map_args(segs)
+            call("mar_layernorm_bwd_mapped", None, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                 dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D, _dt(x), n, ctx.Tin, arrs[0], arrs[1], arrs[2],
+                 arrs[3], ptrs, _stream())
         if sunk:
             _sunk(ctx.gamma_ref); _sunk(ctx.beta_ref)
-            return dx, None, None, None, None, None, None, None
-        return dx, dgamma, dbeta, None, None, None, None, None
+            return (dx,) + (None,) * 9
+        return (dx, dgamma, dbeta) + (None,) * 7
 
 
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
-               zero_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+               zero_rows: Optional[torch.Tensor] = None, place=None, split=None):
+    """nn.LayerNorm over the last dim.  place = (buffer (B,Ttot,D), t_off): write into buffer[:, t_off:t_off+T] and return
+    that view; split = [(t0, t1), ...] (x must be (B, Ttot, D)): return one contiguous (B, t1-t0, D) tensor per slice."""
     shape = x.shape
     x2 = to_compute(x).reshape(-1, shape[-1])
     g = gamma if gamma.dtype == torch.float32 else gamma.float()
     b = beta if beta.dtype == torch.float32 else beta.float()
     need_grad = torch.is_grad_enabled() and (x2.requires_grad or g.requires_grad or b.requires_grad)
-    return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad, gamma if g is gamma else None,
-                            beta if b is beta else None).view(shape)
+    gref, bref = (gamma if g is gamma else None), (beta if b is beta else None)
+    if place is not None:
+        buf, t_off = place
+        return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad, gref, bref, (buf, int(t_off), shape[0], shape[1]), None)
+    if split is not None:
+        return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad, gref, bref, None, (shape[0], shape[1], [tuple(map(int, s_)) for s_ in split]))
+    return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad, gref, bref).view(shape)
+
+
+# ---- placement of an extractor's final norm inside the fused sequence ------------------------------------------------
+_place_hint = threading.local()
+
+
+@contextlib.contextmanager
+def place_final_norm(buffer: torch.Tensor, t_off: int, T: int):
+    """While active, the next sequence encoder whose output is (B, T, D) with B, D of `buffer` writes its FINAL
+    LayerNorm into buffer[:, t_off:t_off+T] (models.encoder_forward takes the hint once)."""
+    _place_hint.value = (buffer, int(t_off), int(T))
+    try:
+        yield
+    finally:
+        _place_hint.value = None
+
+
+def take_final_norm_placement(B: int, T: int, D: int, dtype: torch.dtype):
+    hint = getattr(_place_hint, "value", None)
+    if hint is None:
+        return None
+    buf, t_off, Th = hint
+    _place_hint.value = None
+    if Th != T or buf.shape[0] != B or buf.shape[2] != D or buf.dtype != dtype:
+        return None
+    return buf, t_off
 
 
 # --------------------------------------------------------------------------------------
@@ -599,8 +699,44 @@ class _ConcatT(torch.autograd.Function):
         return tuple(outs)
 
 
+class _AliasConcat(torch.autograd.Function):
+    """The blocks already ARE consecutive time slices of one (B, Ttot, D) buffer (every encoder's final norm wrote its
+    slice there): torch.cat along T is the buffer itself, and its backward hands every block a strided view of the
+    incoming gradient — no copy in either direction."""
+
+    @staticmethod
+    def forward(ctx, buffer, *xs):
+        ctx.Ts = [x.shape[1] for x in xs]
+        return buffer.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [], 0
+        for T in ctx.Ts:
+            outs.append(g[:, off:off + T])
+            off += T
+        return (None,) + tuple(outs)
+
+
+def fused_slices_of(xs):
+    """The shared buffer if `xs` are, in order, the consecutive time slices of ONE contiguous (B, Ttot, D) tensor."""
+    tags = [getattr(x, "_mar_fused", None) for x in xs]
+    if not xs or any(t is None for t in tags):
+        return None
+    buf = tags[0][0]
+    off = 0
+    for x, (b_, t_off) in zip(xs, tags):
+        if b_ is not buf or t_off != off or x.dim() != 3 or x.data_ptr() != buf.data_ptr() + off * buf.shape[2] * buf.element_size():
+            return None
+        off += x.shape[1]
+    return buf if off == buf.shape[1] else None
+
+
 def concat_time(xs) -> torch.Tensor:
     """torch.cat(xs, dim=1) for (B,T_i,D) blocks (models.py:419)."""
+    buf = fused_slices_of(xs)
+    if buf is not None:
+        return _AliasConcat.apply(buf, *xs)
     xs = [to_compute(x) for x in xs]
     return _ConcatT.apply(*xs)
 

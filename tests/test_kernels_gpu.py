@@ -418,6 +418,51 @@ def test_layernorm(rows, D, mode):
     assert_close(bg.grad.cpu(), br.grad, tol, "ln dbeta")
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_layernorm_row_maps_place_and_split(mode):
+    """The final norms write torch.cat / the per-modality slices themselves (mar_layernorm_*_mapped): two encoders'
+    norms placed into one fused (B, Ta+Tv, D) buffer == cat of the plain norms, with gradients arriving through strided
+    views; a norm split into per-slice tensors == slices of the plain norm, with one incoming gradient per slice (one of
+    them None)."""
+    B, Ta, Tv, D = 3, 21, 9, 768
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    xa, xv = torch.randn(B, Ta, D, device=DEV), torch.randn(B, Tv, D, device=DEV)
+    ga, ba, gv, bv = [torch.randn(D, device=DEV) for _ in range(4)]
+    go = torch.randn(B, Ta + Tv, D, device=DEV)
+    with mar.precision(mode):
+        leaves = [t.clone().requires_grad_(True) for t in (xa, ga, ba, xv, gv, bv)]
+        ref = torch.cat([ops.layer_norm(leaves[0], leaves[1], leaves[2]), ops.layer_norm(leaves[3], leaves[4], leaves[5])], dim=1)
+        ref.backward(go.to(ref.dtype))
+        ref_grads = [t.grad.clone() for t in leaves]
+        leaves2 = [t.clone().requires_grad_(True) for t in (xa, ga, ba, xv, gv, bv)]
+        buf = torch.full((B, Ta + Tv, D), float("nan"), device=DEV, dtype=dt)
+        pa = ops.layer_norm(leaves2[0], leaves2[1], leaves2[2], place=(buf, 0))
+        pv = ops.layer_norm(leaves2[3], leaves2[4], leaves2[5], place=(buf, Ta))
+        pa._mar_fused, pv._mar_fused = (buf, 0), (buf, Ta)
+        assert pa.data_ptr() == buf.data_ptr() and pv.shape == (B, Tv, D)
+        cat = ops.concat_time([pa, pv])
+        assert cat.data_ptr() == buf.data_ptr()                       # no copy
+        assert torch.equal(cat, ref)
+        cat.backward(go.to(cat.dtype))
+        for a, b_, name in zip([t.grad for t in leaves2], ref_grads, ("dxa", "dga", "dba", "dxv", "dgv", "dbv")):
+            assert_close(a.float(), b_.float(), 1e-6, f"placed layer norm {name}")
+        # blocks that are NOT slices of one buffer still go through the copying concat
+        assert ops.fused_slices_of([pa, ops.layer_norm(xv, gv, bv)]) is None
+        # split
+        x = torch.randn(B, Ta + Tv, D, device=DEV)
+        g, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+        l1 = [t.clone().requires_grad_(True) for t in (x, g, b)]
+        full = ops.layer_norm(l1[0], l1[1], l1[2])
+        full[:, :Ta].float().pow(2).sum().backward()
+        l2 = [t.clone().requires_grad_(True) for t in (x, g, b)]
+        sa, sv = ops.layer_norm(l2[0], l2[1], l2[2], split=[(0, Ta), (Ta, Ta + Tv)])
+        assert sa.is_contiguous() and sv.is_contiguous() and torch.equal(sa, full[:, :Ta]) and torch.equal(sv, full[:, Ta:])
+        sa.float().pow(2).sum().backward()                          # the second slice gets no gradient at all
+        for a, b_, name in zip([t.grad for t in l2], [t.grad for t in l1], ("dx", "dgamma", "dbeta")):
+            assert_close(a.float(), b_.float(), 1e-6, f"split layer norm {name}")
+        assert float(l2[0].grad[:, Ta:].abs().max()) == 0.0
+
+
 def test_layernorm_zero_rows_is_beta():
     x = torch.randn(10, 768, device=DEV)
     g, b = torch.randn(768, device=DEV), torch.randn(768, device=DEV)
