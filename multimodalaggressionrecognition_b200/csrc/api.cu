@@ -112,10 +112,14 @@ int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* 
   MAR_CHECK_ARG(!(add && act), "mar_linear_dgrad: add and act are mutually exclusive");
   if (M == 0) return MAR_OK;
   TcGemmArgs a;
-  a.A = dz; a.lda = N; a.B = wt; a.ldb = N; a.out = dx; a.ldo = lddx; a.out_fp32 = 0;
+  a.A = dz; a.lda = N; a.out = dx; a.ldo = lddx; a.out_fp32 = 0;
   a.M = M; a.N = K; a.Kr = N; a.residual = add; a.ldr = lddx; a.aux = act; a.ldaux = lddx; a.aux_scale = act_scale;
-  const bool tc_ok = dtype == MAR_BF16 && wt != nullptr && gemm_tcgen05_supported(a);
-  if (engine == MAR_ENGINE_TCGEN05 && !tc_ok) MAR_UNSUPPORTED("mar_linear_dgrad: tcgen05 engine cannot take M=%lld N=%lld K=%lld (needs bf16 and wt)", (long long)M, (long long)N, (long long)K);
+  // B operand: W itself, (N,K) row-major = MN-major over the reduction dimension N (no transposed copy needed);
+  // a caller-provided Wᵀ (K,N) is used as a K-major operand when W is absent (MAR_DGRAD_WT=1 prefers it, for A/B runs)
+  if (w != nullptr && !(wt != nullptr && env_flag("MAR_DGRAD_WT"))) { a.B = w; a.ldb = K; a.b_mn_major = 1; }
+  else { a.B = wt; a.ldb = N; a.b_mn_major = 0; }
+  const bool tc_ok = dtype == MAR_BF16 && a.B != nullptr && gemm_tcgen05_supported(a);
+  if (engine == MAR_ENGINE_TCGEN05 && !tc_ok) MAR_UNSUPPORTED("mar_linear_dgrad: tcgen05 engine cannot take M=%lld N=%lld K=%lld (needs bf16)", (long long)M, (long long)N, (long long)K);
   const bool use_tc = engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && tc_ok && M >= 64 && K >= 64 && !env_flag("MAR_FORCE_SIMT"));
   if (use_tc) return gemm_tcgen05(a, S(stream));
   if (skinny_supported(N) && w != nullptr && act == nullptr) return skinny_dgrad(dz, w, add, dx, lddx, M, N, K, dtype, S(stream));

@@ -418,10 +418,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, 
   return MAR_OK;
 }
 
-template <int BN, bool MN, typename OutT>
+template <int BN, bool A_MN, bool B_MN, typename OutT>
 int launch_cl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& ms, const TcParams& p,
               int cl, cudaStream_t st) {
-  return cl == 2 ? launch<BN, MN, MN, OutT, 2>(ma, mb, mo, ms, p, st) : launch<BN, MN, MN, OutT, 1>(ma, mb, mo, ms, p, st);
+  return cl == 2 ? launch<BN, A_MN, B_MN, OutT, 2>(ma, mb, mo, ms, p, st) : launch<BN, A_MN, B_MN, OutT, 1>(ma, mb, mo, ms, p, st);
 }
 
 }  // namespace
@@ -439,8 +439,11 @@ bool gemm_tcgen05_supported(const TcGemmArgs& a) {
   if ((a.aux != nullptr || a.residual != nullptr) && a.out_fp32) return false;
   const int64_t osz = a.out_fp32 ? 4 : 2;
   if ((a.ldo * osz) % 16 != 0) return false;
-  if (a.a_mn_major != a.b_mn_major) return false;   // TN (fwd/dgrad) and NT-on-rows (wgrad) only
+  // TN (forward, dgrad on a transposed weight copy), NT-on-rows (wgrad, fp32 out) and dgrad on the weight itself
+  // (A = dz K-major, B = W (N,K) row-major = MN-major over the reduction, bf16 out)
+  if (a.a_mn_major && !a.b_mn_major) return false;
   if (a.a_mn_major && !a.out_fp32) return false;
+  if (!a.a_mn_major && a.b_mn_major && a.out_fp32) return false;
   if (a.M >= (1ll << 31) || a.N >= (1ll << 31) || a.Kr >= (1ll << 31)) return false;
   return true;
 }
@@ -496,7 +499,9 @@ int gemm_tcgen05(const TcGemmArgs& a, cudaStream_t st) {
   int rc;
   if (!a.a_mn_major) {
     rc = make_map(&ma, a.A, a.M, a.Kr, a.lda, BLOCK_M); if (rc) return rc;
-    rc = make_map(&mb, a.B, a.N, a.Kr, a.ldb, BN / cl); if (rc) return rc;
+    if (a.b_mn_major) rc = make_map(&mb, a.B, a.Kr, a.N, a.ldb, BLOCK_K);
+    else rc = make_map(&mb, a.B, a.N, a.Kr, a.ldb, BN / cl);
+    if (rc) return rc;
   } else {
     rc = make_map(&ma, a.A, a.Kr, a.M, a.lda, BLOCK_K); if (rc) return rc;
     rc = make_map(&mb, a.B, a.Kr, a.N, a.ldb, BLOCK_K); if (rc) return rc;
@@ -510,8 +515,9 @@ int gemm_tcgen05(const TcGemmArgs& a, cudaStream_t st) {
     mo = ma; ms = ma;   // unused by the fp32 epilogue
   }
   if (!a.a_mn_major) {
-    if (a.out_fp32) return BN == 256 ? launch_cl<256, false, float>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, float>(ma, mb, mo, ms, p, cl, st);
-    return BN == 256 ? launch_cl<256, false, bf16>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, bf16>(ma, mb, mo, ms, p, cl, st);
+    if (a.b_mn_major) return BN == 256 ? launch_cl<256, false, true, bf16>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, true, bf16>(ma, mb, mo, ms, p, cl, st);
+    if (a.out_fp32) return BN == 256 ? launch_cl<256, false, false, float>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, false, float>(ma, mb, mo, ms, p, cl, st);
+    return BN == 256 ? launch_cl<256, false, false, bf16>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, false, bf16>(ma, mb, mo, ms, p, cl, st);
   }
-  return BN == 256 ? launch_cl<256, true, float>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, true, float>(ma, mb, mo, ms, p, cl, st);
+  return BN == 256 ? launch_cl<256, true, true, float>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, true, true, float>(ma, mb, mo, ms, p, cl, st);
 }

@@ -276,6 +276,7 @@ import os as _os
 # AccumulateGrad node ran at all); since the step driver registers a post-accumulate hook on every parameter, created
 # on the capture stream, the nodes exist and capture works (measured on B200, round 2: 9.16 -> 9.05 ms per step).
 _SINK_KINDS = set(_os.environ.get("MAR_SINK", "w,b,ln").split(","))
+_DGRAD_WT = _os.environ.get("MAR_DGRAD_WT") == "1"
 
 
 def _sink_target(param, kind: str = "w") -> Optional[torch.Tensor]:
@@ -310,7 +311,8 @@ class _Linear(torch.autograd.Function):
         M, K = x.shape
         N = weight.shape[0]
         cd = x.dtype
-        need_t = cd == torch.bfloat16 and need_dx
+        # dgrad reads W itself as an MN-major tcgen05 operand: no transposed bf16 copy (MAR_DGRAD_WT=1: the round-1 path)
+        need_t = cd == torch.bfloat16 and need_dx and _DGRAD_WT
         wc, wt = compute_weight(weight, cd, need_t)
         out = torch.empty((M, N), dtype=out_dtype, device=x.device)
         site = 0
