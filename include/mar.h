@@ -232,10 +232,12 @@ int mar_adam_tick(float* step_dev, void* stream);
  * buffers; every segment starts on a multiple of `chunk` floats (a power of two); chunk_seg (n / chunk, int32) names
  * the segment of each chunk (< 0: padding); seg_active (nseg fp32) > 0 marks the parameters that received a gradient;
  * seg_steps (nseg fp32) are the per-parameter step counts (advanced here); seg_coef (2·nseg fp32, 8 B aligned) is
- * scratch.  Two launches, graph-capturable. */
+ * scratch.  bf16_mirror (n bf16, 8 B aligned, or NULL): the compute-dtype copy of the flat parameter buffer, rewritten
+ * wherever a parameter is updated, so that no per-step weight cast is needed.  Two launches, graph-capturable. */
 int mar_adam_step_segments(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                            const int32_t* chunk_seg, float* seg_steps, const float* seg_active, float* seg_coef,
-                           int64_t n, int chunk, int nseg, float lr, float beta1, float beta2, float eps, void* stream);
+                           int64_t n, int chunk, int nseg, float lr, float beta1, float beta2, float eps, void* bf16_mirror,
+                           void* stream);
 /* out[0] = sum over rows with 0 <= label < C of class_weight[label] (1 per row when class_weight is NULL): the
  * denominator of nn.CrossEntropyLoss(reduction='mean') (models.py:232-263).  Data-parallel ranks exchange it to weigh
  * their gradients so that the reduced gradient is the one of the loss over the GLOBAL batch. */

@@ -57,7 +57,7 @@ PROTOTYPES = {
     "mar_lstm_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P]),
     "mar_adam_step": (c_int, [P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P]),
     "mar_adam_tick": (c_int, [P, P]),
-    "mar_adam_step_segments": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_float, c_float, c_float, c_float, P]),
+    "mar_adam_step_segments": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_float, c_float, c_float, c_float, P, P]),
     "mar_label_weight_sum": (c_int, [P, P, P, c_int64, c_int64, P]),
 }
 

@@ -447,7 +447,7 @@ __global__ void adam_seg_tick_kernel(float* __restrict__ seg_steps, const float*
 __global__ void __launch_bounds__(256)
 adam_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 const int32_t* __restrict__ chunk_seg, const float2* __restrict__ seg_coef, int64_t n, int chunk_shift,
-                float b1, float b2, float eps) {
+                float b1, float b2, float eps, bf16* __restrict__ mirror) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   const int seg = chunk_seg[i >> chunk_shift];
@@ -466,6 +466,8 @@ adam_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
   *reinterpret_cast<float4*>(p + i) = pp;
   *reinterpret_cast<float4*>(m + i) = mm;
   *reinterpret_cast<float4*>(v + i) = vv;
+  if (mirror != nullptr)       // the bf16 compute copy of the parameters, refreshed where they change
+    *reinterpret_cast<uint2*>(mirror + i) = make_uint2(pack_bf16x2(pp.x, pp.y), pack_bf16x2(pp.z, pp.w));
 }
 
 // norm[0] = Σ_{rows with label >= 0} class_weight[label] (1 per row without weights): the denominator of
@@ -645,14 +647,15 @@ int mar_adam_tick(float* step_dev, void* stream) {
 
 int mar_adam_step_segments(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                            const int32_t* chunk_seg, float* seg_steps, const float* seg_active, float* seg_coef,
-                           int64_t n, int chunk, int nseg, float lr, float beta1, float beta2, float eps, void* stream) {
+                           int64_t n, int chunk, int nseg, float lr, float beta1, float beta2, float eps, void* bf16_mirror,
+                           void* stream) {
   MAR_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && chunk_seg && seg_steps && seg_active && seg_coef && n >= 0 &&
                     nseg > 0, "mar_adam_step_segments: bad arguments");
   MAR_CHECK_ARG(chunk >= 4 && (chunk & (chunk - 1)) == 0, "mar_adam_step_segments: chunk must be a power of two >= 4");
   MAR_CHECK_ARG(n % chunk == 0, "mar_adam_step_segments: n must be a multiple of chunk");
   if (n == 0) return MAR_OK;
   MAR_CHECK_ARG(((uintptr_t)param % 16 == 0) && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)exp_avg % 16 == 0) &&
-                    ((uintptr_t)exp_avg_sq % 16 == 0) && ((uintptr_t)seg_coef % 8 == 0),
+                    ((uintptr_t)exp_avg_sq % 16 == 0) && ((uintptr_t)seg_coef % 8 == 0) && ((uintptr_t)bf16_mirror % 8 == 0),
                 "mar_adam_step_segments: buffers must be 16 B aligned");
   int shift = 0;
   while ((1 << shift) < chunk) shift++;
@@ -660,7 +663,8 @@ int mar_adam_step_segments(float* param, const float* grad, float* exp_avg, floa
                                                                             reinterpret_cast<float2*>(seg_coef), nseg, lr, beta1, beta2);
   MAR_LAUNCH_CHECK("adam_seg_tick");
   adam_seg_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, S(stream)>>>(
-      param, grad, exp_avg, exp_avg_sq, chunk_seg, reinterpret_cast<const float2*>(seg_coef), n, shift, beta1, beta2, eps);
+      param, grad, exp_avg, exp_avg_sq, chunk_seg, reinterpret_cast<const float2*>(seg_coef), n, shift, beta1, beta2, eps,
+      reinterpret_cast<bf16*>(bf16_mirror));
   MAR_LAUNCH_CHECK("adam_seg");
   return MAR_OK;
 }

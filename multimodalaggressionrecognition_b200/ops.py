@@ -194,6 +194,14 @@ def weights_changed() -> None:
     _wepoch[0] += 1
 
 
+# bf16 mirrors maintained by the step driver's Adam kernel (training.FlatParams): parameter address -> (view, weakref, version)
+_mirror = {}
+
+
+def register_weight_mirror(param: torch.Tensor, view: torch.Tensor) -> None:
+    _mirror[param.data_ptr()] = [view, weakref.ref(param), param._version]
+
+
 def compute_weight(w: torch.Tensor, dtype: torch.dtype, need_t: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """(W, Wᵀ) in the compute dtype.  fp32 mode uses the parameter itself.  bf16 copies are cached per
     parameter version (torch optimizers bump it; `weights_changed()` covers updates torch does not see), so eval
@@ -202,6 +210,12 @@ def compute_weight(w: torch.Tensor, dtype: torch.dtype, need_t: bool) -> Tuple[t
     version counter must not pick up the old model's copy."""
     if dtype == torch.float32:
         return (w if w.is_contiguous() else w.contiguous()), None
+    if dtype == torch.bfloat16 and not need_t:
+        # the step driver keeps a bf16 copy current from inside its Adam kernel; it is valid as long as nobody else wrote
+        # the parameter (any torch in-place update bumps the version) — then the ordinary cast below takes over
+        ent = _mirror.get(w.data_ptr())
+        if ent is not None and ent[1]() is w and ent[2] == w._version and tuple(ent[0].shape) == tuple(w.shape):
+            return ent[0], None
     key = (w.data_ptr(), tuple(w.shape), dtype)
     ent = _wcache.get(key)
     ver = w._version

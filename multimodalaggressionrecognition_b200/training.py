@@ -59,6 +59,15 @@ class FlatParams:
                 self.flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
                 p.data = self.flat[o:o + p.numel()].view(p.shape)
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        # bf16 compute copy of the whole buffer: the Adam kernel rewrites it wherever it updates a parameter, so the
+        # forward's weights need no per-step cast kernels (ops.compute_weight finds the 2-D parameters' views here)
+        self.mirror = None
+        if dev.type == "cuda":
+            self.mirror = torch.empty(off, dtype=torch.bfloat16, device=dev)
+            call("mar_cast", self.flat.data_ptr(), 0, self.mirror.data_ptr(), 1, off, _stream())
+            for p, o in zip(self.params, self.offsets):
+                if p.dim() == 2:
+                    ops.register_weight_mirror(p, self.mirror[o:o + p.numel()].view(p.shape))
 
     def zero_grad(self) -> None:
         self.grad.zero_()
@@ -91,7 +100,7 @@ class FlatAdam:
         call("mar_adam_step_segments", f.flat.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
              self.exp_avg_sq.data_ptr(), f.chunk_seg.data_ptr(), self.seg_steps.data_ptr(), f.flags.data_ptr(),
              self.seg_coef.data_ptr(), f.numel, f.align, f.nseg, self.lr, self.betas[0], self.betas[1], self.eps,
-             _stream())
+             None if f.mirror is None else f.mirror.data_ptr(), _stream())
         ops.weights_changed()      # raw-pointer update: torch's version counters did not move
 
     def zero_grad(self, set_to_none: bool = False) -> None:

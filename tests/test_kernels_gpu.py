@@ -752,7 +752,15 @@ def test_segmented_adam_kernel_skips_inactive_parameters_and_counts_steps_per_pa
     with pytest.raises(RuntimeError, match="chunk"):
         call("mar_adam_step_segments", flat.flat.data_ptr(), flat.grad.data_ptr(), opt.exp_avg.data_ptr(),
              opt.exp_avg_sq.data_ptr(), flat.chunk_seg.data_ptr(), opt.seg_steps.data_ptr(), flat.flags.data_ptr(),
-             opt.seg_coef.data_ptr(), flat.numel, 48, flat.nseg, 1e-3, 0.9, 0.999, 1e-8, 0)
+             opt.seg_coef.data_ptr(), flat.numel, 48, flat.nseg, 1e-3, 0.9, 0.999, 1e-8, None, 0)
+    # the bf16 mirror the kernel maintains equals a fresh cast of the updated parameters, and ops.compute_weight serves it
+    assert torch.equal(flat.mirror.float(), flat.flat.to(torch.bfloat16).float())
+    wc, _ = ops.compute_weight(params[0], torch.bfloat16, False)
+    assert wc.data_ptr() == flat.mirror.data_ptr() + 2 * flat.offsets[0]
+    with torch.no_grad():
+        params[0].add_(1.0)                       # a foreign in-place update: the mirror is no longer trusted
+    wc2, _ = ops.compute_weight(params[0], torch.bfloat16, False)
+    assert wc2.data_ptr() != wc.data_ptr() and torch.equal(wc2.float(), params[0].detach().to(torch.bfloat16).float())
 
 
 def test_label_weight_sum_kernel():
