@@ -212,7 +212,15 @@ def run_ours(args):
     B = args.batch
     data, labels = W.batch_c3(B=B, t_audio=T_AUDIO, t_video=T_VIDEO, seed=1000 + rank)
     use_graph = not args.no_graph           # world > 1: the NCCL all-reduces are captured into the step graph too
-    step = training.TrainStep(model, crit, graph=use_graph)
+    # data-parallel knobs for A/B measurements (defaults = TrainStep's): MAR_WIRE=fp32|bf16, MAR_BUCKETS=n, MAR_TAIL=elements
+    dp_kw = {}
+    if os.environ.get("MAR_WIRE"):
+        dp_kw["wire"] = os.environ["MAR_WIRE"]
+    if os.environ.get("MAR_BUCKETS"):
+        dp_kw["num_buckets"] = int(os.environ["MAR_BUCKETS"])
+    if os.environ.get("MAR_TAIL"):
+        dp_kw["tail_elems"] = int(os.environ["MAR_TAIL"])
+    step = training.TrainStep(model, crit, graph=use_graph, **dp_kw)
 
     def barrier():
         if world > 1:
@@ -277,7 +285,11 @@ def run_ours(args):
     roof = None
     if rank == 0:
         step.sync.enabled = False          # this extra backward runs on rank 0 only: no collectives
-        roof = gemm_roofline(model, crit, gdata, glabels, args, ops, training)
+        side = step._side if step._side is not None else torch.cuda.current_stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):       # the stream the parameters' AccumulateGrad nodes live on
+            roof = gemm_roofline(model, crit, gdata, glabels, args, ops, training)
+        torch.cuda.current_stream().wait_stream(side)
 
     def shutdown():
         # graphs that captured NCCL collectives must go before the communicator; a watchdog makes sure a stuck
@@ -317,6 +329,8 @@ def run_ours(args):
                                f"T_a={T_AUDIO}x768, T_v={T_VIDEO}x512, d=768, 8 heads, d_ff=2048, 19.7M params, dropout on",
                    "global_batch": global_batch, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "cuda_graph": bool(use_graph),
+                   "grad_exchange": None if world == 1 else {"wire": step.sync.wire, "buckets": len(step.sync.buckets),
+                                                              "bucket_elems": [e1 - e0 for _, _, e0, e1 in step.sync.buckets]},
                    "l2": "inputs (229 MB/step fp32) and activations (> 3 GB/step) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": global_batch / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8},

@@ -122,21 +122,38 @@ class GradSync:
       last bucket holds the header flags and always goes from `finish()`: a parameter is active if ANY rank saw a
       gradient for it, as in a single process on the global batch."""
 
-    def __init__(self, flat: FlatParams, group=None, num_buckets: int = 4):
+    def __init__(self, flat: FlatParams, group=None, num_buckets: int = 4, wire: str = "fp32", tail_elems: int = 0):
+        """wire: "fp32" (exact) or "bf16" — gradients are rounded to bf16 for the exchange (half the bytes on NVLink; the
+        sum is accumulated by NCCL in bf16) and widened again before Adam; the bf16-mode step uses it, fp32 mode never.
+        tail_elems > 0: the LAST bucket (the first parameters = the end of backward, whose all-reduce nothing can hide)
+        is cut as small as parameter boundaries allow above that many elements."""
         self.flat = flat
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.cuda = flat.grad.is_cuda
         self.comm_stream = torch.cuda.Stream() if (self.cuda and self.world > 1) else None
+        if wire not in ("fp32", "bf16"):
+            raise ValueError("wire must be 'fp32' or 'bf16'")
+        self.wire = wire if (self.cuda and self.world > 1) else "fp32"
         n = len(flat.params)
         total = flat.numel
-        # split by element count, aligned to parameter boundaries
-        bounds, target, acc = [n], total / max(1, num_buckets), 0
-        for i in range(n - 1, -1, -1):
+        # the small tail bucket first (from parameter 0 upwards), then the rest split by element count from the end,
+        # all aligned to parameter boundaries
+        first = 0
+        if tail_elems > 0 and num_buckets > 1:
+            acc = 0
+            while first < n - 1 and acc < tail_elems:
+                acc += flat.params[first].numel()
+                first += 1
+        rest = sum(flat.params[i].numel() for i in range(first, n))
+        bounds, target, acc = [n], rest / max(1, num_buckets - (1 if first else 0)), 0
+        for i in range(n - 1, first - 1, -1):
             acc += flat.params[i].numel()
-            if acc >= target and i > 0:
+            if acc >= target and i > first:
                 bounds.append(i)
                 acc = 0
+        if first:
+            bounds.append(first)
         bounds.append(0)
         self.buckets = []           # (param index range [lo, hi), element range [e0, e1))
         for hi, lo in zip(bounds[:-1], bounds[1:]):
@@ -157,6 +174,10 @@ class GradSync:
         self.index_of = {id(p): i for i, p in enumerate(flat.params)}
         self._hooks = [self._make_hook(i) for i in range(n)]
         self._masks: Dict[bytes, torch.Tensor] = {}      # active pattern -> device flags (one upload per pattern)
+        self._wire_buf = None
+        if self.wire == "bf16":
+            self._wire_buf = torch.empty(max(e1 - e0 for _, _, e0, e1 in self.buckets), dtype=torch.bfloat16, device=flat.grad.device)
+            self._wire_done: List[Optional[torch.cuda.Event]] = [None]
         self.last_active: Optional[List[bool]] = None
         for i, p in enumerate(flat.params):
             p.register_post_accumulate_grad_hook(self._hooks[i])
@@ -222,7 +243,16 @@ class GradSync:
                     if key != cur.cuda_stream:
                         self.comm_stream.wait_stream(s)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+                if self.wire == "bf16":
+                    # fp32 slice -> bf16 staging -> all-reduce -> back into the fp32 slice, all on the communication stream
+                    # (one staging buffer: the buckets go through it one after the other in stream order)
+                    stage = self._wire_buf[: e1 - e0]
+                    st = self.comm_stream.cuda_stream
+                    call("mar_cast", view.data_ptr(), 0, stage.data_ptr(), 1, e1 - e0, st)
+                    dist.all_reduce(stage, op=dist.ReduceOp.SUM, group=self.group)
+                    call("mar_cast", stage.data_ptr(), 1, view.data_ptr(), 0, e1 - e0, st)
+                else:
+                    dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
         else:
             dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
 
@@ -261,7 +291,8 @@ class TrainStep:
     step i is still executing, so the transfer is hidden behind compute without any change to the call."""
 
     def __init__(self, model: nn.Module, criterion: Callable, lr: float = 1e-3, graph: bool = False,
-                 group=None, num_buckets: int = 4, precision: Optional[str] = None):
+                 group=None, num_buckets: int = 6, precision: Optional[str] = None, wire: Optional[str] = None,
+                 tail_elems: int = 1 << 20):
         self.model, self.criterion = model, criterion
         self.flat = FlatParams(list(model.parameters()))
         self.opt = FlatAdam(self.flat, lr=lr)
@@ -270,7 +301,10 @@ class TrainStep:
         # cross-stream synchronisation per parameter and warns about the mismatch on every backward.
         self._side = torch.cuda.Stream() if (graph and self.flat.flat.is_cuda) else None
         with (torch.cuda.stream(self._side) if self._side is not None else _null()):
-            self.sync = GradSync(self.flat, group=group, num_buckets=num_buckets)
+            if wire is None:       # bf16 compute -> bf16 gradient exchange; fp32 mode keeps the exchange exact
+                mode = precision if precision is not None else ("fp32" if ops.get_precision() == torch.float32 else "bf16")
+                wire = "bf16" if (mode == "bf16" and self.flat.flat.is_cuda) else "fp32"
+            self.sync = GradSync(self.flat, group=group, num_buckets=num_buckets, wire=wire, tail_elems=tail_elems)
         if self.sync.world > 1 and self.flat.flat.is_cuda and ops._rng.seed is None:
             # every rank seeds torch identically (same initial weights), which would also give every rank the SAME
             # dropout masks for its different clips; a single process on the global batch draws independent masks per

@@ -343,3 +343,19 @@ def test_bucket_layout_covers_every_parameter_once():
         assert e0 == (flat.offsets[lo] if lo > 0 else 0) and e1 > e0      # parameter 0's bucket carries the flag header
     assert sorted(covered) == list(range(len(flat.params)))
     assert sync.buckets[0][1] == len(flat.params)                    # first bucket = the LAST parameters (backward order)
+
+
+def test_tail_bucket_is_cut_small():
+    """The last bucket to be reduced (the first parameters: the end of backward, nothing left to hide its all-reduce
+    behind) is cut just above `tail_elems`; the others split the rest from the end; every parameter exactly once."""
+    torch.manual_seed(0)
+    model = nn.Sequential(*[nn.Linear(64, 64) for _ in range(6)])
+    flat = training.FlatParams(list(model.parameters()))
+    sync = training.GradSync(flat, num_buckets=4, tail_elems=3000)
+    lo, hi, e0, e1 = sync.buckets[-1]
+    assert (lo, hi) == (0, 1) and e0 == 0                      # one 4096-element weight >= 3000, plus the flag header
+    covered = [i for lo_, hi_, _, _ in sync.buckets for i in range(lo_, hi_)]
+    assert sorted(covered) == list(range(len(flat.params))) and len(sync.buckets) == 4
+    assert sync.wire == "fp32"                                    # the bf16 wire is a CUDA / multi-rank option only
+    with pytest.raises(ValueError):
+        training.GradSync(flat, wire="fp16")

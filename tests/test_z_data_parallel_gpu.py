@@ -59,14 +59,15 @@ def _rows(labels):
     return {names[0].split("_")[0]: sum(n.split("_")[-1] != "EMPTY" for n in names) for names, _ in labels}
 
 
-def _worker(rank, world, port, steps, graph, result_q, mixed=False):
+def _worker(rank, world, port, steps, graph, result_q, mixed=False, precision="fp32"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        step = training.TrainStep(_model(dev), _crit(), lr=1e-3, graph=graph, precision="fp32")
+        step = training.TrainStep(_model(dev), _crit(), lr=1e-3, graph=graph, precision=precision)
         assert step.sync.world == world and len(step.sync.buckets) >= 2
+        assert step.sync.wire == ("bf16" if precision == "bf16" else "fp32")
         curve = []
         for s in range(steps):
             data, labels = _batch(s, world, rank, mixed)
@@ -122,6 +123,39 @@ def test_two_gpu_step_matches_single_gpu_on_the_global_batch(graph, mixed):
             # same bar as the eager-vs-graph test: reduction order differs (two 8-clip gradients averaged by NCCL
             # instead of one 16-clip gradient), Adam amplifies that to a few 1e-4 over the steps
             assert abs(got - v) <= 2e-3 * max(1.0, abs(v)), f"step {s} loss[{k}]: {world} GPUs {got} vs single GPU {v}"
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_bf16_step_with_bf16_gradient_exchange():
+    """bf16 mode exchanges the gradients in bf16 (half the NVLink bytes): after 7 graph-captured steps the ranks hold
+    bit-identical parameters and the loss curve stays with the single-GPU bf16 run on the global batch (two bf16 runs
+    of this transient agree to ~1e-2; a broken exchange is ~0.3 off)."""
+    world, steps = 2, 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, steps, True, q, False, "bf16")) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        same, curves = q.get(timeout=240)
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs)
+    assert same, "ranks hold different parameters after the same steps"
+    dev = torch.device("cuda", 0)
+    single = training.TrainStep(_model(dev), _crit(), lr=1e-3, graph=False, precision="bf16")
+    for s in range(steps):
+        data, labels = _batch(s, world)
+        ref = {k: float(v) for k, v in single(W.to_device(data, dev), W.to_device(labels, dev)).items()}
+        for k, v in ref.items():
+            parts = [c[s][k] for c in curves if k in c[s]]
+            got = sum(l * n for l, n in parts) / sum(n for _, n in parts)
+            assert abs(got - v) <= 0.1 * max(1.0, abs(v)), f"step {s} loss[{k}]: 2 GPUs (bf16 exchange) {got} vs single GPU {v}"
 
 
 def test_eager_bf16_train_step_sees_its_own_weight_updates():
