@@ -24,6 +24,10 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+import os as _os
+_NOCOMM = _os.environ.get("MAR_DP_NOCOMM") == "1"
+
+
 class FlatParams:
     """Moves a model's parameters into ONE contiguous fp32 buffer (params become views, state_dict keys and
     shapes are unchanged) and gives every parameter a persistent .grad view into ONE flat gradient buffer.
@@ -230,6 +234,8 @@ class GradSync:
     def _launch(self, b: int) -> None:
         self.launched[b] = True
         self.order.append(b)
+        if _NOCOMM:          # diagnostic only (MAR_DP_NOCOMM=1): what the step costs without any exchange — ranks drift apart
+            return
         _, _, e0, e1 = self.buckets[b]
         view = self.flat.grad[e0:e1]
         if self.comm_stream is not None:
@@ -291,8 +297,12 @@ class TrainStep:
     step i is still executing, so the transfer is hidden behind compute without any change to the call."""
 
     def __init__(self, model: nn.Module, criterion: Callable, lr: float = 1e-3, graph: bool = False,
-                 group=None, num_buckets: int = 6, precision: Optional[str] = None, wire: Optional[str] = None,
-                 tail_elems: int = 1 << 20):
+                 group=None, num_buckets: int = 1, precision: Optional[str] = None, wire: Optional[str] = None,
+                 tail_elems: int = 0):
+        # num_buckets = 1 (ONE all-reduce after backward) is the measured optimum on B200 for this model (19.7 M parameters,
+        # 39 MB in bf16): NCCL's CTAs running beside the persistent one-CTA-per-SM GEMMs cost the GEMMs as much as the
+        # overlap hides — N = 8: 6 buckets 9.34 ms, 2 buckets 9.29, 1 bucket 9.28, no exchange at all 8.99 ms per step
+        # (profiles/r02_dp_matrix_n8.txt); larger models / slower links: raise num_buckets, set tail_elems.
         self.model, self.criterion = model, criterion
         self.flat = FlatParams(list(model.parameters()))
         self.opt = FlatAdam(self.flat, lr=lr)

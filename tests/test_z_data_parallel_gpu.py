@@ -65,7 +65,7 @@ def _worker(rank, world, port, steps, graph, result_q, mixed=False, precision="f
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        step = training.TrainStep(_model(dev), _crit(), lr=1e-3, graph=graph, precision=precision)
+        step = training.TrainStep(_model(dev), _crit(), lr=1e-3, graph=graph, precision=precision, num_buckets=4, tail_elems=100_000)
         assert step.sync.world == world and len(step.sync.buckets) >= 2
         assert step.sync.wire == ("bf16" if precision == "bf16" else "fp32")
         curve = []
