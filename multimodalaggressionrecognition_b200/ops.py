@@ -123,7 +123,12 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         raise RuntimeError(
             f"{what}: got a {t.device} tensor. multimodalaggressionrecognition_b200 runs only on sm_100a CUDA "
             "devices; there is no CPU path (use shape_probe() for the reference's CPU shape probing).")
-    _lib.check_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        # kernels are enqueued on torch's CURRENT stream, which belongs to the current device
+        raise RuntimeError(f"{what}: tensor lives on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()}; "
+                           f"call torch.cuda.set_device({idx}) (one process per GPU) or wrap the call in torch.cuda.device({idx})")
+    _lib.check_device(idx)
 
 
 def _rows(t: torch.Tensor) -> torch.Tensor:

@@ -14,6 +14,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+import torch.utils.data
 
 from . import ops
 from ._lib import call
@@ -541,6 +542,52 @@ class TrainStep:
         self._graphs = {}
         if self.flat.flat.is_cuda:
             torch.cuda.synchronize()
+
+
+def shard_batch(batch, rank: int, world: int):
+    """Rank `rank`'s contiguous share of every per-sample sequence of a (nested) batch in the datasets.py layouts:
+    tensors are sliced along dim 0, name tuples (the `_EMPTY` markers, datasets.py:592-608) along their length."""
+    def cut(n):
+        return n * rank // world, n * (rank + 1) // world
+
+    def walk(x):
+        if isinstance(x, torch.Tensor):
+            lo, hi = cut(x.shape[0])
+            return x[lo:hi]
+        if isinstance(x, (list, tuple)) and x and isinstance(x[0], str):
+            lo, hi = cut(len(x))
+            return type(x)(x[lo:hi])
+        if isinstance(x, (list, tuple)):
+            return [walk(y) for y in x]
+        return x
+    return walk(batch)
+
+
+class ShardedBatchSampler(torch.utils.data.Sampler):
+    """Data-parallel wrapper for the reference's `AggrBatchSampler` (datasets.py:620-655), as the `batch_sampler` of every
+    rank's DataLoader.  That sampler makes every batch homogeneous in aggression type and reshuffles with
+    `random.seed(None)` (datasets.py:636,643), so two ranks building their own would draw different batches: here rank 0's
+    list of index batches is broadcast once per epoch and every rank yields ITS contiguous slice of the SAME batch — all
+    ranks step on one homogeneous batch, i.e. the same set of active heads and modalities, exactly as a single process on
+    the global batch (batch_size of the wrapped sampler = the GLOBAL batch)."""
+
+    def __init__(self, base, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+        self.base, self.group = base, group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+
+    def __iter__(self):
+        batches = [list(b) for b in self.base] if self.rank == 0 else None     # (iterating also reshuffles the reference's sampler)
+        if self.world > 1:
+            box = [batches]
+            dist.broadcast_object_list(box, src=0, group=self.group)
+            batches = box[0]
+        for b in batches:
+            lo, hi = len(b) * self.rank // self.world, len(b) * (self.rank + 1) // self.world
+            yield b[lo:hi]
+
+    def __len__(self):
+        return len(self.base)
 
 
 class EpochAccumulator:

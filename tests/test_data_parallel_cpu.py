@@ -359,3 +359,78 @@ def test_tail_bucket_is_cut_small():
     assert sync.wire == "fp32"                                    # the bf16 wire is a CUDA / multi-rank option only
     with pytest.raises(ValueError):
         training.GradSync(flat, wire="fp16")
+
+
+class _AggrLikeSampler:
+    """The reference's AggrBatchSampler protocol (datasets.py:620-655): homogeneous batches per group, reshuffled with
+    an UNSEEDED random generator after every pass."""
+
+    def __init__(self, groups, batch_size):
+        self.groups, self.batch_size = groups, batch_size
+        self.batches = self._make()
+
+    def _make(self):
+        import random
+        out = []
+        for idx in self.groups.values():
+            idx = list(idx)
+            random.seed(None)
+            random.shuffle(idx)
+            out += [idx[i:i + self.batch_size] for i in range(0, len(idx), self.batch_size)]
+        random.seed(None)
+        random.shuffle(out)
+        return out
+
+    def __iter__(self):
+        yield from self.batches
+        self.batches = self._make()
+
+    def __len__(self):
+        return len(self.batches)
+
+
+def _sampler_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        groups = {"phys": range(0, 40), "verb": range(40, 103)}
+        sampler = training.ShardedBatchSampler(_AggrLikeSampler(groups, 16))
+        epochs = [[list(b) for b in sampler] for _ in range(2)]
+        q.put((rank, epochs, len(sampler)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_batch_sampler_gives_every_rank_a_slice_of_the_same_homogeneous_batch():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sampler_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict((r, (e, n)) for r, e, n in (q.get(timeout=100) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    (e0, n0), (e1, n1) = got[0], got[1]
+    assert n0 == n1 == len(e0[0]) == len(e1[0])
+    seen = []
+    for ep in range(2):
+        for b0, b1 in zip(e0[ep], e1[ep]):
+            both = b0 + b1
+            assert len(set(both)) == len(both) and 0 < len(both) <= 16 and abs(len(b0) - len(b1)) <= 1
+            assert all(i < 40 for i in both) or all(i >= 40 for i in both)       # one aggression type per global batch
+        seen.append(sorted(i for b in e0[ep] + e1[ep] for i in b))
+        assert seen[-1] == list(range(103))                                       # every sample exactly once per epoch
+    assert e0[0] != e0[1]                                                         # reshuffled between epochs
+
+
+def test_shard_batch_slices_tensors_and_names():
+    from multimodalaggressionrecognition_b200 import workloads as W
+    data, labels = W.batch_c3_mixed(B=6, t_audio=4, t_video=2)
+    parts = [training.shard_batch([data, labels], r, 3) for r in range(3)]
+    for r, (d, l) in enumerate(parts):
+        assert d[0][0] == data[0][0][2 * r:2 * r + 2] and torch.equal(d[1][1], data[1][1][2 * r:2 * r + 2])
+        assert l[1][0] == labels[1][0][2 * r:2 * r + 2] and torch.equal(l[0][1], labels[0][1][2 * r:2 * r + 2])
