@@ -13,7 +13,7 @@ def main():
     ap.add_argument("--shapes", default="qkv,ffn1,ffn2,out")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--mode", default="fwd")
-    ap.add_argument("--epi", default="bias", help="none|bias|full (bias+dropout+residual)")
+    ap.add_argument("--epi", default="bias", help="none|bias|res (bias+residual)|full (bias+dropout+residual)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     st = torch.cuda.current_stream().cuda_stream
@@ -27,7 +27,7 @@ def main():
         wt = w.t().contiguous()
         b = torch.randn(N, device=dev)
         y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        res = torch.randn(M, N, device=dev).bfloat16() if args.epi == "full" else None
+        res = torch.randn(M, N, device=dev).bfloat16() if args.epi in ("full", "res") else None
         dw = torch.empty(N, K, device=dev)
         def run():
             if args.mode == "fwd":
@@ -36,7 +36,7 @@ def main():
                           None if res is None else res.data_ptr(), N, y.data_ptr(), N, M, N, K, 1, 1, flags, p,
                           rng.data_ptr(), 1, 2, st)
             elif args.mode == "dgrad":
-                _lib.call("mar_linear_dgrad", y.data_ptr(), w.data_ptr(), wt.data_ptr(), None, x.data_ptr(), K, M, N, K, 1, 2, st)
+                _lib.call("mar_linear_dgrad", y.data_ptr(), w.data_ptr(), wt.data_ptr(), None, None, 1.0, x.data_ptr(), K, M, N, K, 1, 2, st)
             else:
                 _lib.call("mar_linear_wgrad", y.data_ptr(), x.data_ptr(), K, dw.data_ptr(), M, N, K, 1, 0, 2, st)
         for _ in range(3):
