@@ -26,10 +26,13 @@ __device__ __forceinline__ T* mapped_row(const RowMap& m, T* plain, int64_t row,
   if (m.nseg == 0) return plain + row * D;
   const int64_t b = row / m.Tin;
   const int t = (int)(row - b * m.Tin);
-  int k = 0;
+  // constant indices only (a dynamic index into a by-value kernel parameter puts the struct on the local-memory stack)
+  int t0 = m.t0[0], Tout = m.Tout[0], tout0 = m.tout0[0];
+  void* ptr = m.ptr[0];
 #pragma unroll
-  for (int i = 1; i < 4; i++) if (i < m.nseg && t >= m.t0[i]) k = i;
-  return reinterpret_cast<T*>(m.ptr[k]) + (b * m.Tout[k] + m.tout0[k] + (t - m.t0[k])) * (int64_t)D;
+  for (int i = 1; i < 4; i++)
+    if (i < m.nseg && t >= m.t0[i]) { t0 = m.t0[i]; Tout = m.Tout[i]; tout0 = m.tout0[i]; ptr = m.ptr[i]; }
+  return reinterpret_cast<T*>(ptr) + (b * Tout + tout0 + (t - t0)) * (int64_t)D;
 }
 
 template <typename T, int NCH>
