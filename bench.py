@@ -479,10 +479,12 @@ def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
     achieved = flops / (ms / 1e3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     traffic = None                     # DRAM bytes per launch of this kernel from the committed ncu capture of the same command
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+    for name in ("r02_gemm_dram_traffic.json", "r01_gemm_dram_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+            break
     return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, mean over the step's 49 launches)",
             "launches": len(tc), "gemm_ms_per_step": ms,
