@@ -320,6 +320,10 @@ def run_ours(args):
         r = cpu_clips_per_s(steps=3, warmup=1, budget_s=25.0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
+    torch_b200 = None
+    if world == 1 and not args.no_extras:
+        torch_b200 = torch_on_b200(dev, W, gdata, glabels)
+
     global_batch = B * world
     line = {
         "metric": METRIC, "value": global_batch / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -339,6 +343,7 @@ def run_ours(args):
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "ranks_identical": ranks_identical,
         "other_configs": other,
+        "torch_b200": torch_b200,
         "losses_last_step": loss_vals,
         "flops_per_clip_train": 3 * W.c3_flops_per_clip(T_AUDIO, T_VIDEO)["total"],
         "model_tflops": 3 * W.c3_flops_per_clip(T_AUDIO, T_VIDEO)["total"] * global_batch / (ms_dev / 1e3) / 1e12,
@@ -423,6 +428,59 @@ def other_configs(args, world, rank, dev, timed, M, ops, training, W):
         del st, model
         ops.clear_weight_cache()
         torch.cuda.empty_cache()
+    return out
+
+
+def torch_on_b200(dev, W, data, labels, steps=5):
+    """The survey's kernel bar, in the same run: the UNMODIFIED reference modules
+    (oracle/_ref/models.py) on this B200 under torch eager — every device op a PyTorch library call (cuBLAS, cuDNN /
+    flash SDPA, ATen) — on the same C3 batch: bf16 autocast and fp32 with TF32 off; plus F.scaled_dot_product_attention
+    at the step's two large attention shapes.  tools/ref_on_b200.py has the full table (C2 / cuDNN GRU, C5 lengths)."""
+    import torch.nn.functional as F
+    ref = load_reference_models()
+    out = {"torch": torch.__version__}
+
+    def timeit(fn, n, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    if ref is not None:
+        B = data[0][1].shape[0]
+        for mode in ("bf16_autocast", "fp32"):
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            torch.manual_seed(0)
+            model = W.build_c3(ref, T_AUDIO, T_VIDEO).to(dev).train()
+            crit = ref.MultiModalCrossEntropyLoss({"phys": torch.nn.CrossEntropyLoss(), "verb": torch.nn.CrossEntropyLoss()})
+            opt = torch.optim.Adam(model.parameters())
+
+            def step():
+                opt.zero_grad()
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16_autocast"):
+                    losses = crit(model(data), labels)
+                losses.backward()
+                opt.step()
+            ms = timeit(step, steps if mode == "bf16_autocast" else 3)
+            out[f"c3_step_reference_modules_{mode}"] = {"ms": ms, "clips_per_s": B / ms * 1e3}
+            del model, opt
+            torch.cuda.empty_cache()
+    else:
+        out["c3_step_reference_modules"] = "oracle/_ref/models.py absent (python oracle/build_ref.py in the build container)"
+    for T in (T_AUDIO, T_AUDIO + T_VIDEO):
+        q, k, v = [torch.randn(PER_GPU_BATCH, 8, T, 96, device=dev, dtype=torch.bfloat16, requires_grad=True) for _ in range(3)]
+        go = torch.randn_like(q)
+        with torch.no_grad():
+            f = timeit(lambda: F.scaled_dot_product_attention(q, k, v, dropout_p=0.1), 10)
+        fb = timeit(lambda: F.scaled_dot_product_attention(q, k, v, dropout_p=0.1).backward(go), 10)
+        out[f"sdpa_T{T}_B{PER_GPU_BATCH}_H8_dh96_p0.1"] = {"fwd_ms": f, "bwd_ms": fb - f}
     return out
 
 
