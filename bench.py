@@ -490,7 +490,7 @@ def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
     from multimodalaggressionrecognition_b200 import _lib
     recs = []
     orig = _lib.call
-    gemm_names = {"mar_linear_fwd": (8, 9, 10), "mar_linear_dgrad": (8, 9, 10), "mar_linear_wgrad": (4, 5, 6)}
+    gemm_names = {"mar_linear_fwd": (8, 9, 10), "mar_linear_dgrad": (9, 10, 11), "mar_linear_wgrad": (4, 5, 6)}
 
     def timed_call(name, *a):
         if name in gemm_names:

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MAR_VERSION 100
+#define MAR_VERSION 101
 
 enum { MAR_F32 = 0, MAR_BF16 = 1 };
 
@@ -100,9 +100,13 @@ int mar_linear_bwd_epilogue(const void* dout, const void* out, void* dz, float* 
  * act (M,K) row stride lddx or NULL (not together with add): the forward VALUE of this linear's input when that input
  * came out of a ReLU(+dropout) epilogue — zero exactly where the activation's derivative is zero — so that
  * dx = (dz·W) ⊙ (act > 0 ? act_scale : 0) leaves the GEMM with the producer's activation backward already applied
- * (FFN linear2 → linear1 of transformer.py:980-982: the (M, d_ff) gradient is written once, masked). */
+ * (FFN linear2 → linear1 of transformer.py:980-982: the (M, d_ff) gradient is written once, masked).
+ * dx_colsum (K) fp32 or NULL (needs lddx == K): += column sums of dx — when dx already IS the producer's dz (act given),
+ * that is the producer's bias gradient, taken from the accumulator tiles in the GEMM's own epilogue instead of by a
+ * pass over the (M, d_ff) tensor. */
 int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* add, const void* act, float act_scale,
-                     void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K, int dtype, int engine, void* stream);
+                     void* dx, int64_t lddx, float* dx_colsum, int64_t M, int64_t N, int64_t K, int dtype, int engine,
+                     void* stream);
 
 /* dw (N,K) fp32 (+)= dzᵀ·x.  dz (M,N) contiguous, x (M,K) row stride ldx.  accumulate=0 overwrites. */
 int mar_linear_wgrad(const void* dz, const void* x, int64_t ldx, float* dw, int64_t M, int64_t N,
@@ -132,10 +136,12 @@ int mar_attention_fwd(const void* qkv, const uint8_t* key_mask, void* out, float
 int64_t mar_attention_dropbits_words(int64_t B, int64_t T, int64_t H);
 /* dqkv (B,T,3d) from dout (B,T,d).  work: mar_attention_bwd_work_floats() floats of 16 B-aligned scratch
  * (delta = rowsum(dO ⊙ O) (B,H,T), then the tcgen05 engine's fp32 dQ accumulator (B,T,d) when T > 128).
- * drop_bits: the buffer the forward call filled (NULL when p_drop == 0). */
+ * drop_bits: the buffer the forward call filled (NULL when p_drop == 0).
+ * dqkv_colsum (3d) fp32 or NULL: += column sums of dqkv over all B*T tokens = the gradient of the in-projection bias
+ * (functional.py:5798); the tcgen05 engine takes them from its dK / dV / dQ accumulators before they are written. */
 int64_t mar_attention_bwd_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh);
 int mar_attention_bwd(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout,
-                      const float* lse, float* work, void* dqkv, int64_t B, int64_t T, int64_t H,
+                      const float* lse, float* work, void* dqkv, float* dqkv_colsum, int64_t B, int64_t T, int64_t H,
                       int64_t dh, int dtype, float p_drop, const uint32_t* drop_bits, int engine, void* stream);
 
 /* ---- LayerNorm ------------------------------------------------------------------------------ */
@@ -151,6 +157,15 @@ int mar_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
 int mar_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                       const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t rows,
                       int64_t D, int dtype, void* stream);
+
+/* mar_layernorm_bwd for a LayerNorm whose input was  x = residual + dropout_p(z)  written by mar_linear_fwd with
+ * MAR_EPI_DROPOUT (out_proj -> norm1 and linear2 -> norm2 of the post-norm encoder layer, transformer.py:953-956): besides
+ * dx it writes dz = dx ⊙ keep/(1-p) (rows, D) — the gradient that linear's dgrad / wgrad consume, mask regenerated from
+ * (rng_state, site) exactly as mar_linear_bwd_epilogue would — and accumulates dbias (D fp32, may be NULL) += column
+ * sums of dz: the dropout-backward pass over the tensor is folded into the pass LayerNorm's backward makes anyway. */
+int mar_layernorm_bwd_dropout(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                              void* dx, float* dgamma, float* dbeta, void* dz, float* dbias, int64_t rows, int64_t D,
+                              int dtype, float p_drop, const uint64_t* rng_state, uint32_t site, void* stream);
 
 /* The same two kernels with a ROW MAP on the output (forward: y) / incoming-gradient (backward: dy) side, so that
  * torch.cat along T (models.py:419) and the per-modality slices (models.py:430) cost no copy.  Rows are (b, t) =

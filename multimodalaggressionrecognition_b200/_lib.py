@@ -32,16 +32,17 @@ PROTOTYPES = {
     "mar_linear_fwd": (c_int, [P, c_int64, P, P, P, c_int64, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
                                c_int, c_float, P, c_uint32, c_int, P]),
     "mar_linear_bwd_epilogue": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_float, P, c_uint32, c_int64, P]),
-    "mar_linear_dgrad": (c_int, [P, P, P, P, P, c_float, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P]),
+    "mar_linear_dgrad": (c_int, [P, P, P, P, P, c_float, P, c_int64, P, c_int64, c_int64, c_int64, c_int, c_int, P]),
     "mar_linear_wgrad": (c_int, [P, P, c_int64, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, P]),
     "mar_cast_weight": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
     "mar_cast": (c_int, [P, c_int, P, c_int, c_int64, P]),
     "mar_attention_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, c_uint32, P, c_int, P]),
     "mar_attention_dropbits_words": (c_int64, [c_int64, c_int64, c_int64]),
-    "mar_attention_bwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, c_int, P]),
+    "mar_attention_bwd": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, c_int, P]),
     "mar_attention_bwd_work_floats": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
     "mar_layernorm_fwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_float, c_int, P]),
     "mar_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, P]),
+    "mar_layernorm_bwd_dropout": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_float, P, c_uint32, P]),
     "mar_layernorm_fwd_mapped": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_float, c_int, c_int, c_int64, P, P, P, P, P, P]),
     "mar_layernorm_bwd_mapped": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_int64, P, P, P, P, P, P]),
     "mar_meanpool_fwd": (c_int, [P, P, c_int64, c_int64, c_int64, c_int, P]),

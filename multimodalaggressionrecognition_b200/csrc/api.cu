@@ -105,8 +105,10 @@ int mar_linear_fwd(const void* x, int64_t ldx, const void* w, const float* bias,
 }
 
 int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* add, const void* act, float act_scale,
-                     void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K, int dtype, int engine, void* stream) {
+                     void* dx, int64_t lddx, float* dx_colsum, int64_t M, int64_t N, int64_t K, int dtype, int engine,
+                     void* stream) {
   MAR_CHECK_ARG(dz && (w || wt) && dx, "mar_linear_dgrad: null pointer");
+  MAR_CHECK_ARG(!dx_colsum || lddx == K, "mar_linear_dgrad: dx_colsum needs a contiguous dx");
   MAR_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lddx >= K, "mar_linear_dgrad: bad shape");
   MAR_CHECK_ARG(dtype == MAR_F32 || dtype == MAR_BF16, "mar_linear_dgrad: bad dtype %d", dtype);
   MAR_CHECK_ARG(!(add && act), "mar_linear_dgrad: add and act are mutually exclusive");
@@ -114,6 +116,7 @@ int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* 
   TcGemmArgs a;
   a.A = dz; a.lda = N; a.out = dx; a.ldo = lddx; a.out_fp32 = 0;
   a.M = M; a.N = K; a.Kr = N; a.residual = add; a.ldr = lddx; a.aux = act; a.ldaux = lddx; a.aux_scale = act_scale;
+  a.colsum = dx_colsum;
   // B operand: W itself, (N,K) row-major = MN-major over the reduction dimension N (no transposed copy needed);
   // a caller-provided Wᵀ (K,N) is used as a K-major operand when W is absent (MAR_DGRAD_WT=1 prefers it, for A/B runs)
   if (w != nullptr && !(wt != nullptr && env_flag("MAR_DGRAD_WT"))) { a.B = w; a.ldb = K; a.b_mn_major = 1; }
@@ -121,14 +124,22 @@ int mar_linear_dgrad(const void* dz, const void* w, const void* wt, const void* 
   const bool tc_ok = dtype == MAR_BF16 && a.B != nullptr && gemm_tcgen05_supported(a);
   if (engine == MAR_ENGINE_TCGEN05 && !tc_ok) MAR_UNSUPPORTED("mar_linear_dgrad: tcgen05 engine cannot take M=%lld N=%lld K=%lld (needs bf16)", (long long)M, (long long)N, (long long)K);
   const bool use_tc = engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && tc_ok && M >= 64 && K >= 64 && !env_flag("MAR_FORCE_SIMT"));
-  if (use_tc) return gemm_tcgen05(a, S(stream));
-  if (skinny_supported(N) && w != nullptr && act == nullptr) return skinny_dgrad(dz, w, add, dx, lddx, M, N, K, dtype, S(stream));
-  SimtEpilogue epi;
-  epi.residual = add; epi.ldr = lddx; epi.res_is_bf16 = dtype == MAR_BF16;
-  epi.aux = act; epi.ldaux = lddx; epi.aux_scale = act_scale;
-  if (w != nullptr)   // dx(m,k) = Σ_n dz(m,n) W(n,k):  B(kr=n, col=k) = w[n*K + k]
-    return gemm_simt(dz, dtype, N, 1, w, dtype, K, 1, dx, dtype, lddx, M, K, N, epi, S(stream));
-  return gemm_simt(dz, dtype, N, 1, wt, dtype, 1, N, dx, dtype, lddx, M, K, N, epi, S(stream));
+  if (use_tc) return gemm_tcgen05(a, S(stream));   // column sums leave the GEMM's own epilogue
+  int rc;
+  if (skinny_supported(N) && w != nullptr && act == nullptr) {
+    rc = skinny_dgrad(dz, w, add, dx, lddx, M, N, K, dtype, S(stream));
+  } else {
+    SimtEpilogue epi;
+    epi.residual = add; epi.ldr = lddx; epi.res_is_bf16 = dtype == MAR_BF16;
+    epi.aux = act; epi.ldaux = lddx; epi.aux_scale = act_scale;
+    if (w != nullptr)   // dx(m,k) = Σ_n dz(m,n) W(n,k):  B(kr=n, col=k) = w[n*K + k]
+      rc = gemm_simt(dz, dtype, N, 1, w, dtype, K, 1, dx, dtype, lddx, M, K, N, epi, S(stream));
+    else
+      rc = gemm_simt(dz, dtype, N, 1, wt, dtype, 1, N, dx, dtype, lddx, M, K, N, epi, S(stream));
+  }
+  if (rc == MAR_OK && dx_colsum != nullptr)        // the SIMT engines sum the columns in a pass of their own
+    rc = mar_linear_bwd_epilogue(dx, nullptr, nullptr, dx_colsum, M, K, dtype, dtype, 0, 0.f, nullptr, 0, 0, stream);
+  return rc;
 }
 
 int mar_linear_wgrad(const void* dz, const void* x, int64_t ldx, float* dw, int64_t M, int64_t N, int64_t K, int dtype,
@@ -190,8 +201,8 @@ int64_t mar_attention_dropbits_words(int64_t B, int64_t T, int64_t H) {
 }
 
 int mar_attention_bwd(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
-                      float* delta, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, int dtype, float p_drop,
-                      const uint32_t* drop_bits, int engine, void* stream) {
+                      float* delta, void* dqkv, float* dqkv_colsum, int64_t B, int64_t T, int64_t H, int64_t dh, int dtype,
+                      float p_drop, const uint32_t* drop_bits, int engine, void* stream) {
   MAR_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "mar_attention_bwd: null pointer");
   MAR_CHECK_ARG(B >= 0 && T > 0 && H > 0 && dh > 0, "mar_attention_bwd: bad shape");
   MAR_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "mar_attention_bwd: p_drop out of range");
@@ -201,14 +212,19 @@ int mar_attention_bwd(const void* qkv, const uint8_t* key_mask, const void* out,
   const uint32_t* dbits = p_drop > 0.f ? drop_bits : nullptr;
   const bool mma_ok = attention_mma_supported(T, dh, dtype);
   if (engine == MAR_ENGINE_TCGEN05 && !mma_ok) MAR_UNSUPPORTED("mar_attention_bwd: tensor-core engine cannot take dh=%lld dtype=%d", (long long)dh, dtype);
+  int rc;
   if (engine == MAR_ENGINE_TCGEN05 || (engine == MAR_ENGINE_AUTO && mma_ok && !env_flag("MAR_FORCE_SIMT"))) {
     mar_set_engine(MAR_ENGINE_TCGEN05);
-    if (attention_tc_supported(B, T, H, dh, dtype) && !env_flag("MAR_ATTN_MMA") && !env_flag("MAR_ATTN_BWD_MMA"))
-      return attention_bwd_tc(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p_drop, dbits, S(stream));
-    return attention_bwd_mma(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p_drop, dbits, S(stream));
+    if (attention_tc_supported(B, T, H, dh, dtype) && !env_flag("MAR_ATTN_MMA") && !env_flag("MAR_ATTN_BWD_MMA"))   // sums inside the kernel
+      return attention_bwd_tc(qkv, key_mask, out, dout, lse, delta, dqkv, dqkv_colsum, B, T, H, dh, p_drop, dbits, S(stream));
+    rc = attention_bwd_mma(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, p_drop, dbits, S(stream));
+  } else {
+    mar_set_engine(MAR_ENGINE_SIMT);
+    rc = attention_bwd_simt(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, dtype, p_drop, dbits, S(stream));
   }
-  mar_set_engine(MAR_ENGINE_SIMT);
-  return attention_bwd_simt(qkv, key_mask, out, dout, lse, delta, dqkv, B, T, H, dh, dtype, p_drop, dbits, S(stream));
+  if (rc == MAR_OK && dqkv_colsum != nullptr)     // the other engines sum dqkv's columns in a pass of their own
+    rc = mar_linear_bwd_epilogue(dqkv, nullptr, nullptr, dqkv_colsum, B * T, 3 * H * dh, dtype, dtype, 0, 0.f, nullptr, 0, 0, stream);
+  return rc;
 }
 
 int64_t mar_attention_bwd_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh) {

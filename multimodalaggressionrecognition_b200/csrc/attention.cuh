@@ -25,9 +25,10 @@ int attention_fwd_tc2(const void* qkv, const uint8_t* key_mask, void* out, float
                       int64_t dh, float p, const uint32_t* dbits, cudaStream_t st);
 // backward: `work` holds attention_bwd_tc_work_floats() floats (delta, then the fp32 dQ accumulator when T > 128)
 int64_t attention_bwd_tc_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh);
+// dbias (3d fp32, or nullptr): += column sums of dqkv over all tokens, taken inside the kernel
 int attention_bwd_tc(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
-                     float* work, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, float p, const uint32_t* dbits,
-                     cudaStream_t st);
+                     float* work, void* dqkv, float* dbias, int64_t B, int64_t T, int64_t H, int64_t dh, float p,
+                     const uint32_t* dbits, cudaStream_t st);
 
 // dropout keep bits of one attention call (attention_dropbits.cu; layout: common.cuh DropBits)
 int64_t attention_dropbits_words(int64_t B, int64_t T, int64_t H);

@@ -55,6 +55,7 @@ struct BwdParams {
   const float* delta;
   float* dq_acc;      // (B,T,d) fp32, zero-initialised; nullptr when T <= 128 (dQ goes straight to dqkv)
   bf16* dqkv;         // (B,T,3d)
+  float* dbias;       // (3d) fp32 or nullptr: += column sums of dqkv over all tokens (the in-projection's bias gradient)
   int B, T, H;
   float p_drop;
   const uint32_t* dbits;     // dropout keep bits of the forward call (common.cuh DropBits), nullptr when p_drop == 0
@@ -389,6 +390,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
             *reinterpret_cast<uint4*>(o + g * 8) = u;
           }
         }
+        if (p.dbias != nullptr) {
+          // column sums over this warp's 32 key rows, in place in r: butterfly transpose-reduce, lane l ends with column l
+#pragma unroll
+          for (int j = 0; j < 32; j++) r[j] = key < T ? __float_as_uint(__uint_as_float(r[j]) * sc) : 0u;
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; j++) {
+              const uint32_t send = upper ? r[j] : r[j + off];
+              const uint32_t keep = upper ? r[j + off] : r[j];
+              r[j] = __float_as_uint(__uint_as_float(keep) + __uint_as_float(__shfl_xor_sync(0xffffffffu, send, off)));
+            }
+          }
+          if (chunk * 32 + lane < DH) atomicAdd(p.dbias + (which == 0 ? d : 2 * d) + h * DH + chunk * 32 + lane, __uint_as_float(r[0]));
+        }
       }
     }
   } else {
@@ -398,6 +415,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float scale = rsqrtf((float)DH);
     const bool live = quarter * 32 < DH;                // warp-uniform
+    float qsum = 0.f;                                   // this key tile's share of Σ_q dQ[q, c] (the in-projection's bias gradient)
     for (int i = 0; i < n_q; i++) {
       const int nq = min(BQ, T - q_tile(i) * BQ);
       uint32_t r0[32], r1[32];
@@ -411,6 +429,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dqr);      // the MMA issuer may overwrite dQᵀ while we drain the registers
+      if (p.dbias != nullptr && live) {
+        if (nq == BQ) {                           // warp-uniform: only the last query tile of a sequence is ragged
+#pragma unroll
+          for (int j = 0; j < 32; j++) qsum += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            if (j < nq) qsum += __uint_as_float(r0[j]);
+            if (32 + j < nq) qsum += __uint_as_float(r1[j]);
+          }
+        }
+      }
       if (p.dq_acc != nullptr) {
         // dQ block -> fp32 staging [q][dh] in shared memory -> ONE TMA reduce-add per DQ_ROWS query rows (the L2 does the
         // adds; scalar red.global.add ran at about one element per clock per SM and paced the whole kernel)
@@ -444,6 +474,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
           if (32 + j < nq) dst[(int64_t)(32 + j) * 3 * d] = __float2bfloat16_rn(__uint_as_float(r1[j]) * scale);
       }
     }
+    if (p.dbias != nullptr && live && c < DH) atomicAdd(p.dbias + h * DH + c, qsum * scale);
     if (warp == 2 + NCOMPUTE && lane == 0) tma_store_wait_all();      // every reduce has landed before the CTA retires
   }
 
@@ -504,7 +535,7 @@ attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, i
 
 template <int DH, bool DROP>
 int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
-               void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint32_t* dbits, cudaStream_t st) {
+               void* dqkv, float* dbias, int64_t B, int64_t T, int64_t H, float p, const uint32_t* dbits, cudaStream_t st) {
   constexpr int NBOX = (DH + 63) / 64;
   constexpr int USED = 2 * NBOX * BOX_BYTES + 2 * QSTAGES * NBOX * QBOX_BYTES + 2 * BT * 128 + (DH <= 96 ? 32 : 16) * DH * 4 +
                        2 * LSTAGES * BQ * 4 + LSTAGES * 4 * BQ * 4 + 20 * 8 + 16;
@@ -540,7 +571,7 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
     tm_dq = tm_do;            // unused by the kernel when T <= 128
   }
   BwdParams prm;
-  prm.key_mask = key_mask; prm.lse = lse; prm.delta = delta; prm.dq_acc = dq_acc; prm.dqkv = (bf16*)dqkv;
+  prm.key_mask = key_mask; prm.lse = lse; prm.delta = delta; prm.dq_acc = dq_acc; prm.dqkv = (bf16*)dqkv; prm.dbias = dbias;
   prm.B = (int)B; prm.T = (int)T; prm.H = (int)H; prm.p_drop = p; prm.dbits = dbits; prm.smem_bytes = SMEM;
   const int64_t n_t = ceil_div(T, BT);
   attn_bwd_tc_kernel<DH, DROP><<<(unsigned)(B * H * n_t), NTHREADS, SMEM, st>>>(tm_kv, tm_q, tm_do, tm_dq, prm);
@@ -556,9 +587,9 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
 
 template <int DH>
 int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
-               void* dqkv, int64_t B, int64_t T, int64_t H, float p, const uint32_t* dbits, cudaStream_t st) {
-  if (p <= 0.f) return bwd_launch_t<DH, false>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
-  return bwd_launch_t<DH, true>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
+               void* dqkv, float* dbias, int64_t B, int64_t T, int64_t H, float p, const uint32_t* dbits, cudaStream_t st) {
+  if (p <= 0.f) return bwd_launch_t<DH, false>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
+  return bwd_launch_t<DH, true>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
 }
 
 }  // namespace
@@ -568,16 +599,16 @@ int64_t attention_bwd_tc_work_floats(int64_t B, int64_t T, int64_t H, int64_t dh
 }
 
 int attention_bwd_tc(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse,
-                     float* work, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t dh, float p, const uint32_t* dbits,
-                     cudaStream_t st) {
+                     float* work, void* dqkv, float* dbias, int64_t B, int64_t T, int64_t H, int64_t dh, float p,
+                     const uint32_t* dbits, cudaStream_t st) {
   MAR_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)dout % 16 == 0) &&
                     ((uintptr_t)dqkv % 16 == 0) && ((uintptr_t)work % 16 == 0) && ((uintptr_t)dbits % 16 == 0),
                 "attention: pointers must be 16 B aligned");
   MAR_CHECK_ARG(p == 0.f || dbits, "attention: dropout needs the keep-bit buffer of the forward call");
   switch (dh) {
-    case 64: return bwd_launch<64>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
-    case 96: return bwd_launch<96>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
-    case 128: return bwd_launch<128>(qkv, key_mask, out, dout, lse, work, dqkv, B, T, H, p, dbits, st);
+    case 64: return bwd_launch<64>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
+    case 96: return bwd_launch<96>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
+    case 128: return bwd_launch<128>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
   }
   MAR_UNSUPPORTED("attention backward (tcgen05 engine): head dim %lld", (long long)dh);
 }

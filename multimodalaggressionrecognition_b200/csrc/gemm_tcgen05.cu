@@ -59,6 +59,7 @@ struct TcParams {
   float p_drop;
   const uint64_t* rng;
   uint32_t site;
+  float* colsum;          // bf16 out: colsum[n] += Σ_m result[m,n] (fp32; the bias gradient of the layer that produced A's gradient)
   int atomic_out;         // fp32 out via red.add (split-K)
   int accumulate;         // fp32 out += (no split)
 };
@@ -302,6 +303,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               }
             }
           }
+          if (p.colsum != nullptr) {
+            // column sums of this warp's 32 x 32 block: butterfly transpose-reduce (31 shuffles), after which lane l
+            // holds the sum of column l over the 32 rows; one 128 B red.add per block
+            float s[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) s[j] = row < p.M ? v[j] : 0.f;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int j = 0; j < off; j++) {
+                const float send = upper ? s[j] : s[j + off];
+                const float keep = upper ? s[j + off] : s[j];
+                s[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, s[0]);
+          }
 #pragma unroll
           for (int g = 0; g < 4; g++) {
             uint4 u;
@@ -436,7 +455,7 @@ bool gemm_tcgen05_supported(const TcGemmArgs& a) {
   if (a.residual != nullptr && (!al16(a.residual) || (a.ldr * 2) % 16 != 0)) return false;
   if (a.aux != nullptr && (!al16(a.aux) || (a.ldaux * 2) % 16 != 0)) return false;
   if (a.aux != nullptr && a.residual != nullptr) return false;   // one staged input per launch
-  if ((a.aux != nullptr || a.residual != nullptr) && a.out_fp32) return false;
+  if ((a.aux != nullptr || a.residual != nullptr || a.colsum != nullptr) && a.out_fp32) return false;
   const int64_t osz = a.out_fp32 ? 4 : 2;
   if ((a.ldo * osz) % 16 != 0) return false;
   // TN (forward, dgrad on a transposed weight copy), NT-on-rows (wgrad, fp32 out) and dgrad on the weight itself
@@ -458,6 +477,7 @@ int gemm_tcgen05(const TcGemmArgs& a, cudaStream_t st) {
   p.aux_scale = a.aux_scale;
   p.flags = a.flags; p.p_drop = a.p_drop; p.rng = a.rng; p.site = a.site;
   p.atomic_out = 0; p.accumulate = a.accumulate;
+  p.colsum = a.out_fp32 ? nullptr : a.colsum;
   const int BN = (a.N > 128) ? 256 : 128;
   const int64_t m_blocks = ceil_div(a.M, BLOCK_M);
   // cluster of 2 when there are at least two M-blocks to pair (MAR_TC_CLUSTER=1 disables, for A/B measurements)

@@ -18,6 +18,7 @@ struct TcGemmArgs {
   const void* aux = nullptr;       // bf16 (M,N), ldaux: result *= (aux > 0 ? aux_scale : 0)  (activation backward)
   int64_t ldaux = 0;
   float aux_scale = 1.f;
+  float* colsum = nullptr;         // fp32 (N): += column sums of the bf16 result (after the whole epilogue)
   int flags = 0;
   float p_drop = 0.f;
   const uint64_t* rng = nullptr;

@@ -113,16 +113,42 @@ template <> struct Raw8<float> {
   }
 };
 
-template <typename T, int NCH>
+// DROP: x is the output of a linear whose epilogue was  x = residual + dropout(z)  (out_proj / linear2 of the encoder
+// layer, transformer.py:953-956): the kernel ALSO writes dz = dx ⊙ keep / (1 - p) — the gradient that linear's dgrad and
+// wgrad GEMMs consume — and accumulates that linear's bias gradient (column sums of dz), so the separate dropout-backward
+// pass over the tensor (one read + one write) disappears.  The mask is regenerated from (rng, site, element index) like
+// everywhere else (common.cuh).  dz's column sums live in per-warp shared-memory rows (a lane owns its columns: plain
+// read-modify-write, no atomics) — a third set of register accumulators would cost the second resident block.
+struct LnDrop {
+  void* dz;
+  float* dbias;
+  const uint64_t* rng;
+  uint32_t site;
+  float p;
+};
+
+template <typename T, int NCH, bool DROP>
 __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int D, const RowMap map) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int D, const RowMap map,
+                     const LnDrop drp) {
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
   const int warps_per_block = blockDim.x / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + warp;
   const int64_t warp_stride = (int64_t)gridDim.x * warps_per_block;
   const float invD = 1.f / (float)D;
+  extern __shared__ __align__(16) float red[];  // [warps][D] reused for dgamma then dbeta ; DROP: + [warps][NCH][2][32] float4 of dz sums
+  float4* zacc = reinterpret_cast<float4*>(red + warps_per_block * D) + warp * NCH * 64;
+  DropKey dk;
+  T* dzp = nullptr;
+  [[maybe_unused]] const bool idx32 = ((uint64_t)rows * (uint64_t)D >> 1) < 0xffffffffull;   // every pair index fits 32 bits
+  if (DROP) {
+    dk = make_drop_key(drp.rng, drp.site, drp.p);
+    dzp = reinterpret_cast<T*>(drp.dz);
+#pragma unroll
+    for (int i = 0; i < NCH * 2; i++) zacc[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 
   float dg[NCH][8], db[NCH][8];
 #pragma unroll
@@ -176,7 +202,6 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
   }
 
   // block reduction of the column partials: 8 warps -> 1, then one vector atomicAdd per 4 columns per block
-  extern __shared__ float red[];  // [warps][D] reused for dgamma then dbeta
   for (int pass = 0; pass < 2; pass++) {
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
@@ -196,6 +221,18 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
       atomicAdd(reinterpret_cast<float4*>((pass == 0 ? dgamma : dbeta) + col), s);
     }
     __syncthreads();
+  }
+  if (DROP && drp.dbias != nullptr) {                                     // (the loop above ended with a __syncthreads)
+    const float4* zall = reinterpret_cast<const float4*>(red + warps_per_block * D);
+    for (int col = threadIdx.x * 4; col < D; col += blockDim.x * 4) {
+      const int c = col / 256, l = (col % 256) / 8, half = (col % 8) / 4;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int w = 0; w < warps_per_block; w++) {
+        const float4 t = zall[w * NCH * 64 + (c * 2 + half) * 32 + l];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      atomicAdd(reinterpret_cast<float4*>(drp.dbias + col), s);
+    }
   }
 }
 
@@ -227,23 +264,25 @@ int launch_fwd(const void* x, const float* gamma, const float* beta, void* y, fl
 
 template <typename T>
 int launch_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
-               float* dgamma, float* dbeta, int64_t rows, int64_t D, const RowMap& map, cudaStream_t st) {
+               float* dgamma, float* dbeta, int64_t rows, int64_t D, const RowMap& map, const LnDrop& drp, cudaStream_t st) {
   const int nch = (int)ceil_div(D, 256);
   int64_t blocks = ceil_div(rows, 8 * 4);
   int64_t cap = (int64_t)mar_sm_count() * 2;    // one resident wave (2 blocks/SM): the column partials end in one atomic per block
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  size_t smem = (size_t)8 * D * sizeof(float);
-#define LN_BWD(N)                                                                                                 \
+  const bool drop = drp.dz != nullptr;
+  size_t smem = (size_t)8 * D * sizeof(float) + (drop ? (size_t)8 * nch * 64 * sizeof(float4) : 0);
+#define LN_BWD_T(N, DR)                                                                                           \
   do {                                                                                                            \
     static bool cfg = false;                                                                                      \
     if (smem > 48 * 1024 && !cfg) {                                                                               \
-      cudaFuncSetAttribute(layernorm_bwd_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);   \
+      cudaFuncSetAttribute(layernorm_bwd_kernel<T, N, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (N * 256) * 4 * 2); \
       cfg = true;                                                                                                 \
     }                                                                                                             \
-    layernorm_bwd_kernel<T, N><<<(unsigned)blocks, 256, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, \
-                                                                    (T*)dx, dgamma, dbeta, rows, (int)D, map);    \
+    layernorm_bwd_kernel<T, N, DR><<<(unsigned)blocks, 256, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, \
+                                                                        (T*)dx, dgamma, dbeta, rows, (int)D, map, drp); \
   } while (0)
+#define LN_BWD(N) do { if (drop) LN_BWD_T(N, true); else LN_BWD_T(N, false); } while (0)
   switch (nch) {
     case 1: LN_BWD(1); break;
     case 2: LN_BWD(2); break;
@@ -256,6 +295,7 @@ int launch_bwd(const void* dy, const void* x, const float* mean, const float* rs
     default: MAR_UNSUPPORTED("layernorm: D=%lld > 2048 not supported", (long long)D);
   }
 #undef LN_BWD
+#undef LN_BWD_T
   MAR_LAUNCH_CHECK("layernorm_bwd");
   return MAR_OK;
 }
@@ -328,9 +368,27 @@ int mar_layernorm_bwd_mapped(const void* dy, const void* x, const float* mean, c
   RowMap map;
   int rc = make_row_map(&map, rows, nseg, Tin, t0, t1, Tout, tout0, dy_ptrs, "mar_layernorm_bwd_mapped");
   if (rc) return rc;
-  if (dtype == MAR_BF16) return launch_bwd<bf16>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, map, S(stream));
-  if (dtype == MAR_F32) return launch_bwd<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, map, S(stream));
+  LnDrop drp = {nullptr, nullptr, nullptr, 0u, 0.f};
+  if (dtype == MAR_BF16) return launch_bwd<bf16>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, map, drp, S(stream));
+  if (dtype == MAR_F32) return launch_bwd<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, map, drp, S(stream));
   MAR_UNSUPPORTED("mar_layernorm_bwd: dtype %d", dtype);
+}
+
+int mar_layernorm_bwd_dropout(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                              void* dx, float* dgamma, float* dbeta, void* dz, float* dbias, int64_t rows, int64_t D,
+                              int dtype, float p_drop, const uint64_t* rng_state, uint32_t site, void* stream) {
+  MAR_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && dz && rows >= 0 && D > 0,
+                "mar_layernorm_bwd_dropout: bad arguments");
+  MAR_CHECK_ARG(D % 8 == 0, "mar_layernorm_bwd_dropout: D must be a multiple of 8 (got %lld)", (long long)D);
+  MAR_CHECK_ARG(p_drop > 0.f && p_drop < 1.f && rng_state, "mar_layernorm_bwd_dropout: needs 0 < p_drop < 1 and rng_state");
+  MAR_CHECK_ARG(((uintptr_t)dz % 16) == 0 && ((uintptr_t)dbias % 16) == 0, "mar_layernorm_bwd_dropout: dz / dbias must be 16 B aligned");
+  if (rows == 0) return MAR_OK;
+  RowMap map;
+  map.nseg = 0; map.Tin = 1;
+  LnDrop drp = {dz, dbias, rng_state, site, p_drop};
+  if (dtype == MAR_BF16) return launch_bwd<bf16>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, map, drp, S(stream));
+  if (dtype == MAR_F32) return launch_bwd<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, D, map, drp, S(stream));
+  MAR_UNSUPPORTED("mar_layernorm_bwd_dropout: dtype %d", dtype);
 }
 
 }  // extern "C"

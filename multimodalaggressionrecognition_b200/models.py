@@ -96,19 +96,24 @@ def encoder_layer_forward(layer: nn.TransformerEncoderLayer, h: torch.Tensor, B:
     d = h.shape[-1]
     # fork=True: the residual branch takes h / x1 from the projection op, so in backward the residual gradient is
     # added inside that projection's dgrad GEMM epilogue instead of by a separate elementwise pass
-    qkv, h_res = ops.linear(h, sa.in_proj_weight, sa.in_proj_bias, fork=True)
-    o = ops.attention(qkv.view(B, T, 3 * d), key_mask, sa.num_heads, sa.dropout if train else 0.0)
+    # hand-offs (ops.new_handoff): each linear's dropout backward / bias-gradient sum is done by the neighbour that
+    # touches the same tensor in backward anyway (norm1 / norm2, the attention kernel, linear2's dgrad GEMM), so no
+    # separate pass over a (B*T, ·) gradient is launched for them
+    h_in, h_out, h_l1, h_l2 = (ops.new_handoff() for _ in range(4))
+    qkv, h_res = ops.linear(h, sa.in_proj_weight, sa.in_proj_bias, fork=True, handoff=h_in)
+    o = ops.attention(qkv.view(B, T, 3 * d), key_mask, sa.num_heads, sa.dropout if train else 0.0, qkv_handoff=h_in)
     pre1 = ops.linear(o.view(B * T, d), sa.out_proj.weight, sa.out_proj.bias, residual=h_res,
-                      dropout_p=layer.dropout1.p if train else 0.0)
-    x1 = ops.layer_norm(pre1, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+                      dropout_p=layer.dropout1.p if train else 0.0, handoff=h_out)
+    x1 = ops.layer_norm(pre1, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, x_handoff=h_out)
     # linear1's ReLU+dropout backward is applied inside linear2's dgrad GEMM (hid is zero exactly where that derivative
     # is zero): the (B*T, d_ff) gradient is written once, already masked, and linear1 only sums its bias gradient
     p_ff = float(layer.dropout.p) if train else 0.0
     hid, x1_res = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu_pre=True, dropout_p=p_ff, fork=True,
-                             defer_act=True)
+                             defer_act=True, handoff=h_l1)
     pre2 = ops.linear(hid, layer.linear2.weight, layer.linear2.bias, residual=x1_res,
-                      dropout_p=layer.dropout2.p if train else 0.0, x_act_scale=1.0 / (1.0 - p_ff))
-    return ops.layer_norm(pre2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
+                      dropout_p=layer.dropout2.p if train else 0.0, x_act_scale=1.0 / (1.0 - p_ff), handoff=h_l2,
+                      x_handoff=h_l1)
+    return ops.layer_norm(pre2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, x_handoff=h_l2)
 
 
 def _left_aligned(key_mask: torch.Tensor) -> bool:

@@ -313,12 +313,56 @@ def _sunk(param) -> None:
 
 
 # --------------------------------------------------------------------------------------
+# backward hand-offs between neighbouring ops of an encoder sub-layer.  A linear may be given a `handoff` dict (one per
+# forward call).  Its NEIGHBOURS in the backward chain then do parts of its backward inside passes they make anyway:
+#   * the LayerNorm that consumes  residual + dropout(linear)  writes the linear's dz (dropout backward) next to its own
+#     dx and sums the linear's bias gradient (mar_layernorm_bwd_dropout);
+#   * the linear that consumes a deferred ReLU(+dropout) output sums the producer's bias gradient in its dgrad GEMM
+#     epilogue (dx_colsum of mar_linear_dgrad);
+#   * the attention op sums the in-projection's bias gradient where dQ / dK / dV leave TMEM (dqkv_colsum).
+# The neighbour's backward runs first (it produces the linear's incoming gradient), leaves its results in the dict, and
+# the linear's own backward picks them up instead of launching mar_linear_bwd_epilogue.  Only valid when the linear's
+# output has exactly ONE consumer (true inside models.encoder_layer_forward, the only place that passes a handoff).
+# --------------------------------------------------------------------------------------
+_handoff_cfg = {"on": _os.environ.get("MAR_HANDOFF", "1") != "0"}      # MAR_HANDOFF=0: the separate passes (A/B runs)
+
+
+@contextlib.contextmanager
+def handoffs(enabled: bool):
+    """Switch the backward hand-offs off (every linear launches its own epilogue-backward pass) — tests and A/B runs."""
+    old = _handoff_cfg["on"]
+    _handoff_cfg["on"] = bool(enabled)
+    try:
+        yield
+    finally:
+        _handoff_cfg["on"] = old
+
+
+def new_handoff() -> Optional[dict]:
+    return {} if (_handoff_cfg["on"] and torch.is_grad_enabled()) else None
+
+
+def _handoff_bias_target(h: Optional[dict], n: int, device) -> Optional[torch.Tensor]:
+    """fp32 (n) buffer a neighbour accumulates the linear's bias gradient into (the flat-buffer .grad view inside a
+    TrainStep, else fresh zeros), or None when the bias needs no gradient / there is no hand-off."""
+    if h is None or h.get("bias_done"):
+        return None
+    bias = h.get("bias")
+    if bias is None or not bias.requires_grad or bias.numel() != n:
+        return None
+    sunk = _sink_target(bias, "b")
+    tgt = sunk if sunk is not None else torch.zeros(n, dtype=torch.float32, device=device)
+    h["bias_done"], h["dbias"], h["sunk"] = True, tgt, sunk is not None
+    return tgt
+
+
+# --------------------------------------------------------------------------------------
 # linear (+ fused epilogue)
 # --------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, flags, p, out_dtype, need_dx, fork=False, x_act_scale=None,
-                defer_act=False, pool_T=0):
+                defer_act=False, pool_T=0, handoff=None, x_handoff=None):
         # x (M,K) compute dtype; weight (N,K) fp32 master; bias (N) fp32; residual (M,N) compute dtype
         # fork: also return x itself as a second output.  A consumer that uses x twice (the projection and the
         # residual branch of an encoder sub-layer) takes the residual from that output, so its gradient arrives
@@ -361,6 +405,11 @@ class _Linear(torch.autograd.Function):
         ctx.save_for_backward(x, out if need_out else None)
         ctx.fork = bool(fork)
         ctx.weight_ref, ctx.bias_ref = weight, bias
+        ctx.handoff, ctx.x_handoff = handoff, x_handoff
+        if handoff is not None:
+            handoff["bias"] = bias if isinstance(bias, torch.nn.Parameter) else None
+            if flags == EPI_DROPOUT and residual is not None and not pool_T and out_dtype == x.dtype:
+                handoff["drop"] = (rng, site, float(p))          # what the consuming LayerNorm needs to regenerate the mask
         if pool_T:
             pooled = torch.empty((M // pool_T, N), dtype=out_dtype, device=x.device)
             call("mar_meanpool_fwd", out.data_ptr(), pooled.data_ptr(), M // pool_T, pool_T, N, _dt(out), _stream())
@@ -381,17 +430,34 @@ class _Linear(torch.autograd.Function):
         dout = dout.contiguous()
         needs_x, needs_w, needs_b, needs_r = ctx.needs_input_grad[0:4]
         dbias = sunk_b = None
-        if ctx.has_bias and needs_b:
+        h = ctx.handoff
+        pre_dz = None
+        bias_done = False
+        if h is not None:
+            pre_dz = h.pop("dz", None)
+            if pre_dz is not None and (h.pop("dx_ptr", None) != dout.data_ptr() or tuple(pre_dz.shape) != (M, N)):
+                raise RuntimeError("linear: the LayerNorm that took over this linear's dropout backward is not the only "
+                                   "consumer of its output (hand-offs need a single consumer)")
+            if h.pop("bias_done", False):                 # a neighbour's kernel already accumulated the bias gradient
+                bias_done = True
+                dbias = h.pop("dbias")
+                sunk_b = dbias if h.pop("sunk") else None
+        if ctx.has_bias and needs_b and not bias_done:
             sunk_b = _sink_target(ctx.bias_ref, "b")
             dbias = sunk_b if sunk_b is not None else torch.zeros(N, dtype=torch.float32, device=x.device)
         flags = 0 if ctx.defer_act else ctx.flags        # deferred: the consumer's dgrad GEMM already applied this mask
-        if flags != 0 or ctx.pool_T:
+        if pre_dz is not None:
+            dz = pre_dz                                   # written by mar_layernorm_bwd_dropout next to dout
+            if dbias is not None and not bias_done:
+                call("mar_linear_bwd_epilogue", dz.data_ptr(), None, None, dbias.data_ptr(), M, N, _dt(dz), _dt(dz), 0, 0.0,
+                     None, 0, 0, st)
+        elif flags != 0 or ctx.pool_T:
             dz = torch.empty((M, N), dtype=cd, device=x.device)
             call("mar_linear_bwd_epilogue", dout.data_ptr(), _p(out), dz.data_ptr(), _p(dbias), M, N, _dt(dout),
                  _dt(out) if out is not None else _dt(dout), flags, ctx.p, _p(ctx.rng), ctx.site, ctx.pool_T, st)
         else:
             dz = dout
-            if dbias is not None:
+            if dbias is not None and not bias_done:
                 call("mar_linear_bwd_epilogue", dout.data_ptr(), None, None, dbias.data_ptr(), M, N, _dt(dout),
                      _dt(dout), 0, 0.0, None, 0, 0, st)
         dx = dw = None
@@ -404,8 +470,10 @@ class _Linear(torch.autograd.Function):
             act = x if ctx.x_act_scale is not None else None
             if act is not None and add is not None:
                 raise RuntimeError("linear: x_act_scale cannot be combined with fork (one staged epilogue input per GEMM)")
+            # dx is already the producer's dz when its activation backward is applied here: sum its bias gradient too
+            colsum = _handoff_bias_target(ctx.x_handoff, K, x.device) if act is not None else None
             call("mar_linear_dgrad", dz.data_ptr(), ctx.wc.data_ptr(), _p(ctx.wt), _p(add), _p(act),
-                 float(ctx.x_act_scale or 1.0), dx.data_ptr(), K, M, N, K, _dt(dz), ctx.eng, st)
+                 float(ctx.x_act_scale or 1.0), dx.data_ptr(), K, _p(colsum), M, N, K, _dt(dz), ctx.eng, st)
         if needs_w:
             sunk_w = _sink_target(ctx.weight_ref)
             if sunk_w is not None and tuple(sunk_w.shape) == ctx.w_shape:
@@ -420,20 +488,23 @@ class _Linear(torch.autograd.Function):
             dbias = None
             _sunk(ctx.bias_ref)
         dres = dout if (ctx.has_res and needs_r) else None
-        return dx, dw, dbias, dres, None, None, None, None, None, None, None, None
+        return dx, dw, dbias, dres, None, None, None, None, None, None, None, None, None, None
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, relu_pre: bool = False, dropout_p: float = 0.0,
            relu_post: bool = False, out_dtype: Optional[torch.dtype] = None, fork: bool = False,
-           x_act_scale: Optional[float] = None, defer_act: bool = False, pool_T: int = 0):
+           x_act_scale: Optional[float] = None, defer_act: bool = False, pool_T: int = 0,
+           handoff: Optional[dict] = None, x_handoff: Optional[dict] = None):
     """out = residual + relu_post(dropout(relu_pre(x·Wᵀ + b))) on the last dim of x.
     fork=True returns (out, x_fork): use x_fork wherever x is needed again (a residual branch) and its gradient is
     folded into this linear's dgrad GEMM instead of a separate elementwise add.
     defer_act / x_act_scale (a pair): a ReLU(+dropout) producer called with defer_act=True leaves its activation
     backward to its ONLY consumer, a linear called with x_act_scale = the producer's dropout scale 1/(1-p) (1.0
     without dropout): the consumer's dgrad GEMM writes the gradient already masked (zero where x is zero).
-    pool_T > 0 (x must be (B, pool_T, K)): returns mean over the pool_T rows of every group, (B, N)."""
+    pool_T > 0 (x must be (B, pool_T, K)): returns mean over the pool_T rows of every group, (B, N).
+    handoff / x_handoff: see new_handoff() — this linear's own hand-off dict, and the one of the linear that produced x
+    (with x_act_scale: its bias gradient is summed in this linear's dgrad epilogue)."""
     shape = x.shape
     x2 = _rows(to_compute(x))
     r2 = None
@@ -449,13 +520,13 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         if fork or residual is not None or x.dim() != 3 or x.shape[1] != pool_T:
             raise ValueError("pool_T needs x of shape (B, pool_T, K), no fork and no residual")
         return _Linear.apply(x2, weight, bias, None, flags, float(dropout_p), out_dtype or x2.dtype, need_dx, False,
-                             x_act_scale, defer_act, int(pool_T))
+                             x_act_scale, defer_act, int(pool_T), None, None)
     if fork and need_dx:
         out, xf = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype, need_dx, True,
-                                x_act_scale, defer_act, 0)
+                                x_act_scale, defer_act, 0, handoff, x_handoff)
         return out.view(*shape[:-1], weight.shape[0]), xf.view(shape)
     out = _Linear.apply(x2, weight, bias, r2, flags, float(dropout_p), out_dtype or x2.dtype, need_dx, False,
-                        x_act_scale, defer_act, 0)
+                        x_act_scale, defer_act, 0, handoff, x_handoff)
     out = out.view(*shape[:-1], weight.shape[0])
     return (out, x2.view(shape)) if fork else out
 
@@ -465,7 +536,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
 # --------------------------------------------------------------------------------------
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, key_mask, H, p):
+    def forward(ctx, qkv, key_mask, H, p, qkv_handoff=None):
         B, T, d3 = qkv.shape
         d = d3 // 3
         dh = d // H
@@ -481,6 +552,7 @@ class _Attention(torch.autograd.Function):
              float(p), _p(rng), site, _p(bits), _eng(), _stream())
         ctx.dims = (B, T, H, dh)
         ctx.p, ctx.eng = float(p), _eng()
+        ctx.qkv_handoff = qkv_handoff
         ctx.save_for_backward(qkv, out, lse, key_mask, bits)
         return out
 
@@ -494,19 +566,23 @@ class _Attention(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         nwork = int(_lib.load().mar_attention_bwd_work_floats(B, T, H, dh))
         work = torch.empty(nwork, dtype=torch.float32, device=qkv.device)
+        # the in-projection's bias gradient = column sums of dqkv: taken where dQ / dK / dV leave the kernel
+        colsum = _handoff_bias_target(ctx.qkv_handoff, 3 * H * dh, qkv.device)
         call("mar_attention_bwd", qkv.data_ptr(), _p(key_mask), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-             work.data_ptr(), dqkv.data_ptr(), B, T, H, dh, _dt(qkv), ctx.p, _p(bits), ctx.eng, _stream())
-        return dqkv, None, None, None
+             work.data_ptr(), dqkv.data_ptr(), _p(colsum), B, T, H, dh, _dt(qkv), ctx.p, _p(bits), ctx.eng, _stream())
+        return dqkv, None, None, None, None
 
 
-def attention(qkv: torch.Tensor, key_mask: Optional[torch.Tensor], num_heads: int, dropout_p: float) -> torch.Tensor:
-    """qkv (B,T,3d) packed in-projection output → (B,T,d).  key_mask (B,T) uint8/bool, 1 = ignore key."""
+def attention(qkv: torch.Tensor, key_mask: Optional[torch.Tensor], num_heads: int, dropout_p: float,
+              qkv_handoff: Optional[dict] = None) -> torch.Tensor:
+    """qkv (B,T,3d) packed in-projection output → (B,T,d).  key_mask (B,T) uint8/bool, 1 = ignore key.
+    qkv_handoff: the hand-off dict of the linear that produced qkv (its bias gradient is summed in the backward kernel)."""
     qkv = to_compute(qkv)
     if key_mask is not None:
         if key_mask.dtype == torch.bool:
             key_mask = key_mask.view(torch.uint8) if key_mask.is_contiguous() else key_mask.contiguous().view(torch.uint8)
         key_mask = key_mask.contiguous()
-    return _Attention.apply(qkv, key_mask, int(num_heads), float(dropout_p))
+    return _Attention.apply(qkv, key_mask, int(num_heads), float(dropout_p), qkv_handoff)
 
 
 # --------------------------------------------------------------------------------------
@@ -538,9 +614,13 @@ class _LayerNorm(torch.autograd.Function):
     every modality's slice (models.py:430) itself.  Backward reads the incoming gradient(s) through the same row map."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, zero_rows, need_grad, gamma_ref=None, beta_ref=None, place=None, split=None):
+    def forward(ctx, x, gamma, beta, eps, zero_rows, need_grad, gamma_ref=None, beta_ref=None, place=None, split=None,
+                x_handoff=None):
         rows, D = x.shape
         ctx.gamma_ref, ctx.beta_ref = gamma_ref, beta_ref
+        # x = residual + dropout(linear): this op's backward also writes that linear's dz and sums its bias gradient
+        ctx.x_handoff = x_handoff if (x_handoff is not None and x_handoff.get("drop") is not None and need_grad
+                                      and place is None and split is None) else None
         if zero_rows is not None and need_grad:
             raise RuntimeError("layer_norm(zero_rows=...) is the eval-only nested-tensor zero fill; no backward")
         mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need_grad else None
@@ -600,7 +680,16 @@ class _LayerNorm(torch.autograd.Function):
         sunk = sg is not None and sb is not None
         dgamma = sg if sunk else torch.zeros(D, dtype=torch.float32, device=x.device)
         dbeta = sb if sunk else torch.zeros(D, dtype=torch.float32, device=x.device)
-        if segs is None:
+        h = ctx.x_handoff
+        if segs is None and h is not None:
+            rng, site, p = h["drop"]
+            dz = torch.empty_like(x)
+            dbias = _handoff_bias_target(h, D, x.device)
+            call("mar_layernorm_bwd_dropout", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                 dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dz.data_ptr(), _p(dbias), rows, D, _dt(x), p,
+                 rng.data_ptr(), site, _stream())
+            h["dz"], h["dx_ptr"] = dz, dx.data_ptr()
+        elif segs is None:
             call("mar_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                  dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, D, _dt(x), _stream())
         else:
@@ -610,12 +699,12 @@ class _LayerNorm(torch.autograd.Function):
                  arrs[3], ptrs, _stream())
         if sunk:
             _sunk(ctx.gamma_ref); _sunk(ctx.beta_ref)
-            return (dx,) + (None,) * 9
-        return (dx, dgamma, dbeta) + (None,) * 7
+            return (dx,) + (None,) * 10
+        return (dx, dgamma, dbeta) + (None,) * 8
 
 
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
-               zero_rows: Optional[torch.Tensor] = None, place=None, split=None):
+               zero_rows: Optional[torch.Tensor] = None, place=None, split=None, x_handoff: Optional[dict] = None):
     """nn.LayerNorm over the last dim.  place = (buffer (B,Ttot,D), t_off): write into buffer[:, t_off:t_off+T] and return
     that view; split = [(t0, t1), ...] (x must be (B, Ttot, D)): return one contiguous (B, t1-t0, D) tensor per slice."""
     shape = x.shape
@@ -629,7 +718,7 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
         return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad, gref, bref, (buf, int(t_off), shape[0], shape[1]), None)
     if split is not None:
         return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad, gref, bref, None, (shape[0], shape[1], [tuple(map(int, s_)) for s_ in split]))
-    return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad, gref, bref).view(shape)
+    return _LayerNorm.apply(x2, g, b, eps, zero_rows, need_grad, gref, bref, None, None, x_handoff).view(shape)
 
 
 # ---- placement of an extractor's final norm inside the fused sequence ------------------------------------------------

@@ -41,7 +41,7 @@ def test_python_prototypes_match_header():
 
 def test_load_and_version():
     lib = _lib.load()
-    assert lib.mar_version() == 100
+    assert lib.mar_version() == 101
     assert lib.mar_launch_count() == 0 or lib.mar_launch_count() > 0
     assert isinstance(_lib.last_error(), str)
 

@@ -36,7 +36,7 @@ def main():
                           None if res is None else res.data_ptr(), N, y.data_ptr(), N, M, N, K, 1, 1, flags, p,
                           rng.data_ptr(), 1, 2, st)
             elif args.mode == "dgrad":
-                _lib.call("mar_linear_dgrad", y.data_ptr(), w.data_ptr(), wt.data_ptr(), None, None, 1.0, x.data_ptr(), K, M, N, K, 1, 2, st)
+                _lib.call("mar_linear_dgrad", y.data_ptr(), w.data_ptr(), wt.data_ptr(), None, None, 1.0, x.data_ptr(), K, None, M, N, K, 1, 2, st)
             else:
                 _lib.call("mar_linear_wgrad", y.data_ptr(), x.data_ptr(), K, dw.data_ptr(), M, N, K, 1, 0, 2, st)
         for _ in range(3):
