@@ -35,16 +35,26 @@ constexpr int BLOCK_K = 64;            // 64 bf16 = 128 B = one swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int ATOM_BYTES = BLOCK_K * 128;              // one MN-major box: 64 k-rows x 128 B = 8 KB
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_BOX_BYTES = 32 * 128;                // [32 rows][64 bf16]
+// Epilogue warps: EW = 8 (warp <-> 32 rows x BN/2 columns, 4 KB staging box of 64 columns, 128 B swizzle) or EW = 16
+// (warp <-> 32 rows x BN/4 columns, 2 KB staging box of 32 columns, 64 B swizzle; the producer warp-group hands its
+// registers to the four epilogue warp-groups with setmaxnreg).  ncu on the K = 768 shapes with the dropout / residual
+// epilogue (profiles/r02b_gemm_out_full_ncu.txt): the epilogue, not the tensor pipe, paces the kernel — 790 instructions
+// per 32 x 32 chunk, 2 epilogue warps per scheduler, 45 % of the issue slots used, the rest latency (tcgen05.ld, bias
+// loads, staged-box arrival, store-read waits) that two warps cannot cover.  Four warps per scheduler can.
+constexpr int EPI_BYTES = 32 * 1024;                   // staging boxes, all epilogue warps together
+template <int EW> struct Epi {
+  static constexpr int THREADS = 128 + EW * 32;
+  static constexpr int BOX_BYTES = EPI_BYTES / EW;     // 4 KB [32 rows][64 bf16] or 2 KB [32 rows][32 bf16]
+  static constexpr int BOX_COLS = BOX_BYTES / 64;
+};
+constexpr int MAX_EPI_WARPS = 16;
 
 template <int BN> struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;   // 512 or 256: power of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_BOX_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 struct TcParams {
@@ -64,12 +74,23 @@ struct TcParams {
   int accumulate;         // fp32 out += (no split)
 };
 
+// 32 lanes x 16 consecutive 32-bit TMEM columns
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, typename OutT, int CL>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, typename OutT, int CL, int EW>
+__global__ void __launch_bounds__(Epi<EW>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_o, const __grid_constant__ CUtensorMap tma_s, const TcParams p) {
   using C = Cfg<BN>;
@@ -78,13 +99,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * A_STAGE_BYTES;
   uint8_t* smem_e = smem + C::STAGES * C::STAGE_BYTES;                       // epilogue staging boxes (1024 B aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_e + EPI_WARPS * EPI_BOX_BYTES);
+  constexpr int EPI_WARPS = EW;
+  constexpr int EPI_BOX_BYTES = Epi<EW>::BOX_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_e + EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full = bars + 2 * C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* epi_bar = tmem_empty + 2;                                        // [EPI_WARPS] staged-input arrival
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + EPI_WARPS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + MAX_EPI_WARPS);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
@@ -116,6 +139,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  if (EW == 16) {      // 20 warps x 96 registers at launch: the producer group keeps 56, each epilogue thread gets 104
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -194,7 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int ew = warp - 4;                // epilogue warp index
-    const int half = ew >> 2;               // column half of the tile
+    const int half = ew >> 2;               // column half (EW = 8) / quarter (EW = 16) of the tile
     const bool do_drop = (p.flags & MAR_EPI_DROPOUT) && p.p_drop > 0.f;
     const bool idx32 = ((uint64_t)(p.M + BLOCK_M) * (uint64_t)p.N >> 1) < 0xffffffffull;   // incl. the rows of a ragged last tile
     DropKey dk;
@@ -202,7 +230,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint8_t* box = smem_e + ew * EPI_BOX_BYTES;
     uint64_t* sbar = &epi_bar[ew];
     uint32_t sphase = 0;
-    constexpr int CHUNKS = BN / 64;         // 32-column TMEM chunks handled by this warp
+    constexpr int CHUNKS = BN * 4 / (32 * EW);   // 32-column TMEM chunks handled by this warp
+    // Bias of the tile's columns, lane <-> column (one coalesced 128 B load per 32-column chunk), fetched ONE TILE AHEAD
+    // and handed out with shuffles: the per-chunk 16 B bias loads sat in every chunk's dependent chain (ncu: the FADDs
+    // behind them were the largest long-scoreboard stall of the epilogue warps)
+    float bias_nxt[CHUNKS];
+    auto load_bias = [&](int w2) {
+#pragma unroll
+      for (int cc = 0; cc < CHUNKS; cc++) {
+        const int col = ((w2 % num_tiles) % n_blocks) * BN + (half * CHUNKS + cc) * 32 + lane;
+        bias_nxt[cc] = (p.bias != nullptr && w2 < num_work && w2 / num_tiles == 0 && col < p.N) ? __ldg(p.bias + col) : 0.f;
+      }
+    };
+    load_bias(cluster_id);
     int it = 0;
     for (int w = cluster_id; w < num_work; w += num_clusters, it++) {
       const int tile = w % num_tiles, split = w / num_tiles;
@@ -211,9 +251,129 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = m_blk * BLOCK_M + q * 32;
       const int row = row0 + lane;
-      const bool first_split = split == 0;
+      float bias_cur[CHUNKS];
+#pragma unroll
+      for (int cc = 0; cc < CHUNKS; cc++) bias_cur[cc] = bias_nxt[cc];
+      load_bias(w + num_clusters);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
+      if constexpr (EW == 16 && sizeof(OutT) == 2) {
+        // one 2 KB box per 32-column chunk: [32 rows][32 bf16], 16 B pieces XOR-swizzled by (row / 2) % 4 (TMA 64 B swizzle)
+#pragma unroll 1
+        for (int cc = 0; cc < CHUNKS; cc++) {
+          const int c = half * CHUNKS + cc;
+          const int col0 = n_blk * BN + c * 32;
+          const bool active = col0 < p.N && row0 < p.M;        // warp-uniform
+          if (active) {
+            if (lane == 0) {
+              tma_store_wait_read();                           // the previous store has finished reading the box
+              if (p.staged_mode) {
+                mbar_expect_tx(sbar, EPI_BOX_BYTES);
+                tma_load_2d(box, &tma_s, sbar, col0, row0);
+              }
+            }
+            __syncwarp();
+          }
+          // two 16-column halves: 16 accumulator registers live at a time (104 registers per epilogue thread)
+          uint8_t* rowp = box + lane * 64;
+          const int swz = (lane >> 1) & 3;
+#pragma unroll 1
+          for (int hh = 0; hh < 2; hh++) {
+            uint32_t r[16];
+            tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32 + hh * 16), r);
+            tmem_ld_wait();
+            if (cc == CHUNKS - 1 && hh == 1) {     // accumulator fully read: hand the TMEM stage back to the MMA warp now
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            }
+            if (!active) continue;
+            const int colh = col0 + hh * 16;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]);
+            if (p.bias != nullptr) {
+              const float bl = cc == 0 ? bias_cur[0] : bias_cur[CHUNKS - 1];
+#pragma unroll
+              for (int j = 0; j < 16; j++) v[j] += __shfl_sync(0xffffffffu, bl, hh * 16 + j);
+            }
+            if (p.flags & MAR_EPI_RELU_PRE) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (do_drop) {
+              const uint64_t e0 = (uint64_t)row * (uint64_t)p.N + (uint64_t)colh;
+              if (idx32) {
+                const uint32_t p0 = (uint32_t)(e0 >> 1);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                  bool k0, k1;
+                  drop_keep2_32(dk, p0 + (uint32_t)j, k0, k1);
+                  v[2 * j] = k0 ? v[2 * j] * dk.scale : 0.f;
+                  v[2 * j + 1] = k1 ? v[2 * j + 1] * dk.scale : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                  bool k0, k1;
+                  drop_keep2(dk, (e0 >> 1) + j, k0, k1);
+                  v[2 * j] = k0 ? v[2 * j] * dk.scale : 0.f;
+                  v[2 * j + 1] = k1 ? v[2 * j + 1] * dk.scale : 0.f;
+                }
+              }
+            }
+            if (p.flags & MAR_EPI_RELU_POST) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.staged_mode) {
+              if (hh == 0) { mbar_wait(sbar, sphase); sphase ^= 1; }
+#pragma unroll
+              for (int g = 0; g < 2; g++) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rowp + (((hh * 2 + g) ^ swz) << 4));
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                  const float2 f = __bfloat1622float2(h2[j]);
+                  if (p.staged_mode == 1) { v[g * 8 + 2 * j] += f.x; v[g * 8 + 2 * j + 1] += f.y; }
+                  else {
+                    v[g * 8 + 2 * j] = f.x > 0.f ? v[g * 8 + 2 * j] * p.aux_scale : 0.f;
+                    v[g * 8 + 2 * j + 1] = f.y > 0.f ? v[g * 8 + 2 * j + 1] * p.aux_scale : 0.f;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 2; g++) {
+              uint4 u;
+              u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+              u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+              u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+              u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+              if (p.colsum != nullptr && row >= p.M) u = make_uint4(0u, 0u, 0u, 0u);   // rows past M are clipped by the store
+              *reinterpret_cast<uint4*>(rowp + (((hh * 2 + g) ^ swz) << 4)) = u;
+            }
+          }
+          if (!active) continue;
+          if (p.colsum != nullptr) {
+            // column sums of the ROUNDED block (what a pass over the written tensor would sum), read back lane <-> column:
+            // 32 independent 4 B loads instead of the 31-shuffle butterfly
+            __syncwarp();
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; rr++) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(box + rr * 64 + (((lane >> 3) ^ ((rr >> 1) & 3)) << 4) + ((lane & 7) >> 1) * 4);
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+              if (rr & 1) s1 += (lane & 1) ? f.y : f.x; else s0 += (lane & 1) ? f.y : f.x;
+            }
+            if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, s0 + s1);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tma_o, box, col0, row0); tma_store_commit(); }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int cc = 0; cc < CHUNKS; cc++) {
         const int c = half * CHUNKS + cc;
@@ -244,14 +404,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr && first_split) {
+        if (p.bias != nullptr) {
+          float bl = bias_cur[0];
 #pragma unroll
-          for (int g = 0; g < 8; g++) {
-            if (col0 + g * 4 < p.N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 4));
-              v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
-            }
-          }
+          for (int k = 1; k < CHUNKS; k++) bl = cc == k ? bias_cur[k] : bl;
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] += __shfl_sync(0xffffffffu, bl, j);
         }
         if (p.flags & MAR_EPI_RELU_PRE) {
 #pragma unroll
@@ -391,15 +549,16 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 tensor map over a row-major (rows, cols) matrix with leading dimension ld (elements);
 // box = (box_cols = 64 elements = 128 B, box_rows), 128 B swizzle, zero fill out of bounds.
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = 64) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) { mar_set_error("cuTensorMapEncodeTiled not available from the driver"); return MAR_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};   // 64 columns = 128 B rows / 32 columns = 64 B rows
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     mar_set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld base=%p", (int)r, (long long)rows,
@@ -409,11 +568,11 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
   return MAR_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, typename OutT, int CL>
+template <int BN, bool A_MN, bool B_MN, typename OutT, int CL, int EW>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& ms, const TcParams& p,
            cudaStream_t st) {
   using C = Cfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, OutT, CL>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, OutT, CL, EW>;
   static bool configured = false;
   if (!configured) {
     MAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -425,7 +584,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, 
   const int clusters = (int)(work < max_clusters ? work : max_clusters);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CL), 1, 1);
-  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.blockDim = dim3(Epi<EW>::THREADS, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -439,8 +598,12 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, 
 
 template <int BN, bool A_MN, bool B_MN, typename OutT>
 int launch_cl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& ms, const TcParams& p,
-              int cl, cudaStream_t st) {
-  return cl == 2 ? launch<BN, A_MN, B_MN, OutT, 2>(ma, mb, mo, ms, p, st) : launch<BN, A_MN, B_MN, OutT, 1>(ma, mb, mo, ms, p, st);
+              int cl, int ew, cudaStream_t st) {
+  if constexpr (sizeof(OutT) == 2) {
+    if (ew == 16)
+      return cl == 2 ? launch<BN, A_MN, B_MN, OutT, 2, 16>(ma, mb, mo, ms, p, st) : launch<BN, A_MN, B_MN, OutT, 1, 16>(ma, mb, mo, ms, p, st);
+  }
+  return cl == 2 ? launch<BN, A_MN, B_MN, OutT, 2, 8>(ma, mb, mo, ms, p, st) : launch<BN, A_MN, B_MN, OutT, 1, 8>(ma, mb, mo, ms, p, st);
 }
 
 }  // namespace
@@ -526,18 +689,26 @@ int gemm_tcgen05(const TcGemmArgs& a, cudaStream_t st) {
     rc = make_map(&ma, a.A, a.Kr, a.M, a.lda, BLOCK_K); if (rc) return rc;
     rc = make_map(&mb, a.B, a.Kr, a.N, a.ldb, BLOCK_K); if (rc) return rc;
   }
+  // Epilogue warps: 16 where the epilogue is heavy against a short main loop — the column sums, or dropout hashing with
+  // a reduction length below 1024 — else 8 (measured per shape, profiles/r02b_gemm_epilogue_warps.jsonl: 16 warps win
+  // 3-10 % there and lose 2-5 % on the bias-only / long-K launches).  MAR_TC_EPI_WARPS=8|16 forces one layout (A/B runs).
+  static int env_ew = -1;
+  if (env_ew < 0) { const char* e = getenv("MAR_TC_EPI_WARPS"); env_ew = e != nullptr ? atoi(e) : 0; }
+  const bool heavy = a.colsum != nullptr || ((a.flags & MAR_EPI_DROPOUT) && a.p_drop > 0.f && a.Kr < 1024);
+  const int ew = a.out_fp32 ? 8 : (env_ew == 8 || env_ew == 16 ? env_ew : (heavy ? 16 : 8));
   if (!a.out_fp32) {
-    rc = make_map(&mo, a.out, a.M, a.N, a.ldo, 32); if (rc) return rc;
+    const int bc = ew == 16 ? 32 : 64;
+    rc = make_map(&mo, a.out, a.M, a.N, a.ldo, 32, bc); if (rc) return rc;
     const void* sp = a.residual != nullptr ? a.residual : a.aux;
-    if (sp != nullptr) { rc = make_map(&ms, sp, a.M, a.N, a.residual != nullptr ? a.ldr : a.ldaux, 32); if (rc) return rc; }
+    if (sp != nullptr) { rc = make_map(&ms, sp, a.M, a.N, a.residual != nullptr ? a.ldr : a.ldaux, 32, bc); if (rc) return rc; }
     else ms = mo;
   } else {
     mo = ma; ms = ma;   // unused by the fp32 epilogue
   }
   if (!a.a_mn_major) {
-    if (a.b_mn_major) return BN == 256 ? launch_cl<256, false, true, bf16>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, true, bf16>(ma, mb, mo, ms, p, cl, st);
-    if (a.out_fp32) return BN == 256 ? launch_cl<256, false, false, float>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, false, float>(ma, mb, mo, ms, p, cl, st);
-    return BN == 256 ? launch_cl<256, false, false, bf16>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, false, false, bf16>(ma, mb, mo, ms, p, cl, st);
+    if (a.b_mn_major) return BN == 256 ? launch_cl<256, false, true, bf16>(ma, mb, mo, ms, p, cl, ew, st) : launch_cl<128, false, true, bf16>(ma, mb, mo, ms, p, cl, ew, st);
+    if (a.out_fp32) return BN == 256 ? launch_cl<256, false, false, float>(ma, mb, mo, ms, p, cl, 8, st) : launch_cl<128, false, false, float>(ma, mb, mo, ms, p, cl, 8, st);
+    return BN == 256 ? launch_cl<256, false, false, bf16>(ma, mb, mo, ms, p, cl, ew, st) : launch_cl<128, false, false, bf16>(ma, mb, mo, ms, p, cl, ew, st);
   }
-  return BN == 256 ? launch_cl<256, true, true, float>(ma, mb, mo, ms, p, cl, st) : launch_cl<128, true, true, float>(ma, mb, mo, ms, p, cl, st);
+  return BN == 256 ? launch_cl<256, true, true, float>(ma, mb, mo, ms, p, cl, 8, st) : launch_cl<128, true, true, float>(ma, mb, mo, ms, p, cl, 8, st);
 }

@@ -13,7 +13,8 @@ def main():
     ap.add_argument("--shapes", default="qkv,ffn1,ffn2,out")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--mode", default="fwd")
-    ap.add_argument("--epi", default="bias", help="none|bias|res (bias+residual)|full (bias+dropout+residual)")
+    ap.add_argument("--epi", default="bias", help="fwd: none|bias|res (bias+residual)|full (bias+dropout+residual); "
+                    "dgrad: none|res (+ fork gradient)|aux (activation mask)|auxsum (mask + column sums)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     st = torch.cuda.current_stream().cuda_stream
@@ -29,6 +30,8 @@ def main():
         y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         res = torch.randn(M, N, device=dev).bfloat16() if args.epi in ("full", "res") else None
         dw = torch.empty(N, K, device=dev)
+        xres = torch.randn(M, K, device=dev).bfloat16() if args.mode == "dgrad" else None
+        csum = torch.zeros(K, device=dev)
         def run():
             if args.mode == "fwd":
                 flags, p = (2, 0.1) if args.epi == "full" else (0, 0.0)
@@ -36,7 +39,9 @@ def main():
                           None if res is None else res.data_ptr(), N, y.data_ptr(), N, M, N, K, 1, 1, flags, p,
                           rng.data_ptr(), 1, 2, st)
             elif args.mode == "dgrad":
-                _lib.call("mar_linear_dgrad", y.data_ptr(), w.data_ptr(), wt.data_ptr(), None, None, 1.0, x.data_ptr(), K, None, M, N, K, 1, 2, st)
+                _lib.call("mar_linear_dgrad", y.data_ptr(), w.data_ptr(), wt.data_ptr(), xres.data_ptr() if args.epi == "res" else None,
+                          xres.data_ptr() if args.epi in ("aux", "auxsum") else None, 1.1, x.data_ptr(), K,
+                          csum.data_ptr() if args.epi == "auxsum" else None, M, N, K, 1, 2, st)
             else:
                 _lib.call("mar_linear_wgrad", y.data_ptr(), x.data_ptr(), K, dw.data_ptr(), M, N, K, 1, 0, 2, st)
         for _ in range(3):
