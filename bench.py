@@ -310,6 +310,8 @@ def run_ours(args):
         gathered = [torch.zeros_like(digest) for _ in range(world)]
         dist.all_gather(gathered, digest)
         ranks_identical = all(torch.equal(gathered[0], g_) for g_ in gathered[1:])
+        if step.sync.peer is not None:
+            step.sync.peer.check()          # raises if a wait on a peer inside the fused exchange kernel ever timed out
         dist.barrier()
     if rank != 0:
         shutdown()
@@ -334,6 +336,8 @@ def run_ours(args):
                    "global_batch": global_batch, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "cuda_graph": bool(use_graph),
                    "grad_exchange": None if world == 1 else {"wire": step.sync.wire, "buckets": len(step.sync.buckets),
+                                                              "engine": "one kernel over NVLink peer memory: bf16 reduce-scatter (peer loads) + all-gather (peer stores) + Adam"
+                                                              if step.sync.fused() else "ncclAllReduce + Adam kernel",
                                                               "bucket_elems": [e1 - e0 for _, _, e0, e1 in step.sync.buckets]},
                    "l2": "inputs (229 MB/step fp32) and activations (> 3 GB/step) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": global_batch / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,

@@ -258,6 +258,35 @@ int mar_adam_step_segments(float* param, const float* grad, float* exp_avg, floa
  * their gradients so that the reduced gradient is the one of the loss over the GLOBAL batch. */
 int mar_label_weight_sum(const int64_t* labels, const float* class_weight, float* out, int64_t B, int64_t C, void* stream);
 
+/* ---- Data-parallel exchange fused with the optimizer (one process per GPU, one node, NVLink peer memory) --------
+ * The reference has no distributed code; data parallelism over clips is this repo's addition
+ * (§8e) and its only exchange is the parameter-gradient sum in front of torch.optim.Adam (train_multimodal.py:444).
+ * mar_dp_allreduce_adam does that exchange AND the Adam step in ONE kernel: fp32 gradients -> bf16 wire copy ->
+ * reduce-scatter by peer loads -> all-gather by peer stores -> per-parameter Adam (semantics of
+ * mar_adam_step_segments; seg_active is the reduced header of the gradient buffer: a parameter is active if ANY rank
+ * saw a gradient) -> bf16 mirror.  Every rank applies the same bf16-rounded sums: parameters stay bit-identical.
+ *
+ * Symmetric memory: every rank allocates one block of mar_dp_block_bytes(n) with mar_peer_alloc (cudaMalloc, zeroed),
+ * exports it (64-byte CUDA IPC handle), the handles travel over the caller's own channel (torch.distributed here) and
+ * each rank imports its peers' blocks.  `blocks` is a HOST array of `world` device pointers in rank order (own block
+ * included).  `ctrl` is mar_dp_ctrl_bytes() of zeroed LOCAL device memory that must persist between calls (the
+ * exchange counter lives there, so a captured CUDA graph replays).  seg_steps / chunk_seg / chunk / nseg as in
+ * mar_adam_step_segments (chunk >= 8).  write_back != 0: the reduced gradient is also written back into `grad`.
+ * All ranks must make the same sequence of calls.  A peer that never arrives makes the kernel give up after a
+ * time-out instead of hanging the GPU; mar_dp_check (synchronises `stream`) reports it. */
+int64_t mar_dp_block_bytes(int64_t n);
+int64_t mar_dp_ctrl_bytes(void);
+int mar_peer_alloc(void** ptr, int64_t bytes);
+int mar_peer_free(void* ptr);
+int mar_peer_export(void* ptr, void* handle64);
+int mar_peer_import(const void* handle64, void** ptr);
+int mar_peer_close(void* ptr);
+int mar_dp_allreduce_adam(float* grad, int write_back, int64_t n, int world, int rank, void* const* blocks, void* ctrl,
+                          float* param, float* exp_avg, float* exp_avg_sq, const int32_t* chunk_seg, float* seg_steps,
+                          int chunk, int nseg, float lr, float beta1, float beta2, float eps, void* bf16_mirror,
+                          void* stream);
+int mar_dp_check(void* ctrl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

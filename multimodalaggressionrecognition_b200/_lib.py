@@ -60,6 +60,16 @@ PROTOTYPES = {
     "mar_adam_tick": (c_int, [P, P]),
     "mar_adam_step_segments": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_float, c_float, c_float, c_float, P, P]),
     "mar_label_weight_sum": (c_int, [P, P, P, c_int64, c_int64, P]),
+    "mar_dp_block_bytes": (c_int64, [c_int64]),
+    "mar_dp_ctrl_bytes": (c_int64, []),
+    "mar_peer_alloc": (c_int, [P, c_int64]),
+    "mar_peer_free": (c_int, [P]),
+    "mar_peer_export": (c_int, [P, P]),
+    "mar_peer_import": (c_int, [P, P]),
+    "mar_peer_close": (c_int, [P]),
+    "mar_dp_allreduce_adam": (c_int, [P, c_int, c_int64, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_float, c_float,
+                                      c_float, c_float, P, P]),
+    "mar_dp_check": (c_int, [P, P]),
 }
 
 _lib = None

@@ -112,6 +112,87 @@ class FlatAdam:
         self.flat.zero_grad()
 
 
+class PeerExchange:
+    """Symmetric NVLink peer memory of the fused exchange + Adam kernel (`mar_dp_allreduce_adam`, csrc/dp_exchange.cu):
+    every rank cudaMallocs one block [arrival flags | bf16 wire copy | bf16 reduced gradient], exports it as a CUDA IPC
+    handle, the handles are all-gathered over the process group and every rank maps its peers' blocks.  One node only.
+    Raises if any rank fails to set it up (the caller then keeps the NCCL all-reduce)."""
+
+    def __init__(self, n: int, group=None):
+        import ctypes
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n = int(n)
+        lib = _lib_load()
+        self._own = ctypes.c_void_p()
+        self._opened: List = []
+        self.blocks = (ctypes.c_void_p * self.world)()
+        err = None
+        handle = ctypes.create_string_buffer(64)
+        try:
+            call("mar_peer_alloc", ctypes.byref(self._own), int(lib.mar_dp_block_bytes(self.n)))
+            call("mar_peer_export", self._own, handle)
+        except RuntimeError as e:            # keep the collective below symmetric: every rank learns that one failed
+            err = str(e)
+        gathered: List = [None] * self.world
+        dist.all_gather_object(gathered, (err, bytes(handle.raw), _host_id()), group=group)
+        errs = [g[0] for g in gathered if g[0] is not None]
+        if errs or len({g[2] for g in gathered}) != 1:
+            self.close()
+            raise RuntimeError("peer-memory exchange unavailable: " + (errs[0] if errs else "ranks on different hosts"))
+        try:
+            for r, (_, h, _) in enumerate(gathered):
+                if r == self.rank:
+                    self.blocks[r] = self._own.value
+                else:
+                    ptr = ctypes.c_void_p()
+                    call("mar_peer_import", ctypes.create_string_buffer(h, 64), ctypes.byref(ptr))
+                    self._opened.append(ptr)
+                    self.blocks[r] = ptr.value
+        except RuntimeError as e:
+            err = str(e)
+        ok = [None] * self.world
+        dist.all_gather_object(ok, err, group=group)
+        if any(o is not None for o in ok):
+            self.close()
+            raise RuntimeError("peer-memory exchange unavailable: " + next(o for o in ok if o is not None))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.ctrl = torch.zeros((int(lib.mar_dp_ctrl_bytes()) + 7) // 8, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)             # every block is zeroed and mapped before anybody's first kernel
+
+    def check(self) -> None:
+        """Synchronises the current stream; raises if a wait on a peer inside the kernel ever timed out."""
+        call("mar_dp_check", self.ctrl.data_ptr(), _stream())
+
+    def close(self) -> None:
+        for ptr in self._opened:
+            try:
+                call("mar_peer_close", ptr)
+            except RuntimeError:
+                pass
+        self._opened = []
+        if self._own is not None and self._own.value:
+            try:
+                call("mar_peer_free", self._own)
+            except RuntimeError:
+                pass
+            self._own = None
+
+
+def _lib_load():
+    from . import _lib
+    return _lib.load()
+
+
+def _host_id() -> str:
+    import socket
+    try:
+        return open("/proc/sys/kernel/random/boot_id").read().strip()
+    except OSError:
+        return socket.gethostname()
+
+
 class GradSync:
     """Tracks which parameters received a gradient this step and, with more than one rank, exchanges the gradients.
 
@@ -186,6 +267,18 @@ class GradSync:
         self.last_active: Optional[List[bool]] = None
         for i, p in enumerate(flat.params):
             p.register_post_accumulate_grad_hook(self._hooks[i])
+        # Fused exchange + Adam over NVLink peer memory (one kernel instead of cast + ncclAllReduce + cast + Adam):
+        # bf16 wire, ONE bucket (the measured optimum anyway), NCCL process group on one node.  MAR_DP_FUSED=0 keeps NCCL.
+        self.peer: Optional[PeerExchange] = None
+        self.fused_opt = None            # the FlatAdam whose step the fused kernel performs (set by TrainStep)
+        self.fused_write_back = False    # also leave the reduced gradient in the fp32 .grad views
+        if (self.wire == "bf16" and len(self.buckets) == 1 and _os.environ.get("MAR_DP_FUSED", "1") != "0" and not _NOCOMM
+                and dist.get_backend(group) == "nccl" and flat.align >= 8):
+            try:
+                self.peer = PeerExchange(flat.numel, group)
+            except RuntimeError as e:
+                import warnings
+                warnings.warn(f"{e}; falling back to the NCCL all-reduce")
         self.reset()
 
     def notify(self, param) -> None:
@@ -275,8 +368,31 @@ class GradSync:
         self.flat.flags.copy_(mask)
         self.last_active = list(self.fired)
 
+    def fused(self) -> bool:
+        return self.peer is not None and self.fused_opt is not None
+
+    def _launch_fused(self) -> None:
+        """gradient exchange AND the Adam step, one kernel on the current stream (nothing left to overlap with)."""
+        import ctypes
+        f, o, pe = self.flat, self.fused_opt, self.peer
+        cur = torch.cuda.current_stream()
+        for b in range(len(self.buckets)):           # gradients written on other streams (kept-alive AccumulateGrad nodes)
+            for key, s in self._streams[b].items():
+                if key != cur.cuda_stream:
+                    cur.wait_stream(s)
+            self.launched[b] = True
+        call("mar_dp_allreduce_adam", f.grad.data_ptr(), int(self.fused_write_back), f.numel, pe.world, pe.rank,
+             ctypes.cast(pe.blocks, ctypes.c_void_p), pe.ctrl.data_ptr(), f.flat.data_ptr(), o.exp_avg.data_ptr(),
+             o.exp_avg_sq.data_ptr(), f.chunk_seg.data_ptr(), o.seg_steps.data_ptr(), f.align, f.nseg, o.lr, o.betas[0],
+             o.betas[1], o.eps, None if f.mirror is None else f.mirror.data_ptr(), cur.cuda_stream)
+        ops.weights_changed()
+
     def finish(self) -> None:
         self._write_flags()
+        if self.world > 1 and self.fused():
+            self._launch_fused()
+            self.reset()
+            return
         if self.world > 1:
             for b in range(len(self.buckets)):
                 if not self.launched[b]:
@@ -316,6 +432,7 @@ class TrainStep:
                 mode = precision if precision is not None else ("fp32" if ops.get_precision() == torch.float32 else "bf16")
                 wire = "bf16" if (mode == "bf16" and self.flat.flat.is_cuda) else "fp32"
             self.sync = GradSync(self.flat, group=group, num_buckets=num_buckets, wire=wire, tail_elems=tail_elems)
+            self.sync.fused_opt = self.opt       # with peer memory available, the exchange kernel also does the Adam step
         if self.sync.world > 1 and self.flat.flat.is_cuda and ops._rng.seed is None:
             # every rank seeds torch identically (same initial weights), which would also give every rank the SAME
             # dropout masks for its different clips; a single process on the global batch draws independent masks per
@@ -416,8 +533,10 @@ class TrainStep:
             losses = LossesDict(loss=losses)
         with ops.grad_sink(self.sync.notify):       # weight / bias / LayerNorm gradients accumulate straight into the flat buffer
             self._backward(losses, weights)
+        fused = self.sync.world > 1 and self.sync.fused()
         self.sync.finish()
-        self.opt.step()
+        if not fused:                 # the fused exchange kernel has already applied Adam
+            self.opt.step()
         self.last_pred = pred
         return {k: v.detach() for k, v in losses.items()}
 

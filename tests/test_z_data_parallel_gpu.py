@@ -59,14 +59,21 @@ def _rows(labels):
     return {names[0].split("_")[0]: sum(n.split("_")[-1] != "EMPTY" for n in names) for names, _ in labels}
 
 
-def _worker(rank, world, port, steps, graph, result_q, mixed=False, precision="fp32"):
+def _worker(rank, world, port, steps, graph, result_q, mixed=False, precision="fp32", fused=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if fused is not None:
+        os.environ["MAR_DP_FUSED"] = "1" if fused else "0"
+        os.environ["MAR_DP_TIMEOUT_S"] = "10"      # a broken exchange fails the test instead of spinning for a minute per wait
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        step = training.TrainStep(_model(dev), _crit(), lr=1e-3, graph=graph, precision=precision, num_buckets=4, tail_elems=100_000)
-        assert step.sync.world == world and len(step.sync.buckets) >= 2
+        if fused is None:
+            step = training.TrainStep(_model(dev), _crit(), lr=1e-3, graph=graph, precision=precision, num_buckets=4, tail_elems=100_000)
+            assert step.sync.world == world and len(step.sync.buckets) >= 2
+        else:       # the default exchange: ONE bucket; with peer memory the exchange kernel also does the Adam step
+            step = training.TrainStep(_model(dev), _crit(), lr=1e-3, graph=graph, precision=precision)
+            assert step.sync.world == world and len(step.sync.buckets) == 1 and step.sync.fused() == fused
         assert step.sync.wire == ("bf16" if precision == "bf16" else "fp32")
         curve = []
         for s in range(steps):
@@ -80,9 +87,12 @@ def _worker(rank, world, port, steps, graph, result_q, mixed=False, precision="f
         curves = [None] * world
         dist.all_gather_object(curves, curve)
         same = all(torch.equal(gathered[0], g) for g in gathered[1:])
+        if step.sync.peer is not None:
+            step.sync.peer.check()      # no wait on a peer ever timed out inside the exchange kernel
+        steps_per_param = step.opt.seg_steps.detach().cpu()
         step.release_graphs()           # before the communicator goes away (graphs captured its collectives)
         if rank == 0:
-            result_q.put((same, curves))
+            result_q.put((same, curves) if fused is None else (same, curves, flat.cpu(), steps_per_param))
     finally:
         dist.destroy_process_group()
 
@@ -156,6 +166,48 @@ def test_two_gpu_bf16_step_with_bf16_gradient_exchange():
             parts = [c[s][k] for c in curves if k in c[s]]
             got = sum(l * n for l, n in parts) / sum(n for _, n in parts)
             assert abs(got - v) <= 0.1 * max(1.0, abs(v)), f"step {s} loss[{k}]: 2 GPUs (bf16 exchange) {got} vs single GPU {v}"
+
+
+def _run_two_ranks(graph, mixed, fused, steps=7):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, steps, graph, q, mixed, "bf16", fused)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        out = q.get(timeout=240)
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs)
+    return out
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("graph,mixed", [(False, False), (True, True)])
+def test_two_gpu_fused_peer_memory_exchange_matches_the_nccl_path(graph, mixed):
+    """The fused exchange + Adam kernel (csrc/dp_exchange.cu: bf16 wire copy, reduce-scatter by peer loads, all-gather by
+    peer stores, per-parameter Adam, one launch) against the same steps through cast + ncclAllReduce(bf16) + cast + the
+    Adam kernels: with two ranks the bf16-rounded sums are the same numbers, so the parameters after 7 steps agree to
+    fp32 rounding (the two Adam kernels contract their multiply-adds differently), the ranks hold bit-identical
+    parameters, every parameter's step count is the number of steps in which ANY rank had a gradient for it (mixed:
+    rank 1 never sees a video clip), and no wait on a peer timed out."""
+    same_f, curves_f, flat_f, steps_f = _run_two_ranks(graph, mixed, True)
+    same_n, curves_n, flat_n, steps_n = _run_two_ranks(graph, mixed, False)
+    assert same_f and same_n, "ranks hold different parameters after the same steps"
+    assert torch.equal(steps_f, steps_n), (steps_f, steps_n)
+    assert float(steps_f.min()) >= 1
+    err = float((flat_f - flat_n).norm() / flat_n.norm())
+    assert err < 1e-6, f"fused exchange vs NCCL path: parameters differ by {err:.3e}"
+    for cf, cn in zip(curves_f, curves_n):
+        for a, b in zip(cf, cn):
+            for k in b:
+                assert abs(a[k][0] - b[k][0]) <= 1e-3 * max(1.0, abs(b[k][0])), (k, a[k], b[k])
 
 
 def test_eager_bf16_train_step_sees_its_own_weight_updates():
