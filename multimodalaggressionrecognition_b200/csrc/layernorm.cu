@@ -197,6 +197,22 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 #pragma unroll
         for (int j = 0; j < 8; j++) o[j] = rs * (a[j] * gm[j] - s1 - (b[j] - mu) * rs * s2);
         Vec8<T>::store(dx + row * D + col, o);
+        if (DROP) {
+          const uint64_t e0 = (uint64_t)row * (uint64_t)D + (uint64_t)col;     // even: one hash per pair of elements
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            bool k0, k1;
+            if (idx32) drop_keep2_32(dk, (uint32_t)(e0 >> 1) + (uint32_t)j, k0, k1);
+            else drop_keep2(dk, (e0 >> 1) + j, k0, k1);
+            o[2 * j] = k0 ? o[2 * j] * dk.scale : 0.f;
+            o[2 * j + 1] = k1 ? o[2 * j + 1] * dk.scale : 0.f;
+          }
+          Vec8<T>::store(dzp + row * D + col, o);
+          float4 z0 = zacc[(c * 2) * 32 + lane], z1 = zacc[(c * 2 + 1) * 32 + lane];
+          z0.x += o[0]; z0.y += o[1]; z0.z += o[2]; z0.w += o[3];
+          z1.x += o[4]; z1.y += o[5]; z1.z += o[6]; z1.w += o[7];
+          zacc[(c * 2) * 32 + lane] = z0; zacc[(c * 2 + 1) * 32 + lane] = z1;
+        }
       }
     }
   }

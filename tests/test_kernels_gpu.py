@@ -397,6 +397,94 @@ def test_attention_keep_bits_are_bernoulli_and_shared_by_every_engine(p):
 # ------------------------------------------------------------------------------------------
 # layer norm / pooling / masks / concat / loss / adam
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("p", [0.0, 0.2])
+@pytest.mark.parametrize("B,T,d,H,ff", [(3, 70, 192, 2, 256), (2, 250, 768, 8, 2048), (5, 33, 128, 2, 512)])
+def test_backward_handoffs_match_the_separate_passes(mode, p, B, T, d, H, ff):
+    """One post-norm encoder layer, backward with the hand-offs (norm1 / norm2 write out_proj's / linear2's dropout backward
+    and sum their bias gradients, the attention kernel sums the in-projection's bias gradient, linear2's dgrad GEMM sums
+    linear1's) against the same layer with every linear launching its own epilogue-backward pass: same seed, same sites,
+    hence the same masks — the same gradients."""
+    from multimodalaggressionrecognition_b200.models import encoder_layer_forward
+    torch.manual_seed(5)
+    layer = torch.nn.TransformerEncoderLayer(d, H, dim_feedforward=ff, dropout=p, batch_first=True).to(DEV)
+    layer.train()
+    x = torch.randn(B * T, d, device=DEV)
+    go = torch.randn(B * T, d, device=DEV)
+    key_mask = torch.zeros(B, T, dtype=torch.uint8, device=DEV)
+    key_mask[0, T - 7:] = 1
+    res = {}
+    for on in (False, True):
+        mar.manual_seed(31)
+        ops.clear_weight_cache()          # both runs cast the weights (the launch counts below are compared)
+        for q in layer.parameters():
+            q.grad = None
+        xx = x.clone().requires_grad_(True)
+        with mar.precision(mode), ops.handoffs(on):
+            n0 = ops.launch_count()
+            y = encoder_layer_forward(layer, ops.to_compute(xx), B, T, key_mask)
+            y.backward(go.to(y.dtype))
+            launches = ops.launch_count() - n0
+        res[on] = ([y.detach().float(), xx.grad.float()] + [q.grad.float().clone() for q in layer.parameters()], launches)
+    names = ["y", "dx"] + [n for n, _ in layer.named_parameters()]
+    # fp32: same numbers, only summation orders differ.  bf16: the fused kernel masks the fp32 dx and rounds once, the
+    # separate pass masks the bf16-rounded dx and rounds again — the GEMM operands differ by one bf16 rounding
+    tol = 2e-5 if mode == "fp32" else 6e-3
+    for name, a, b in zip(names, res[True][0], res[False][0]):
+        assert_close(a, b, tol, f"hand-off backward: {name}")
+        assert float(b.abs().max()) > 0, name
+    assert torch.equal(res[True][0][0], res[False][0][0])
+    # passes that are gone: out_proj's and linear2's dropout backward (dropout on), and — on the tensor-core engines, which
+    # sum inside their own epilogues — the bias-only passes of the in-projection and linear1
+    assert res[False][1] - res[True][1] >= (2 if p > 0 else 0) + (2 if mode == "bf16" else 0), (res[False][1], res[True][1])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,D", [(100, 768), (7, 512), (3000, 1280), (33, 64)])
+def test_layernorm_backward_with_fused_dropout_backward(rows, D, mode):
+    """mar_layernorm_bwd_dropout against mar_layernorm_bwd followed by mar_linear_bwd_epilogue (the same mask function):
+    dx bit-identical, the same elements dropped, dz / dbias / dgamma / dbeta to rounding and summation order."""
+    from multimodalaggressionrecognition_b200 import _lib
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    code = 0 if mode == "fp32" else 1
+    x = (torch.randn(rows, D, device=DEV) * 2 + 0.5).to(dt)
+    dy = torch.randn(rows, D, device=DEV).to(dt)
+    gamma = torch.randn(D, device=DEV)
+    mean = x.float().mean(1).contiguous()
+    rstd = (x.float().var(1, unbiased=False) + 1e-5).rsqrt().contiguous()
+    rng = torch.tensor([1234, 7], dtype=torch.int64, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    site, p = 17, 0.3
+    z = lambda *s_: torch.zeros(*s_, dtype=torch.float32, device=DEV)
+    dx0, dg0, db0 = torch.empty_like(x), z(D), z(D)
+    _lib.call("mar_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+              dx0.data_ptr(), dg0.data_ptr(), db0.data_ptr(), rows, D, code, st)
+    dz0, dbias0 = torch.empty_like(x), z(D)
+    _lib.call("mar_linear_bwd_epilogue", dx0.data_ptr(), None, dz0.data_ptr(), dbias0.data_ptr(), rows, D, code, code, 2, p,
+              rng.data_ptr(), site, 0, st)
+    dx1, dg1, db1, dz1, dbias1 = torch.empty_like(x), z(D), z(D), torch.full_like(x, float("nan")), z(D)
+    _lib.call("mar_layernorm_bwd_dropout", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+              dx1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), dz1.data_ptr(), dbias1.data_ptr(), rows, D, code, p,
+              rng.data_ptr(), site, st)
+    torch.cuda.synchronize()
+    assert torch.equal(dx0, dx1)
+    assert not torch.isnan(dz1.float()).any()
+    kept = float((dz1 != 0).float().mean())
+    assert abs(kept - (1 - p)) < 0.02, kept
+    if mode == "fp32":
+        assert torch.equal(dz0, dz1)
+    else:   # the separate pass masks the bf16-ROUNDED dx, the fused kernel the fp32 value: one rounding apart at most
+        assert torch.equal(dz0 != 0, dz1 != 0)
+        assert_close(dz1.float(), dz0.float(), 6e-3, "dz")
+    assert_close(dbias1, dbias0, 2e-3 if mode == "bf16" else 1e-5, "dbias")
+    assert_close(dg1, dg0, 1e-5, "dgamma")
+    assert_close(db1, db0, 1e-5, "dbeta")
+    # dbias = NULL is accepted
+    _lib.call("mar_layernorm_bwd_dropout", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+              dx1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), dz1.data_ptr(), None, rows, D, code, p, rng.data_ptr(), site, st)
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("rows,D", [(100, 768), (7, 512), (1000, 1280), (33, 64), (64, 2048)])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_layernorm(rows, D, mode):
