@@ -426,6 +426,31 @@ def test_full_size_c1_c2_against_oracle():
                 H.assert_close(got[k].cpu(), ref[k], tol, f"C2 {mode} {k}")
 
 
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("T", [600, 1100])
+def test_long_sequences_through_the_model_against_oracle(T):
+    """BASELINE config 5's lengths through the module API: TransformerSequenceProcessor + OutputClassifier at T = 600 /
+    1100 (the pair kernel's range, several key tiles, a ragged last tile) with d = 192 (head dim 96 as in the reference's
+    768 / 8): logits and every parameter gradient against the fp32 oracle, fp32 and bf16 mode."""
+    torch.manual_seed(0)
+    d, heads, B = 192, 2, 3
+    model = W.perturb_norms(W.disable_dropout(W.build_c1(M, d=d, layers=1, heads=heads))).to(DEV).train()
+    x, y = W.batch_c1(B=B, T=T, d=d, seed=77)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = O.output_classifier(O.transformer_sequence_processor(x, sd, "0.", 1, heads), sd, "1.")
+    O.cross_entropy(ref, y).backward()
+    ref_g = {k: v.grad for k, v in sd.items() if v.grad is not None}
+    for mode, tol, gtol in (("fp32", H.FP32_TOL, 3e-4), ("bf16", H.BF16_TOL, 4e-2)):
+        with mar.precision(mode):
+            model.zero_grad()
+            out = model(x.to(DEV))
+            ops.cross_entropy(out, y.to(DEV)).backward()
+        H.assert_close(out.detach().float().cpu(), ref.detach(), tol, f"T={T} {mode} logits")
+        num = sum(float((p.grad.double().cpu() - ref_g[k].double()).pow(2).sum()) for k, p in model.named_parameters())
+        den = sum(float(g.double().pow(2).sum()) for g in ref_g.values())
+        assert (num / den) ** 0.5 <= gtol, f"T={T} {mode}: whole-gradient relative error {(num / den) ** 0.5:.3e}"
+
+
 def test_reference_state_dict_round_trip():
     """Checkpoints interchange with the reference: same keys, load_state_dict strict."""
     a = W.build_c3(M, t_audio=24, t_video=8)
