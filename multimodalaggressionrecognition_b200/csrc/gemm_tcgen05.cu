@@ -689,12 +689,14 @@ int gemm_tcgen05(const TcGemmArgs& a, cudaStream_t st) {
     rc = make_map(&ma, a.A, a.Kr, a.M, a.lda, BLOCK_K); if (rc) return rc;
     rc = make_map(&mb, a.B, a.Kr, a.N, a.ldb, BLOCK_K); if (rc) return rc;
   }
-  // Epilogue warps: 16 where the epilogue is heavy against a short main loop — the column sums, or dropout hashing with
-  // a reduction length below 1024 — else 8 (measured per shape, profiles/r02b_gemm_epilogue_warps.jsonl: 16 warps win
-  // 3-10 % there and lose 2-5 % on the bias-only / long-K launches).  MAR_TC_EPI_WARPS=8|16 forces one layout (A/B runs).
+  // Epilogue warps: 16 for the launches that also take column sums (linear2's dgrad: mask + bias gradient of linear1),
+  // else 8.  Measured INSIDE the step (profiles/r02b_gemm_in_step_tables.txt): with column sums 16 warps 244.6 us against
+  // 277.6 us (M = 80384); for the dropout epilogues of out_proj / linear1 16 warps are 8-18 % SLOWER in the step (257 vs
+  // 218 us) although the isolated microbenchmark had them 2-4 % ahead (profiles/r02b_gemm_epilogue_warps.jsonl).
+  // MAR_TC_EPI_WARPS=8|16 forces one layout (A/B runs).
   static int env_ew = -1;
   if (env_ew < 0) { const char* e = getenv("MAR_TC_EPI_WARPS"); env_ew = e != nullptr ? atoi(e) : 0; }
-  const bool heavy = a.colsum != nullptr || ((a.flags & MAR_EPI_DROPOUT) && a.p_drop > 0.f && a.Kr < 1024);
+  const bool heavy = a.colsum != nullptr;
   const int ew = a.out_fp32 ? 8 : (env_ew == 8 || env_ew == 16 ? env_ew : (heavy ? 16 : 8));
   if (!a.out_fp32) {
     const int bc = ew == 16 ? 32 : 64;
