@@ -247,7 +247,11 @@ def run_ours(args):
     out = {}
     def dev_step():
         out["l"] = step(gdata, glabels)
-    for _ in range(max(args.warmup, 6)):                      # >= 3 eager warm-up calls, then one capture per input-buffer set
+    # initialisation (not warm-up): the step driver runs 3 eager steps, then captures one CUDA graph per input-buffer set
+    setup_steps = 6 if use_graph else 0
+    for _ in range(setup_steps):
+        dev_step()
+    for _ in range(max(args.warmup, 3)):                      # the W untimed warm-up steps of the contract (W >= 3)
         dev_step()
     torch.cuda.synchronize()
     ops.reset_launch_count()
@@ -329,12 +333,12 @@ def run_ours(args):
     global_batch = B * world
     line = {
         "metric": METRIC, "value": global_batch / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 6), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"C3 audio+video transformer fusion train step (fwd+loss+bwd+allreduce+Adam), "
                                f"T_a={T_AUDIO}x768, T_v={T_VIDEO}x512, d=768, 8 heads, d_ff=2048, 19.7M params, dropout on",
                    "global_batch": global_batch, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                   "cuda_graph": bool(use_graph),
+                   "cuda_graph": bool(use_graph), "setup_steps_before_warmup": setup_steps,
                    "grad_exchange": None if world == 1 else {"wire": step.sync.wire, "buckets": len(step.sync.buckets),
                                                               "engine": "one kernel over NVLink peer memory: bf16 reduce-scatter (peer loads) + all-gather (peer stores) + Adam"
                                                               if step.sync.fused() else "ncclAllReduce + Adam kernel",
