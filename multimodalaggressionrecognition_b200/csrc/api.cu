@@ -30,6 +30,14 @@ bool mar_debug_sync() {
   return on;
 }
 
+bool mar_pdl_enabled(int kernel_class) {
+  // default 1: the tcgen05 GEMM launches only — measured per class on B200 (profiles/r02_notes_measured_dead_ends.md): never
+  // slower there, no gain for the attention / elementwise classes, LayerNorm launches get SLOWER (their CTAs become
+  // resident beside the previous persistent GEMM)
+  static const int mask = [] { const char* v = getenv("MAR_PDL"); return v != nullptr ? atoi(v) : 1; }();
+  return (mask & kernel_class) != 0;
+}
+
 int mar_sm_count() {
   if (g_sm_count == 0) {
     int dev = 0, n = 0;

@@ -11,6 +11,7 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 attn_dropbits_kernel(uint32_t* __restrict__ words, int64_t n_words, int m, const uint64_t* __restrict__ rng, uint32_t site) {
+  pdl_entry();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_words) return;
   const DropKey dk = make_drop_key(rng, site, 0.5f);           // only the key is used
@@ -33,7 +34,7 @@ int64_t attention_dropbits_words(int64_t B, int64_t T, int64_t H) {
 int attention_dropbits(uint32_t* words, int64_t B, int64_t T, int64_t H, float p, const uint64_t* rng, uint32_t site,
                        cudaStream_t st) {
   const int64_t n = attention_dropbits_words(B, T, H);
-  attn_dropbits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(words, n, drop_keep_m(p), rng, site);
+  mar_launch(attn_dropbits_kernel, (unsigned)ceil_div(n, 256), 256, 0, st, words, n, drop_keep_m(p), rng, site);
   MAR_LAUNCH_CHECK("attn_dropbits");
   return MAR_OK;
 }

@@ -27,6 +27,7 @@
 // Roofline: tensor pipe (4·T²·dh FLOP per (b,h)); the softmax's exp2 (16/clk/SM) and its ALU work bound it below
 // the MMA rate — see DESIGN.md §4.2.
 #include <stdlib.h>
+#define MAR_PDL_CLASS 8
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "attention.cuh"
@@ -61,6 +62,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 template <int DH, bool DROP>
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
+  pdl_entry();
   constexpr int NBOX = (DH + 63) / 64;
   constexpr int OP_BYTES = NBOX * BOX_BYTES;
   constexpr int KSTEPS = DH / 16;
@@ -326,8 +328,8 @@ int fwd_launch(const void* qkv, const uint8_t* key_mask, void* out, float* lse, 
   prm.p_drop = p; prm.dbits = dbits;
   const int64_t q_tiles = ceil_div(T, BQ);
   const unsigned grid = (unsigned)(B * H * q_tiles);
-  if (p > 0.f) attn_fwd_tc_kernel<DH, true><<<grid, 256, SMEM, st>>>(tm, prm);
-  else attn_fwd_tc_kernel<DH, false><<<grid, 256, SMEM, st>>>(tm, prm);
+  if (p > 0.f) mar_launch(attn_fwd_tc_kernel<DH, true>, grid, 256, SMEM, st, tm, prm);
+  else mar_launch(attn_fwd_tc_kernel<DH, false>, grid, 256, SMEM, st, tm, prm);
   MAR_LAUNCH_CHECK("attn_fwd_tc");
   return MAR_OK;
 }

@@ -23,6 +23,7 @@
 //
 // Roofline: tensor pipe (4·T²·dh FLOP per (b,h)); bounded in practice by the softmax's exp2 (MUFU, 16/clk/SM)
 // and ALU work — DESIGN.md §4.2.
+#define MAR_PDL_CLASS 8
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "attention.cuh"
@@ -60,6 +61,7 @@ template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 template <int DH, bool DROP>
 __global__ void __launch_bounds__(NTHREADS2, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Fwd2Params p) {
+  pdl_entry();
   constexpr int NBOX = (DH + 63) / 64;
   constexpr int OP_BYTES = NBOX * BOX_BYTES;
   constexpr int KSTEPS = DH / 16;
@@ -369,8 +371,8 @@ int fwd2_launch(const void* qkv, const uint8_t* key_mask, void* out, float* lse,
   prm.p_drop = p; prm.dbits = dbits;
   const int64_t q_pairs = (ceil_div(T, BQ) + 1) / 2;
   const unsigned grid = (unsigned)(B * H * q_pairs);
-  if (p > 0.f) attn_fwd_tc2_kernel<DH, true><<<grid, NTHREADS2, SMEM, st>>>(tm, prm);
-  else attn_fwd_tc2_kernel<DH, false><<<grid, NTHREADS2, SMEM, st>>>(tm, prm);
+  if (p > 0.f) mar_launch(attn_fwd_tc2_kernel<DH, true>, grid, NTHREADS2, SMEM, st, tm, prm);
+  else mar_launch(attn_fwd_tc2_kernel<DH, false>, grid, NTHREADS2, SMEM, st, tm, prm);
   MAR_LAUNCH_CHECK("attn_fwd_tc2");
   return MAR_OK;
 }

@@ -30,6 +30,7 @@
 // Fully masked rows (LSE = -inf) contribute nothing.
 #include <algorithm>
 #include <type_traits>
+#define MAR_PDL_CLASS 8
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "attention.cuh"
@@ -90,6 +91,7 @@ template <int DH, bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dq, const BwdParams p) {
+  pdl_entry();
   constexpr int NBOX = (DH + 63) / 64;
   constexpr int KV_BYTES = NBOX * BOX_BYTES;        // 128-row operand tile
   constexpr int Q_BYTES = NBOX * QBOX_BYTES;        // 64-row operand tile
@@ -492,6 +494,7 @@ constexpr int DELTA_ROWS = 8;
 __global__ void __launch_bounds__(256)
 attn_delta_tc_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta, int64_t BT_rows,
                      int T, int H, int dh) {
+  pdl_entry();
   extern __shared__ float part[];                 // [DELTA_ROWS][d/8]
   const int d = H * dh, c8n = d / 8;
   const int64_t row0 = (int64_t)blockIdx.x * DELTA_ROWS;
@@ -522,6 +525,7 @@ attn_delta_tc_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout
 // dqkv[:, :, 0:d] (bf16) = dq_acc (fp32)
 __global__ void __launch_bounds__(256)
 attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, int64_t rows, int d) {
+  pdl_entry();
   const int c8n = d / 8;
   const int64_t n = rows * c8n;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -552,7 +556,7 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
   float* dq_acc = T > BT ? work + ((B * H * T + 3) & ~(int64_t)3) : nullptr;
   {
     const int64_t rows = B * T;
-    attn_delta_tc_kernel<<<(unsigned)ceil_div(rows, DELTA_ROWS), 256, DELTA_ROWS * (d / 8) * sizeof(float), st>>>(
+    mar_launch(attn_delta_tc_kernel, (unsigned)ceil_div(rows, DELTA_ROWS), 256, DELTA_ROWS * (d / 8) * sizeof(float), st, 
         (const bf16*)out, (const bf16*)dout, delta, rows, (int)T, (int)H, DH);
     MAR_LAUNCH_CHECK("attn_delta_tc");
   }
@@ -574,12 +578,12 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
   prm.key_mask = key_mask; prm.lse = lse; prm.delta = delta; prm.dq_acc = dq_acc; prm.dqkv = (bf16*)dqkv; prm.dbias = dbias;
   prm.B = (int)B; prm.T = (int)T; prm.H = (int)H; prm.p_drop = p; prm.dbits = dbits; prm.smem_bytes = SMEM;
   const int64_t n_t = ceil_div(T, BT);
-  attn_bwd_tc_kernel<DH, DROP><<<(unsigned)(B * H * n_t), NTHREADS, SMEM, st>>>(tm_kv, tm_q, tm_do, tm_dq, prm);
+  mar_launch(attn_bwd_tc_kernel<DH, DROP>, (unsigned)(B * H * n_t), NTHREADS, SMEM, st, tm_kv, tm_q, tm_do, tm_dq, prm);
   MAR_LAUNCH_CHECK("attn_bwd_tc");
   if (dq_acc != nullptr) {
     const int64_t n = B * T * (d / 8);
     const int64_t blocks = std::min<int64_t>(ceil_div(n, 256), (int64_t)mar_sm_count() * 16);
-    attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, st>>>(dq_acc, (bf16*)dqkv, B * T, (int)d);
+    mar_launch(attn_dq_convert_kernel, (unsigned)blocks, 256, 0, st, dq_acc, (bf16*)dqkv, B * T, (int)d);
     MAR_LAUNCH_CHECK("attn_dq_convert");
   }
   return MAR_OK;

@@ -57,6 +57,34 @@ bool mar_debug_sync();   // MAR_DEBUG_SYNC=1: synchronise after every launch and
   } while (0)
 
 int mar_sm_count();
+// MAR_PDL = bit mask of the kernel classes launched with programmatic dependent launch: 1 tcgen05 GEMM, 2 LayerNorm,
+// 4 elementwise / skinny GEMM / Adam, 8 attention (default: see api.cu; 0 switches it off)
+bool mar_pdl_enabled(int kernel_class);
+#ifndef MAR_PDL_CLASS
+#define MAR_PDL_CLASS 4
+#endif
+
+// Programmatic dependent launch (sm_90+): a kernel launched with mar_launch may be STARTED while the previous kernel of the
+// stream is still running — its CTAs take SMs as they free up and sit in pdl_entry() until that kernel has completed and
+// flushed its memory — so the launch latency between two kernels (2-4 us of idle GPU per boundary, ~100 boundaries per
+// train step) overlaps the previous kernel's tail.  pdl_entry() must come before the first global-memory access; kernels
+// with a prologue that touches no global memory (barrier init, TMEM allocation) call it after that prologue.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t mar_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = mar_pdl_enabled(MAR_PDL_CLASS) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

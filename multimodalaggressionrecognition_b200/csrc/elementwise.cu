@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256)
 bwd_epilogue_kernel(const T* __restrict__ dout, const TO* __restrict__ out, T* __restrict__ dz,
                     float* __restrict__ dbias, int64_t M, int64_t N, int rows_per_block, int flags, float p,
                     const uint64_t* __restrict__ rng, uint32_t site, int bcast) {
+  pdl_entry();
   // bcast > 0: dout has M / bcast rows and row r reads dout row r / bcast scaled by 1 / bcast — the backward of a mean
   // over `bcast` consecutive rows (SequenceAverageFeatures after an adaptor, models.py:693-699) without materialising it
   const int lane = threadIdx.x, ry = threadIdx.y;
@@ -149,10 +150,10 @@ int launch_bwd_epilogue(const void* dout, const void* out, void* dz, float* dbia
   int64_t gy = ceil_div(M, rows_per_block);
   dim3 grid((unsigned)gx, (unsigned)gy), block(32, 8);
   if (vec)
-    bwd_epilogue_kernel<T, TO, 8><<<grid, block, 0, st>>>((const T*)dout, (const TO*)out, (T*)dz, dbias, M, N,
+    mar_launch(bwd_epilogue_kernel<T, TO, 8>, grid, block, 0, st, (const T*)dout, (const TO*)out, (T*)dz, dbias, M, N,
                                                           (int)rows_per_block, flags, p, rng, site, bcast);
   else
-    bwd_epilogue_kernel<T, TO, 1><<<grid, block, 0, st>>>((const T*)dout, (const TO*)out, (T*)dz, dbias, M, N,
+    mar_launch(bwd_epilogue_kernel<T, TO, 1>, grid, block, 0, st, (const T*)dout, (const TO*)out, (T*)dz, dbias, M, N,
                                                           (int)rows_per_block, flags, p, rng, site, bcast);
   MAR_LAUNCH_CHECK("bwd_epilogue");
   return MAR_OK;
@@ -163,6 +164,7 @@ int launch_bwd_epilogue(const void* dout, const void* out, void* dz, float* dbia
 // ------------------------------------------------------------------------------------------
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n) {
+  pdl_entry();
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     float v[8];
@@ -200,6 +202,7 @@ __global__ void cast_weight_kernel(const float* __restrict__ src, T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256)
 meanpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t Tn, int64_t D) {
+  pdl_entry();
   const int64_t b = blockIdx.y;
   const int64_t c0 = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 8;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -249,6 +252,7 @@ __global__ void meanpool_bwd_kernel(const T* __restrict__ dout, T* __restrict__ 
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void rowzero_kernel(const T* __restrict__ x, uint8_t* __restrict__ mask, int64_t rows, int64_t D) {
+  pdl_entry();
   int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   if (row >= rows) return;
   const int lane = threadIdx.x % 32;
@@ -346,6 +350,7 @@ __global__ void __launch_bounds__(256)
 cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                      const float* __restrict__ cw, float* __restrict__ loss, float* __restrict__ dlogits,
                      int64_t* __restrict__ preds, int64_t B, int64_t C) {
+  pdl_entry();
   __shared__ float s_num[256], s_den[256];
   float num = 0.f, den = 0.f;
   for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
@@ -435,6 +440,7 @@ __global__ void adam_tick_kernel(float* step_dev) { step_dev[0] += 1.f; }
 // advances the step count of the active segments and leaves their bias-correction pair in seg_coef.
 __global__ void adam_seg_tick_kernel(float* __restrict__ seg_steps, const float* __restrict__ seg_active,
                                      float2* __restrict__ seg_coef, int nseg, float lr, float b1, float b2) {
+  pdl_entry();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
   if (!(seg_active[s] > 0.f)) { seg_coef[s] = make_float2(0.f, 0.f); return; }
@@ -448,6 +454,7 @@ __global__ void __launch_bounds__(256)
 adam_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 const int32_t* __restrict__ chunk_seg, const float2* __restrict__ seg_coef, int64_t n, int chunk_shift,
                 float b1, float b2, float eps, bf16* __restrict__ mirror) {
+  pdl_entry();
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   const int seg = chunk_seg[i >> chunk_shift];
@@ -540,10 +547,10 @@ int mar_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n
   MAR_CHECK_ARG(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "mar_cast: pointers must be 16 B aligned");
   unsigned blocks = (unsigned)ceil_div(ceil_div(n, 8), 256);
   cudaStream_t st = S(stream);
-  if (src_dtype == MAR_F32 && dst_dtype == MAR_BF16) cast_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
-  else if (src_dtype == MAR_BF16 && dst_dtype == MAR_F32) cast_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
-  else if (src_dtype == MAR_F32 && dst_dtype == MAR_F32) cast_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, (float*)dst, n);
-  else if (src_dtype == MAR_BF16 && dst_dtype == MAR_BF16) cast_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+  if (src_dtype == MAR_F32 && dst_dtype == MAR_BF16) mar_launch(cast_kernel<float, bf16>, blocks, 256, 0, st, (const float*)src, (bf16*)dst, n);
+  else if (src_dtype == MAR_BF16 && dst_dtype == MAR_F32) mar_launch(cast_kernel<bf16, float>, blocks, 256, 0, st, (const bf16*)src, (float*)dst, n);
+  else if (src_dtype == MAR_F32 && dst_dtype == MAR_F32) mar_launch(cast_kernel<float, float>, blocks, 256, 0, st, (const float*)src, (float*)dst, n);
+  else if (src_dtype == MAR_BF16 && dst_dtype == MAR_BF16) mar_launch(cast_kernel<bf16, bf16>, blocks, 256, 0, st, (const bf16*)src, (bf16*)dst, n);
   else MAR_UNSUPPORTED("mar_cast: dtype %d -> %d", src_dtype, dst_dtype);
   MAR_LAUNCH_CHECK("cast");
   return MAR_OK;
@@ -564,8 +571,8 @@ int mar_meanpool_fwd(const void* x, void* out, int64_t B, int64_t T, int64_t D, 
   MAR_CHECK_ARG(D % 8 == 0, "mar_meanpool_fwd: D must be a multiple of 8 (got %lld)", (long long)D);
   if (B == 0) return MAR_OK;
   dim3 grid((unsigned)ceil_div(D, 256), (unsigned)B), block(32, 8);
-  if (dtype == MAR_BF16) meanpool_fwd_kernel<bf16><<<grid, block, 0, S(stream)>>>((const bf16*)x, (bf16*)out, T, D);
-  else if (dtype == MAR_F32) meanpool_fwd_kernel<float><<<grid, block, 0, S(stream)>>>((const float*)x, (float*)out, T, D);
+  if (dtype == MAR_BF16) mar_launch(meanpool_fwd_kernel<bf16>, grid, block, 0, S(stream), (const bf16*)x, (bf16*)out, T, D);
+  else if (dtype == MAR_F32) mar_launch(meanpool_fwd_kernel<float>, grid, block, 0, S(stream), (const float*)x, (float*)out, T, D);
   else MAR_UNSUPPORTED("mar_meanpool_fwd: dtype %d", dtype);
   MAR_LAUNCH_CHECK("meanpool_fwd");
   return MAR_OK;
@@ -589,8 +596,8 @@ int mar_rowzero_mask(const void* x, uint8_t* mask, int64_t rows, int64_t D, int 
   MAR_CHECK_ARG(D % 8 == 0, "mar_rowzero_mask: D must be a multiple of 8 (got %lld)", (long long)D);
   if (rows == 0) return MAR_OK;
   unsigned blocks = (unsigned)ceil_div(rows, 8);
-  if (dtype == MAR_BF16) rowzero_kernel<bf16><<<blocks, 256, 0, S(stream)>>>((const bf16*)x, mask, rows, D);
-  else if (dtype == MAR_F32) rowzero_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)x, mask, rows, D);
+  if (dtype == MAR_BF16) mar_launch(rowzero_kernel<bf16>, blocks, 256, 0, S(stream), (const bf16*)x, mask, rows, D);
+  else if (dtype == MAR_F32) mar_launch(rowzero_kernel<float>, blocks, 256, 0, S(stream), (const float*)x, mask, rows, D);
   else MAR_UNSUPPORTED("mar_rowzero_mask: dtype %d", dtype);
   MAR_LAUNCH_CHECK("rowzero_mask");
   return MAR_OK;
@@ -613,7 +620,7 @@ int mar_concat_rows(const void* src, void* dst, int64_t B, int64_t T, int64_t T_
 int mar_cross_entropy_fwd(const float* logits, const int64_t* labels, const float* class_weight, float* loss,
                           float* dlogits, int64_t* preds, int64_t B, int64_t C, void* stream) {
   MAR_CHECK_ARG(logits && labels && loss && B > 0 && C > 0, "mar_cross_entropy_fwd: bad arguments");
-  cross_entropy_kernel<<<1, 256, 0, S(stream)>>>(logits, labels, class_weight, loss, dlogits, preds, B, C);
+  mar_launch(cross_entropy_kernel, 1, 256, 0, S(stream), logits, labels, class_weight, loss, dlogits, preds, B, C);
   MAR_LAUNCH_CHECK("cross_entropy");
   return MAR_OK;
 }
@@ -659,10 +666,10 @@ int mar_adam_step_segments(float* param, const float* grad, float* exp_avg, floa
                 "mar_adam_step_segments: buffers must be 16 B aligned");
   int shift = 0;
   while ((1 << shift) < chunk) shift++;
-  adam_seg_tick_kernel<<<(unsigned)ceil_div(nseg, 128), 128, 0, S(stream)>>>(seg_steps, seg_active,
+  mar_launch(adam_seg_tick_kernel, (unsigned)ceil_div(nseg, 128), 128, 0, S(stream), seg_steps, seg_active,
                                                                             reinterpret_cast<float2*>(seg_coef), nseg, lr, beta1, beta2);
   MAR_LAUNCH_CHECK("adam_seg_tick");
-  adam_seg_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, S(stream)>>>(
+  mar_launch(adam_seg_kernel, (unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, S(stream), 
       param, grad, exp_avg, exp_avg_sq, chunk_seg, reinterpret_cast<const float2*>(seg_coef), n, shift, beta1, beta2, eps,
       reinterpret_cast<bf16*>(bf16_mirror));
   MAR_LAUNCH_CHECK("adam_seg");

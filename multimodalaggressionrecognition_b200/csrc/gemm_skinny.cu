@@ -15,6 +15,7 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 skinny_fwd_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ w, const float* __restrict__ bias,
                   TO* __restrict__ out, int64_t ldo, int M, int N, int K) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -42,6 +43,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 skinny_dgrad_kernel(const T* __restrict__ dz, const T* __restrict__ w, const T* __restrict__ add, T* __restrict__ dx,
                     int64_t lddx, int M, int N, int K) {
+  pdl_entry();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)M * K) return;
   const int m = (int)(idx / K), k = (int)(idx % K);
@@ -55,6 +57,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 skinny_wgrad_kernel(const T* __restrict__ dz, const T* __restrict__ x, int64_t ldx, float* __restrict__ dw, int M, int N,
                     int K, int rows_per_block) {
+  pdl_entry();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
@@ -81,11 +84,11 @@ int skinny_fwd(const void* x, int64_t ldx, const void* w, const float* bias, voi
   mar_set_engine(MAR_ENGINE_SIMT);
   const unsigned blocks = (unsigned)ceil_div(M, 8);
   if (in_dtype == MAR_BF16 && out_dtype == MAR_F32)
-    skinny_fwd_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)x, ldx, (const bf16*)w, bias, (float*)out, ldo, (int)M, (int)N, (int)K);
+    mar_launch(skinny_fwd_kernel<bf16, float>, blocks, 256, 0, st, (const bf16*)x, ldx, (const bf16*)w, bias, (float*)out, ldo, (int)M, (int)N, (int)K);
   else if (in_dtype == MAR_BF16 && out_dtype == MAR_BF16)
-    skinny_fwd_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)x, ldx, (const bf16*)w, bias, (bf16*)out, ldo, (int)M, (int)N, (int)K);
+    mar_launch(skinny_fwd_kernel<bf16, bf16>, blocks, 256, 0, st, (const bf16*)x, ldx, (const bf16*)w, bias, (bf16*)out, ldo, (int)M, (int)N, (int)K);
   else if (in_dtype == MAR_F32 && out_dtype == MAR_F32)
-    skinny_fwd_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)x, ldx, (const float*)w, bias, (float*)out, ldo, (int)M, (int)N, (int)K);
+    mar_launch(skinny_fwd_kernel<float, float>, blocks, 256, 0, st, (const float*)x, ldx, (const float*)w, bias, (float*)out, ldo, (int)M, (int)N, (int)K);
   else MAR_UNSUPPORTED("skinny_fwd: dtype %d -> %d", in_dtype, out_dtype);
   MAR_LAUNCH_CHECK("skinny_fwd");
   return MAR_OK;
@@ -96,9 +99,9 @@ int skinny_dgrad(const void* dz, const void* w, const void* add, void* dx, int64
   mar_set_engine(MAR_ENGINE_SIMT);
   const unsigned blocks = (unsigned)ceil_div(M * K, 256);
   if (dtype == MAR_BF16)
-    skinny_dgrad_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)dz, (const bf16*)w, (const bf16*)add, (bf16*)dx, lddx, (int)M, (int)N, (int)K);
+    mar_launch(skinny_dgrad_kernel<bf16>, blocks, 256, 0, st, (const bf16*)dz, (const bf16*)w, (const bf16*)add, (bf16*)dx, lddx, (int)M, (int)N, (int)K);
   else
-    skinny_dgrad_kernel<float><<<blocks, 256, 0, st>>>((const float*)dz, (const float*)w, (const float*)add, (float*)dx, lddx, (int)M, (int)N, (int)K);
+    mar_launch(skinny_dgrad_kernel<float>, blocks, 256, 0, st, (const float*)dz, (const float*)w, (const float*)add, (float*)dx, lddx, (int)M, (int)N, (int)K);
   MAR_LAUNCH_CHECK("skinny_dgrad");
   return MAR_OK;
 }
@@ -110,9 +113,9 @@ int skinny_wgrad(const void* dz, const void* x, int64_t ldx, float* dw, int64_t 
   const int rows_per_block = 32;
   dim3 grid((unsigned)ceil_div(K, 256), (unsigned)ceil_div(M, rows_per_block));
   if (dtype == MAR_BF16)
-    skinny_wgrad_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, dw, (int)M, (int)N, (int)K, rows_per_block);
+    mar_launch(skinny_wgrad_kernel<bf16>, grid, 256, 0, st, (const bf16*)dz, (const bf16*)x, ldx, dw, (int)M, (int)N, (int)K, rows_per_block);
   else
-    skinny_wgrad_kernel<float><<<grid, 256, 0, st>>>((const float*)dz, (const float*)x, ldx, dw, (int)M, (int)N, (int)K, rows_per_block);
+    mar_launch(skinny_wgrad_kernel<float>, grid, 256, 0, st, (const float*)dz, (const float*)x, ldx, dw, (int)M, (int)N, (int)K, rows_per_block);
   MAR_LAUNCH_CHECK("skinny_wgrad");
   return MAR_OK;
 }

@@ -139,6 +139,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: this grid may have been started while the previous kernel of the stream was still
+  // running (its CTAs take an SM as soon as one is free and run the prologue above); nothing of global memory has been
+  // touched so far.  Let the NEXT kernel do the same, then wait for the previous one to complete and flush.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (EW == 16) {      // 20 warps x 96 registers at launch: the producer group keeps 56, each epilogue thread gets 104
     if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -587,10 +592,12 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, 
   cfg.blockDim = dim3(Epi<EW>::THREADS, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // MAR_PDL bit 1 (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = mar_pdl_enabled(1) ? 2 : 1;
   MAR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, ms, p));
   MAR_LAUNCH_CHECK("gemm_tcgen05");
   return MAR_OK;

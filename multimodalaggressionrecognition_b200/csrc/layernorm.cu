@@ -2,6 +2,7 @@
 // One warp per row; a lane owns NCH chunks of 8 consecutive elements (16 B bf16 / 32 B fp32 loads,
 // a warp covers 256 contiguous elements per chunk round => fully coalesced).  Statistics in fp32.
 // Algorithmic bytes: fwd = rows*D*(read+write)*sizeof(T); bwd = rows*D*(2 reads + 1 write)*sizeof(T).
+#define MAR_PDL_CLASS 2
 #include "common.cuh"
 
 namespace {
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd,
                      const uint8_t* __restrict__ zero_rows, int64_t rows, int D, float eps, const RowMap map) {
+  pdl_entry();
   const int lane = threadIdx.x % 32;
   const int warps_per_block = blockDim.x / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + threadIdx.x / 32;
@@ -133,6 +135,7 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
                      const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int D, const RowMap map,
                      const LnDrop drp) {
+  pdl_entry();
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
   const int warps_per_block = blockDim.x / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + warp;
@@ -260,7 +263,7 @@ int launch_fwd(const void* x, const float* gamma, const float* beta, void* y, fl
   int64_t cap = (int64_t)mar_sm_count() * 8;
   if (blocks > cap) blocks = cap;
 #define LN_FWD(N)                                                                                             \
-  layernorm_fwd_kernel<T, N><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd,   \
+  mar_launch(layernorm_fwd_kernel<T, N>, (unsigned)blocks, 256, 0, st, (const T*)x, gamma, beta, (T*)y, mean, rstd,   \
                                                                zero_rows, rows, (int)D, eps, map)
   switch (nch) {
     case 1: LN_FWD(1); break;
@@ -295,7 +298,7 @@ int launch_bwd(const void* dy, const void* x, const float* mean, const float* rs
       cudaFuncSetAttribute(layernorm_bwd_kernel<T, N, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (N * 256) * 4 * 2); \
       cfg = true;                                                                                                 \
     }                                                                                                             \
-    layernorm_bwd_kernel<T, N, DR><<<(unsigned)blocks, 256, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, \
+    mar_launch(layernorm_bwd_kernel<T, N, DR>, (unsigned)blocks, 256, smem, st, (const T*)dy, (const T*)x, mean, rstd, gamma, \
                                                                         (T*)dx, dgamma, dbeta, rows, (int)D, map, drp); \
   } while (0)
 #define LN_BWD(N) do { if (drop) LN_BWD_T(N, true); else LN_BWD_T(N, false); } while (0)
