@@ -201,6 +201,8 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path; use --impl reference for the CPU arm)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NUMA-local pinned staging for the end-to-end arm (MAR_NUMA_BIND=0: leave the affinity alone, for A/B runs)
+    numa_cpus = training.bind_to_gpu_numa_node(local) if os.environ.get("MAR_NUMA_BIND", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
@@ -339,6 +341,7 @@ def run_ours(args):
                                f"T_a={T_AUDIO}x768, T_v={T_VIDEO}x512, d=768, 8 heads, d_ff=2048, 19.7M params, dropout on",
                    "global_batch": global_batch, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "cuda_graph": bool(use_graph), "setup_steps_before_warmup": setup_steps,
+                   "host_cpus_bound_to_gpu_numa_node": None if numa_cpus is None else len(numa_cpus),
                    "grad_exchange": None if world == 1 else {"wire": step.sync.wire, "buckets": len(step.sync.buckets),
                                                               "engine": "one kernel over NVLink peer memory: bf16 reduce-scatter (peer loads) + all-gather (peer stores) + Adam"
                                                               if step.sync.fused() else "ncclAllReduce + Adam kernel",

@@ -180,6 +180,30 @@ class PeerExchange:
             self._own = None
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Pin this process (one process per GPU) to the CPUs NVML names as local to GPU `device_index` — before pinned host
+    buffers are allocated, so that first touch puts the staging memory of the H2D copies on the GPU's own NUMA node (with 8
+    ranks streaming 230 MB of fp32 features per step each, remote-node staging is what the end-to-end step waits for).
+    Returns the CPU list, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = [i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def _lib_load():
     from . import _lib
     return _lib.load()
