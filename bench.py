@@ -548,7 +548,7 @@ def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
     achieved = flops / (ms / 1e3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     traffic = None                     # DRAM bytes per launch of this kernel from the committed ncu capture of the same command
-    for name in ("r02_gemm_dram_traffic.json", "r01_gemm_dram_traffic.json"):
+    for name in ("r02b_gemm_dram_traffic.json", "r02_gemm_dram_traffic.json", "r01_gemm_dram_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tpath):
             with open(tpath) as f:
