@@ -165,13 +165,19 @@ class PeerExchange:
         """Synchronises the current stream; raises if a wait on a peer inside the kernel ever timed out."""
         call("mar_dp_check", self.ctrl.data_ptr(), _stream())
 
-    def close(self) -> None:
+    def close(self, barrier: bool = False) -> None:
+        """Unmap the peers' blocks and free the own one.  A block must not be freed while a peer still has it mapped
+        (CUDA IPC), so with barrier=True — a COLLECTIVE call, every rank of the group makes it — the ranks meet between the
+        two; without a barrier only the mappings are closed and the own block is left to the context's teardown."""
         for ptr in self._opened:
             try:
                 call("mar_peer_close", ptr)
             except RuntimeError:
                 pass
         self._opened = []
+        if not barrier:
+            return
+        dist.barrier(group=self.group)
         if self._own is not None and self._own.value:
             try:
                 call("mar_peer_free", self._own)
@@ -672,10 +678,15 @@ class TrainStep:
         return self._warm >= 3
 
     def release_graphs(self) -> None:
-        """Drop the captured graphs (and their memory pools).  Call before torch.distributed.destroy_process_group():
-        a communicator must not be torn down while graphs that captured its collectives are still alive."""
+        """Drop the captured graphs (and their memory pools) and the peer-memory blocks of the fused exchange (later steps
+        fall back to the NCCL all-reduce).  COLLECTIVE with more than one rank: every rank calls it, before
+        torch.distributed.destroy_process_group() — a communicator must not be torn down while graphs that captured its
+        collectives are still alive, and a peer block must not be freed while another rank still maps it."""
         if self.flat.flat.is_cuda:
             torch.cuda.synchronize()
+        if self.sync.peer is not None:
+            peer, self.sync.peer = self.sync.peer, None
+            peer.close(barrier=True)
         for state in self._graphs.values():
             for s in state["sets"]:
                 s["graph"] = None
