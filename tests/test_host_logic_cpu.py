@@ -137,3 +137,45 @@ def test_flat_adam_cuda_branch_marks_weights_changed():
     import inspect
     assert "ops.weights_changed()" in inspect.getsource(training.FlatAdam.step)
     assert "ops.weights_changed()" in inspect.getsource(training.TrainStep._graphed)
+
+
+def test_backward_handoff_protocol():
+    """ops.new_handoff / _handoff_bias_target: the dict a linear shares with the neighbour that does part of its backward
+    (DESIGN.md §4.3).  One neighbour at most takes the bias gradient; a bias without a gradient, a foreign size, a missing
+    dict or grad mode off hand nothing over; ops.handoffs(False) switches the mechanism off."""
+    b = nn.Parameter(torch.zeros(6))
+    h = ops.new_handoff()
+    assert h == {}
+    h["bias"] = b
+    tgt = ops._handoff_bias_target(h, 6, torch.device("cpu"))
+    assert tgt is not None and tgt.shape == (6,) and tgt.dtype == torch.float32 and float(tgt.abs().sum()) == 0.0
+    assert h["bias_done"] and h["dbias"] is tgt and h["sunk"] is False
+    assert ops._handoff_bias_target(h, 6, torch.device("cpu")) is None            # already taken by a neighbour
+    assert ops._handoff_bias_target(None, 6, torch.device("cpu")) is None
+    assert ops._handoff_bias_target({"bias": None}, 6, torch.device("cpu")) is None
+    assert ops._handoff_bias_target({"bias": nn.Parameter(torch.zeros(6), requires_grad=False)}, 6, torch.device("cpu")) is None
+    assert ops._handoff_bias_target({"bias": b}, 7, torch.device("cpu")) is None   # not this linear's width
+    # inside a gradient sink the target is the parameter's flat-buffer .grad view — CUDA buffers only: a CPU .grad is not sunk
+    b.grad = torch.zeros(6)
+    with ops.grad_sink():
+        h2 = {"bias": b}
+        assert ops._handoff_bias_target(h2, 6, torch.device("cpu")) is not b.grad and h2["sunk"] is False
+    with ops.handoffs(False):
+        assert ops.new_handoff() is None
+    with torch.no_grad():
+        assert ops.new_handoff() is None
+    assert ops.new_handoff() == {}
+
+
+def test_fused_exchange_is_only_chosen_with_peer_memory():
+    """GradSync.fused(): the fused peer-memory exchange + Adam kernel needs CUDA buffers, the bf16 wire format, ONE bucket
+    and an NCCL group; a CPU / single-process GradSync never has a PeerExchange and TrainStep keeps calling FlatAdam.step
+    (source-level check of the branch: the CUDA path cannot run here)."""
+    import inspect
+    lin = nn.Linear(8, 8)
+    flat = training.FlatParams(list(lin.parameters()))
+    sync = training.GradSync(flat)
+    assert sync.peer is None and not sync.fused() and sync.wire == "fp32"
+    src = inspect.getsource(training.TrainStep._eager)
+    assert "if not fused:" in src and "self.opt.step()" in src
+    assert training.bind_to_gpu_numa_node(0) is None or isinstance(training.bind_to_gpu_numa_node(0), list)
