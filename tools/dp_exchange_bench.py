@@ -9,8 +9,8 @@
   nccl  : mar_cast + ncclAllReduce(bf16) + mar_cast + mar_adam_step_segments (what GradSync does without peer memory)
 
 Timed with CUDA events on the launching stream after a barrier, max over ranks, median over iterations.  Rank 0 prints
-one JSON line; `nvlink_floor_us` = bytes one rank must move per direction ((N-1)/N of the bf16 buffer) / 770 GB/s (the
-measured peer-copy bandwidth of this pool, B200_PROFILING.md), `hbm_floor_us` = local bytes (cast + Adam) / measured
+one JSON line; `nvlink_floor_us` = bytes that cross one rank's links per direction (reduce-scatter + all-gather:
+2·(N-1)/N of the bf16 buffer) / 770 GB/s (the measured peer-copy bandwidth of this pool, B200_PROFILING.md), `hbm_floor_us` = local bytes (cast + Adam) / measured
 copy bandwidth."""
 import argparse
 import json
@@ -82,7 +82,7 @@ if rank == 0:
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     out.update({"n_gpus": world, "params": n, "wire_bytes": 2 * n,
-                "nvlink_floor_us": round(2 * n * (world - 1) / world / 770e9 * 1e6, 1),
+                "nvlink_floor_us": round(2 * (2 * n) * (world - 1) / world / 770e9 * 1e6, 1),   # reduce-scatter + all-gather
                 "hbm_floor_us": round((4 * n + 2 * n + 2 * n + 12 * n + 14 * n) / (hbm * 1e9) * 1e6, 1),
                 "hbm_gbs_used": hbm})
     print(json.dumps(out))
