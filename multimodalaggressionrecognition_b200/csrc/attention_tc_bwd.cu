@@ -86,8 +86,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// DROP: compile-time; the keep-bit logic is not compiled into the p = 0 kernel
-template <int DH, bool DROP>
+// DROP: compile-time; the keep-bit logic is not compiled into the p = 0 kernel.  BIAS: the column sums of dqkv (the
+// in-projection's bias gradient) are taken here — dK / dV in the epilogue, dQ in the read-out warps when it goes straight
+// to dqkv (T <= 128), else in the convert kernel; without BIAS none of that code exists (its registers cost the walk
+// 1-13 % even when the pointer was null)
+// BIAS: 0 none, 1 dK / dV sums (dQ's are taken by the convert kernel: T > 128), 2 dK / dV / dQ sums (T <= 128)
+template <int DH, bool DROP, int BIAS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dq, const BwdParams p) {
@@ -392,7 +396,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
             *reinterpret_cast<uint4*>(o + g * 8) = u;
           }
         }
-        if (p.dbias != nullptr) {
+        if (BIAS) {
           // column sums over this warp's 32 key rows, in place in r: butterfly transpose-reduce, lane l ends with column l
 #pragma unroll
           for (int j = 0; j < 32; j++) r[j] = key < T ? __float_as_uint(__uint_as_float(r[j]) * sc) : 0u;
@@ -431,7 +435,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dqr);      // the MMA issuer may overwrite dQᵀ while we drain the registers
-      if (p.dbias != nullptr && live) {
+      if (BIAS == 2 && live) {          // T <= 128 only: otherwise the convert kernel sums dQ's columns
         if (nq == BQ) {                           // warp-uniform: only the last query tile of a sequence is ragged
 #pragma unroll
           for (int j = 0; j < 32; j++) qsum += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
@@ -476,7 +480,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_const
           if (32 + j < nq) dst[(int64_t)(32 + j) * 3 * d] = __float2bfloat16_rn(__uint_as_float(r1[j]) * scale);
       }
     }
-    if (p.dbias != nullptr && live && c < DH) atomicAdd(p.dbias + h * DH + c, qsum * scale);
+    if (BIAS == 2 && live && c < DH) atomicAdd(p.dbias + h * DH + c, qsum * scale);
     if (warp == 2 + NCOMPUTE && lane == 0) tma_store_wait_all();      // every reduce has landed before the CTA retires
   }
 
@@ -522,22 +526,38 @@ attn_delta_tc_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout
   }
 }
 
-// dqkv[:, :, 0:d] (bf16) = dq_acc (fp32)
-__global__ void __launch_bounds__(256)
-attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, int64_t rows, int d) {
+// dqkv[:, :, 0:d] (bf16) = dq_acc (fp32); dbias != nullptr: dbias[0:d] += column sums (the Q part of the in-projection's
+// bias gradient).  Block = (d/8 column groups) x (RL row lanes): a thread keeps ITS 8 columns over all rows of the block.
+__global__ void __launch_bounds__(1024)
+attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, int64_t rows, int d, int rows_per_block,
+                       float* __restrict__ dbias) {
   pdl_entry();
-  const int c8n = d / 8;
-  const int64_t n = rows * c8n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / c8n;
-    const int c = (int)(i % c8n);
+  extern __shared__ float csum_s[];                 // [RL][d], only with dbias
+  const int c = threadIdx.x, rl = threadIdx.y, RL = blockDim.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float cs[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) cs[j] = 0.f;
+  for (int64_t r = r0 + rl; r < r1; r += RL) {
     float v[8];
     Vec8<float>::load(acc + r * d + c * 8, v);
     Vec8<bf16>::store(dqkv + r * 3 * d + c * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) cs[j] += v[j];
+  }
+  if (dbias == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; j++) csum_s[rl * d + c * 8 + j] = cs[j];
+  __syncthreads();
+  for (int col = rl * blockDim.x + c; col < d; col += RL * blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < RL; k++) t += csum_s[k * d + col];
+    atomicAdd(dbias + col, t);
   }
 }
 
-template <int DH, bool DROP>
+template <int DH, bool DROP, int BIAS>
 int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
                void* dqkv, float* dbias, int64_t B, int64_t T, int64_t H, float p, const uint32_t* dbits, cudaStream_t st) {
   constexpr int NBOX = (DH + 63) / 64;
@@ -548,7 +568,7 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
   static_assert(SMEM <= 232448, "attention backward: shared memory budget");
   static bool cfg = false;
   if (!cfg) {
-    MAR_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MAR_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, DROP, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     cfg = true;
   }
   const int64_t d = H * DH;
@@ -578,12 +598,18 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
   prm.key_mask = key_mask; prm.lse = lse; prm.delta = delta; prm.dq_acc = dq_acc; prm.dqkv = (bf16*)dqkv; prm.dbias = dbias;
   prm.B = (int)B; prm.T = (int)T; prm.H = (int)H; prm.p_drop = p; prm.dbits = dbits; prm.smem_bytes = SMEM;
   const int64_t n_t = ceil_div(T, BT);
-  mar_launch(attn_bwd_tc_kernel<DH, DROP>, (unsigned)(B * H * n_t), NTHREADS, SMEM, st, tm_kv, tm_q, tm_do, tm_dq, prm);
+  mar_launch(attn_bwd_tc_kernel<DH, DROP, BIAS>, (unsigned)(B * H * n_t), NTHREADS, SMEM, st, tm_kv, tm_q, tm_do, tm_dq, prm);
   MAR_LAUNCH_CHECK("attn_bwd_tc");
   if (dq_acc != nullptr) {
-    const int64_t n = B * T * (d / 8);
-    const int64_t blocks = std::min<int64_t>(ceil_div(n, 256), (int64_t)mar_sm_count() * 16);
-    mar_launch(attn_dq_convert_kernel, (unsigned)blocks, 256, 0, st, dq_acc, (bf16*)dqkv, B * T, (int)d);
+    const int c8n = (int)(d / 8);
+    const int RL = std::max(1, std::min(8, 512 / c8n));
+    const int64_t rows = B * T;
+    // ~4 blocks per SM; every block a whole number of row-lane rounds
+    int64_t rpb = ceil_div(rows, (int64_t)mar_sm_count() * 4);
+    rpb = ceil_div(rpb, RL) * RL;
+    const size_t smem = BIAS ? (size_t)RL * d * sizeof(float) : 0;
+    mar_launch(attn_dq_convert_kernel, dim3((unsigned)ceil_div(rows, rpb)), dim3((unsigned)c8n, (unsigned)RL), smem, st, dq_acc,
+               (bf16*)dqkv, rows, (int)d, (int)rpb, BIAS ? dbias : (float*)nullptr);
     MAR_LAUNCH_CHECK("attn_dq_convert");
   }
   return MAR_OK;
@@ -592,8 +618,16 @@ int bwd_launch_t(const void* qkv, const uint8_t* key_mask, const void* out, cons
 template <int DH>
 int bwd_launch(const void* qkv, const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* work,
                void* dqkv, float* dbias, int64_t B, int64_t T, int64_t H, float p, const uint32_t* dbits, cudaStream_t st) {
-  if (p <= 0.f) return bwd_launch_t<DH, false>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
-  return bwd_launch_t<DH, true>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
+  if (dbias != nullptr && T > BT) {
+    if (p <= 0.f) return bwd_launch_t<DH, false, 1>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
+    return bwd_launch_t<DH, true, 1>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
+  }
+  if (dbias != nullptr) {
+    if (p <= 0.f) return bwd_launch_t<DH, false, 2>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
+    return bwd_launch_t<DH, true, 2>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
+  }
+  if (p <= 0.f) return bwd_launch_t<DH, false, 0>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
+  return bwd_launch_t<DH, true, 0>(qkv, key_mask, out, dout, lse, work, dqkv, dbias, B, T, H, p, dbits, st);
 }
 
 }  // namespace
