@@ -497,7 +497,11 @@ def torch_on_b200(dev, W, data, labels, steps=5):
 
 def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
     """Achieved TFLOP/s of the tcgen05 GEMM kernel: CUDA events around every mar_linear_{fwd,dgrad,wgrad} call of
-    one full eager train step (on the launching stream), algorithmic FLOPs = 2·M·N·K per launch."""
+    one full eager train step (on the launching stream), algorithmic FLOPs = 2·M·N·K per launch.  The GPU is kept busy
+    (a spin kernel of ~25 ms) while the host enqueues the step, so that the launches execute back to back as they do
+    inside the captured graph and an event pair brackets the kernel's execution, not the host's launch latency (an
+    eager launch submitted to an idle GPU adds 3-8 us of host time between the two events: a third of a 20 us video-branch
+    GEMM).  MAR_ROOFLINE_QUEUE=0 restores the unqueued measurement."""
     from multimodalaggressionrecognition_b200 import _lib
     recs = []
     orig = _lib.call
@@ -522,6 +526,8 @@ def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
         passes = []
         for it in range(4):                    # first pass warms; three recorded passes, per-launch MEDIAN (an eager
             recs.clear()                       # launch can sit behind a host hiccup that a graph replay never sees)
+            if os.environ.get("MAR_ROOFLINE_QUEUE", "1") != "0":
+                torch.cuda._sleep(48_000_000)                  # ~25 ms at 1.9 GHz: the host runs ahead of the GPU
             ops.rng_advance()
             losses = crit(model(gdata), glabels)
             losses.backward()
@@ -558,6 +564,8 @@ def gemm_roofline(model, crit, gdata, glabels, args, ops, training):
             "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, mean over the step's 49 launches)",
             "launches": len(tc), "gemm_ms_per_step": ms,
             "gemm_flops_per_step": flops,
+            "timing": "CUDA events around every GEMM launch of an eager step queued behind a 25 ms spin kernel (back-to-back execution, "
+                      "median of 3 steps)",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernels timed inside a full step "
                            f"(CUDA events around every GEMM launch of an eager step, per-launch median of 3 steps)"}
 
